@@ -1,0 +1,744 @@
+// api.cu — C ABI of libfans_gpu (include/fans_gpu.h): context lifetime, problem data, fields, operators.
+#include "internal.h"
+#include <cmath>
+#include <algorithm>
+
+static std::string g_create_error;
+
+void fans_set_error(fans_ctx *ctx, int code, const std::string &msg)
+{
+    (void)code;
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+}
+
+extern "C" const char *fans_last_error(const fans_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" int fans_version(void) { return 100; }
+extern "C" int64_t fans_launch_count(const fans_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// element matrices on the host (tiny): include/matmodel.h:104-188, 237-253, 284-304; LargeStrainMechModel.h:209-225
+// ------------------------------------------------------------------------------------------------
+static void basic_B(double x, double y, double z, const double le[3], double b[3][8])
+{
+    const double v0[8] = {-(1 - y) * (1 - z), (1 - y) * (1 - z), -y * (1 - z), y * (1 - z), -(1 - y) * z, (1 - y) * z, -y * z, y * z};
+    const double v1[8] = {-(1 - x) * (1 - z), -x * (1 - z), (1 - x) * (1 - z), x * (1 - z), -(1 - x) * z, -x * z, (1 - x) * z, x * z};
+    const double v2[8] = {-(1 - x) * (1 - y), -x * (1 - y), -(1 - x) * y, -x * y, (1 - x) * (1 - y), x * (1 - y), (1 - x) * y, x * y};
+    for (int a = 0; a < 8; ++a) {
+        b[0][a] = v0[a] / le[0];
+        b[1][a] = v1[a] / le[1];
+        b[2][a] = v2[a] / le[2];
+    }
+}
+
+// full strain-displacement matrix (n_str x 8h, row-major) from the basic gradient
+static void full_B(int nstr, int h, const double b[3][8], std::vector<double> &B)
+{
+    const int nd = 8 * h;
+    B.assign((size_t)nstr * nd, 0.0);
+    const double rs = 7.071067811865476e-01;
+    for (int q = 0; q < 8; ++q) {
+        if (nstr == 3) {
+            for (int j = 0; j < 3; ++j) B[j * nd + q] = b[j][q];
+        } else if (nstr == 6) {
+            B[0 * nd + 3 * q + 0] = b[0][q];
+            B[1 * nd + 3 * q + 1] = b[1][q];
+            B[2 * nd + 3 * q + 2] = b[2][q];
+            B[3 * nd + 3 * q + 0] = rs * b[1][q];
+            B[4 * nd + 3 * q + 0] = rs * b[2][q];
+            B[5 * nd + 3 * q + 1] = rs * b[2][q];
+            B[3 * nd + 3 * q + 1] = rs * b[0][q];
+            B[4 * nd + 3 * q + 2] = rs * b[0][q];
+            B[5 * nd + 3 * q + 2] = rs * b[1][q];
+        } else {
+            for (int i = 0; i < 3; ++i)
+                for (int J = 0; J < 3; ++J) B[(3 * i + J) * nd + 3 * q + i] = b[J][q];
+        }
+    }
+}
+
+struct ElemOps {
+    int ngp, nstr, h, nd;
+    std::vector<std::vector<double>> Bint;  // per GP: n_str x 8h
+    double vw;
+};
+
+static void build_elem(fans_ctx *ctx, ElemOps &E)
+{
+    E.nstr = ctx->nstr;
+    E.h = ctx->h;
+    E.nd = 8 * ctx->h;
+    E.ngp = ctx->ngp;
+    E.vw = ctx->ve / ctx->ngp;
+    const double xp = 0.5 + std::sqrt(3.0) / 6.0, xm = 0.5 - std::sqrt(3.0) / 6.0;
+    const double xi[8][3] = {{xm, xm, xm}, {xp, xm, xm}, {xm, xp, xm}, {xp, xp, xm}, {xm, xm, xp}, {xp, xm, xp}, {xm, xp, xp}, {xp, xp, xp}};
+    ctx->Bgp.assign(9 * 24, 0.0);
+    double bc[3][8];
+    basic_B(0.5, 0.5, 0.5, ctx->le, bc);
+    for (int j = 0; j < 3; ++j)
+        for (int a = 0; a < 8; ++a) ctx->Bgp[(8 * 3 + j) * 8 + a] = bc[j][a];
+    std::vector<double> Bvol;
+    full_B(E.nstr, E.h, bc, Bvol);
+    E.Bint.clear();
+    for (int g = 0; g < E.ngp; ++g) {
+        double b[3][8];
+        if (ctx->fe == FANS_FE_HEX8R) basic_B(0.5, 0.5, 0.5, ctx->le, b);
+        else basic_B(xi[g][0], xi[g][1], xi[g][2], ctx->le, b);
+        for (int j = 0; j < 3; ++j)
+            for (int a = 0; a < 8; ++a) ctx->Bgp[(g * 3 + j) * 8 + a] = b[j][a];
+        std::vector<double> B;
+        full_B(E.nstr, E.h, b, B);
+        if (ctx->fe == FANS_FE_BBAR && E.nstr > 3) {  // matmodel.h:113-140
+            for (int col = 0; col < E.nd; ++col) {
+                const double vf = (B[0 * E.nd + col] + B[1 * E.nd + col] + B[2 * E.nd + col]) / 3.0;
+                const double vb = (Bvol[0 * E.nd + col] + Bvol[1 * E.nd + col] + Bvol[2 * E.nd + col]) / 3.0;
+                for (int r = 0; r < 3; ++r) B[r * E.nd + col] = B[r * E.nd + col] - vf + vb;
+            }
+        }
+        E.Bint.push_back(B);
+    }
+}
+
+// K = sum_gp B^T C B v_e/n_gp   (LinearModel::phase_stiffness, e.g. LinearElastic.h:27-40; matmodel.h:237-246)
+static void elem_stiffness(const ElemOps &E, const double *C, std::vector<double> &K)
+{
+    const int nd = E.nd, ns = E.nstr;
+    K.assign((size_t)nd * nd, 0.0);
+    std::vector<double> CB((size_t)ns * nd);
+    for (int g = 0; g < E.ngp; ++g) {
+        const std::vector<double> &B = E.Bint[g];
+        for (int i = 0; i < ns; ++i)
+            for (int c = 0; c < nd; ++c) {
+                double s = 0.0;
+                for (int j = 0; j < ns; ++j) s += C[i * ns + j] * B[j * nd + c];
+                CB[i * nd + c] = s;
+            }
+        for (int r = 0; r < nd; ++r)
+            for (int c = 0; c < nd; ++c) {
+                double s = 0.0;
+                for (int i = 0; i < ns; ++i) s += B[i * nd + r] * CB[i * nd + c];
+                K[r * nd + c] += s * E.vw;
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+static int create_rest(fans_ctx *ctx);
+static int ensure_field(fans_ctx *ctx, int f)
+{
+    if (f < 0 || f >= FANS_N_FIELDS) {
+        fans_set_error(ctx, FANS_ERR_ARG, "invalid field id");
+        return FANS_ERR_ARG;
+    }
+    if (!ctx->field[f]) {
+        const size_t bytes = sizeof(double) * ctx->h * ctx->nloc;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->field[f], bytes));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->field[f], 0, bytes, ctx->st));
+    }
+    return FANS_OK;
+}
+
+int ensure_dalt(fans_ctx *ctx)
+{
+    if (!ctx->d_alt) {
+        const size_t bytes = sizeof(double) * ctx->h * ctx->nloc;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_alt, bytes));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_alt, 0, bytes, ctx->st));
+    }
+    return FANS_OK;
+}
+
+int ensure_fields(fans_ctx *ctx, std::initializer_list<int> ids)
+{
+    for (int f : ids) FANS_CHECK(ensure_field(ctx, f));
+    return FANS_OK;
+}
+
+extern "C" int fans_create(fans_ctx **out, const fans_config *cfg)
+{
+    if (!out || !cfg) {
+        fans_set_error(nullptr, FANS_ERR_ARG, "null argument");
+        return FANS_ERR_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fans_set_error(nullptr, FANS_ERR_CUDA, "no CUDA device available: libfans_gpu has no CPU fallback");
+        return FANS_ERR_CUDA;
+    }
+    fans_ctx *ctx = new fans_ctx();
+    ctx->cfg = *cfg;
+    ctx->nx = cfg->dims[0];
+    ctx->ny = cfg->dims[1];
+    ctx->nz = cfg->dims[2];
+    ctx->h = cfg->howmany;
+    ctx->nstr = cfg->n_str;
+    ctx->fe = cfg->fe_type;
+    ctx->P = cfg->world_size < 1 ? 1 : cfg->world_size;
+    ctx->rank = cfg->world_rank;
+    ctx->n0 = cfg->local_n0;
+    ctx->x0 = cfg->local_0_start;
+    ctx->n1 = cfg->local_n1;
+    ctx->y1 = cfg->local_1_start;
+    auto fail = [&](int code, const std::string &m) {
+        fans_set_error(nullptr, code, m);
+        delete ctx;
+        return code;
+    };
+    if (!((ctx->h == 1 && ctx->nstr == 3) || (ctx->h == 3 && (ctx->nstr == 6 || ctx->nstr == 9))))
+        return fail(FANS_ERR_ARG, "(howmany, n_str) must be (1,3), (3,6) or (3,9)");
+    if (ctx->fe < FANS_FE_HEX8 || ctx->fe > FANS_FE_BBAR)
+        return fail(FANS_ERR_ARG, "Unknown FE_type. Supported types: HEX8, HEX8R, BBAR");
+    for (int d = 0; d < 3; ++d) {
+        const int n = cfg->dims[d];
+        if (n < 4 || (n & (n - 1)) != 0 || n > 2048)
+            return fail(FANS_ERR_ARG, "grid dimensions must be powers of two in [4, 2048] (got " + std::to_string(n) + ")");
+    }
+    if (ctx->P != 1) return fail(FANS_ERR_ARG, "world_size > 1: use the slab entry points (multi-GPU build)");
+    if (ctx->n0 != ctx->nx || ctx->x0 != 0 || ctx->n1 != ctx->ny || ctx->y1 != 0)
+        return fail(FANS_ERR_ARG, "single-rank context must own the whole grid");
+    ctx->ngp = (ctx->fe == FANS_FE_HEX8R) ? 1 : 8;
+    for (int d = 0; d < 3; ++d) {
+        ctx->L[d] = cfg->L[d];
+        ctx->le[d] = cfg->L[d] / cfg->dims[d];
+    }
+    ctx->ve = ctx->le[0] * ctx->le[1] * ctx->le[2];
+    ctx->nloc = (size_t)ctx->n0 * ctx->ny * ctx->nz;
+    for (int i = 0; i < 9; ++i) ctx->g0[i] = 0.0;
+
+    ctx->device = cfg->device;
+    if (ctx->device < 0) cudaGetDevice(&ctx->device);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(FANS_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return fail(FANS_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 10) return fail(FANS_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100-class; libfans_gpu only carries sm_100a code");
+    if (cfg->stream) {
+        ctx->st = (cudaStream_t)cfg->stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) return fail(FANS_ERR_CUDA, "cudaStreamCreate failed");
+        ctx->own_stream = true;
+    }
+    const int rc = create_rest(ctx);
+    if (rc != FANS_OK) {
+        g_create_error = ctx->err;
+        fans_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return FANS_OK;
+}
+
+static int create_rest(fans_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
+
+    ctx->kzc = ctx->nz / 2 + 1;
+    ctx->kzp = (ctx->kzc + 7) / 8 * 8;
+    ctx->gT = (ctx->h == 1) ? 8 : 4;
+    while ((size_t)ctx->h * ctx->nx * ctx->gT * sizeof(double2) > 200 * 1024 && ctx->gT > 1) ctx->gT /= 2;
+    FANS_CHECK(fft_plan_init(ctx, ctx->planx, ctx->nx, ctx->nx));
+    FANS_CHECK(fft_plan_init(ctx, ctx->plany, ctx->ny, ctx->ny));
+    FANS_CHECK(fft_plan_init(ctx, ctx->planz, ctx->nz / 2, ctx->nz));
+    const size_t spec_elems = (size_t)ctx->h * ctx->n0 * ctx->ny * ctx->kzp;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->spec, sizeof(double2) * spec_elems));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec, 0, sizeof(double2) * spec_elems, ctx->st));
+
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * (1 << 20)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_red, sizeof(double) * S_COUNT));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_red, 0, sizeof(double) * S_COUNT, ctx->st));
+    CUDA_TRY(ctx, cudaMallocHost(&ctx->h_red, sizeof(double) * S_COUNT));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), ctx->st));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_flag, sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->st));
+    FANS_CHECK(ensure_fields(ctx, {FANS_FIELD_U, FANS_FIELD_R, FANS_FIELD_U_PREV}));
+    ElemOps E;
+    build_elem(ctx, E);  // fills ctx->Bgp
+    ctx->const_stamp = sweep_new_stamp();
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    return FANS_OK;
+}
+
+extern "C" void fans_destroy(fans_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    for (int f = 0; f < FANS_N_FIELDS; ++f)
+        if (ctx->field[f]) cudaFree(ctx->field[f]);
+    void *ptrs[] = {ctx->d_alt, ctx->stage_io, ctx->ms, ctx->phidx, ctx->spec, ctx->gamma, ctx->d_phase, ctx->d_K, ctx->phase_lut,
+                    ctx->hist, ctx->hist_t, ctx->pflag, ctx->d_part, ctx->d_red, ctx->d_ticket, ctx->d_flag, ctx->d_C};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->h_red) cudaFreeHost(ctx->h_red);
+    fft_plan_free(ctx->planx);
+    fft_plan_free(ctx->plany);
+    fft_plan_free(ctx->planz);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// problem data
+// ------------------------------------------------------------------------------------------------
+extern "C" int fans_set_microstructure(fans_ctx *ctx, const uint16_t *ms)
+{
+    if (!ctx || !ms) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    uint16_t mx = 0;
+    for (size_t i = 0; i < ctx->nloc; ++i) mx = std::max(mx, ms[i]);
+    ctx->ms_max = mx;
+    if (ctx->materials_ready && (int)mx >= ctx->n_phases) {
+        fans_set_error(ctx, FANS_ERR_MATERIAL, "MaterialManager: Phase " + std::to_string(mx) + " not assigned");
+        return FANS_ERR_MATERIAL;
+    }
+    if (!ctx->phidx) CUDA_TRY(ctx, cudaMalloc(&ctx->phidx, sizeof(uint16_t) * ctx->nloc));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->phidx, ms, sizeof(uint16_t) * ctx->nloc, cudaMemcpyHostToDevice, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->ms_ready = true;
+    return FANS_OK;
+}
+
+extern "C" int fans_set_materials(fans_ctx *ctx, int32_t n_phases, const fans_phase_desc *ph)
+{
+    if (!ctx || !ph || n_phases < 1 || n_phases > 65536) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->ms_ready && (int)ctx->ms_max >= n_phases) {
+        fans_set_error(ctx, FANS_ERR_MATERIAL, "MaterialManager: Phase " + std::to_string(ctx->ms_max) + " not assigned");
+        return FANS_ERR_MATERIAL;
+    }
+    ElemOps E;
+    build_elem(ctx, E);
+    const int nd = E.nd, ns = ctx->nstr;
+    std::vector<PhaseDev> dev(n_phases);
+    std::vector<double> Ktab, Ctab;
+    int nk = 0, nhist = 0;
+    bool all_lin = true, any_flag = false;
+    for (int i = 0; i < n_phases; ++i) {
+        PhaseDev &d = dev[i];
+        memset(&d, 0, sizeof(d));
+        d.model = ph[i].model;
+        d.local_mat = ph[i].local_mat;
+        d.group_n_mat = ph[i].group_n_mat;
+        d.k_index = -1;
+        int npar = 0;
+        bool ok = true;
+        switch (ph[i].model) {
+        case FANS_MAT_LINEAR: {
+            d.k_index = nk++;
+            std::vector<double> K;
+            elem_stiffness(E, ph[i].params, K);
+            Ktab.insert(Ktab.end(), K.begin(), K.end());
+            Ctab.insert(Ctab.end(), ph[i].params, ph[i].params + ns * ns);
+            break;
+        }
+        case FANS_MAT_PSEUDOPLASTIC_LINEAR:
+        case FANS_MAT_PSEUDOPLASTIC_NONLIN:
+            npar = 6, any_flag = true, ok = (ns == 6);
+            break;
+        case FANS_MAT_J2_LINEAR_ISO:
+            npar = 7, nhist = std::max(nhist, 13), ok = (ns == 6);
+            break;
+        case FANS_MAT_J2_NONLIN_ISO:
+            npar = 9, nhist = std::max(nhist, 13), ok = (ns == 6);
+            break;
+        case FANS_MAT_J2NEW_LINEAR_ISO:
+            npar = 4, nhist = std::max(nhist, 7), ok = (ns == 6);
+            break;
+        case FANS_MAT_SVK:
+        case FANS_MAT_NEOHOOKE:
+            npar = 2, ok = (ns == 9);
+            break;
+        default:
+            ok = false;
+        }
+        if (!ok) {
+            fans_set_error(ctx, FANS_ERR_MATERIAL, "material model id " + std::to_string(ph[i].model) + " is not valid for n_str = " + std::to_string(ns));
+            return FANS_ERR_MATERIAL;
+        }
+        for (int k = 0; k < npar; ++k) d.params[k] = ph[i].params[k];
+        if (ph[i].model != FANS_MAT_LINEAR) all_lin = false;
+    }
+    ctx->phases.assign(ph, ph + n_phases);
+    ctx->n_phases = n_phases;
+    ctx->n_k = nk;
+    ctx->all_linear = all_lin;
+    ctx->any_history = nhist > 0;
+    ctx->any_flag = any_flag;
+    ctx->k_in_const = (size_t)nk * nd * nd <= (size_t)6144;
+    if (ctx->d_K) cudaFree(ctx->d_K), ctx->d_K = nullptr;
+    if (ctx->d_C) cudaFree(ctx->d_C), ctx->d_C = nullptr;
+    if (nk > 0) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_K, sizeof(double) * Ktab.size()));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->d_K, Ktab.data(), sizeof(double) * Ktab.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_C, sizeof(double) * Ctab.size()));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->d_C, Ctab.data(), sizeof(double) * Ctab.size(), cudaMemcpyHostToDevice));
+        for (int i = 0; i < n_phases; ++i)
+            if (dev[i].k_index >= 0) dev[i].tangent = ctx->d_C + (size_t)dev[i].k_index * ns * ns;
+    }
+    if (ctx->d_phase) cudaFree(ctx->d_phase), ctx->d_phase = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_phase, sizeof(PhaseDev) * n_phases));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_phase, dev.data(), sizeof(PhaseDev) * n_phases, cudaMemcpyHostToDevice));
+    // internal variables: MaterialManager::initialize_internal_variables (solver.h:139) — for EVERY element
+    if (ctx->hist) cudaFree(ctx->hist), ctx->hist = nullptr;
+    if (ctx->hist_t) cudaFree(ctx->hist_t), ctx->hist_t = nullptr;
+    if (ctx->pflag) cudaFree(ctx->pflag), ctx->pflag = nullptr;
+    ctx->n_hist = nhist;
+    if (nhist > 0) {
+        const size_t bytes = sizeof(double) * nhist * ctx->ngp * ctx->nloc;
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        if (2 * bytes > fr) {
+            fans_set_error(ctx, FANS_ERR_CUDA, "history variables need " + std::to_string(2 * bytes >> 20) + " MiB, only " + std::to_string(fr >> 20) + " MiB free");
+            return FANS_ERR_CUDA;
+        }
+        CUDA_TRY(ctx, cudaMalloc(&ctx->hist, bytes));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->hist_t, bytes));
+        CUDA_TRY(ctx, cudaMemset(ctx->hist, 0, bytes));
+        CUDA_TRY(ctx, cudaMemset(ctx->hist_t, 0, bytes));
+    }
+    if (any_flag) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->pflag, sizeof(int) * ctx->ngp * ctx->nloc));
+        CUDA_TRY(ctx, cudaMemset(ctx->pflag, 0, sizeof(int) * ctx->ngp * ctx->nloc));
+    }
+    ctx->const_stamp = sweep_new_stamp();
+    ctx->materials_ready = true;
+    return FANS_OK;
+}
+
+extern "C" int fans_set_reference_stiffness(fans_ctx *ctx, const double *kapparef)
+{
+    if (!ctx || !kapparef) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    ElemOps E;
+    build_elem(ctx, E);
+    const int nd = E.nd, h = ctx->h;
+    for (int i = 0; i < ctx->nstr * ctx->nstr; ++i) ctx->kapparef[i] = kapparef[i];
+    std::vector<double> K, Ker0((size_t)nd * nd);
+    elem_stiffness(E, kapparef, K);
+    // component-major reordering, matmodel.h:247-251
+    for (int i = 0; i < nd; ++i)
+        for (int j = 0; j < nd; ++j) Ker0[((i % h) * 8 + i / h) * nd + (j % h) * 8 + j / h] = K[i * nd + j];
+    double *dK = nullptr;
+    int *frqx = nullptr, *frqy = nullptr;
+    std::vector<int> fx(ctx->nx), fy(ctx->ny);
+    for (int f = 0; f < ctx->nx; ++f) fx[ctx->planx.pos_host[f]] = f;
+    for (int f = 0; f < ctx->ny; ++f) fy[ctx->plany.pos_host[f]] = f;
+    CUDA_TRY(ctx, cudaMalloc(&dK, sizeof(double) * nd * nd));
+    CUDA_TRY(ctx, cudaMalloc(&frqx, sizeof(int) * ctx->nx));
+    CUDA_TRY(ctx, cudaMalloc(&frqy, sizeof(int) * ctx->ny));
+    CUDA_TRY(ctx, cudaMemcpy(dK, Ker0.data(), sizeof(double) * nd * nd, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(frqx, fx.data(), sizeof(int) * ctx->nx, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(frqy, fy.data(), sizeof(int) * ctx->ny, cudaMemcpyHostToDevice));
+    const int T = ctx->gT, nTiles = (ctx->kzc + T - 1) / T, NG = h * (h + 1) / 2;
+    if (!ctx->gamma) CUDA_TRY(ctx, cudaMalloc(&ctx->gamma, sizeof(double) * (size_t)ctx->n1 * nTiles * NG * ctx->nx * T));
+    int rc = gamma_build(ctx, dK, frqx, frqy);
+    cudaStreamSynchronize(ctx->st);
+    cudaFree(dK);
+    cudaFree(frqx);
+    cudaFree(frqy);
+    if (rc == FANS_OK) ctx->gamma_ready = true;
+    return rc;
+}
+
+extern "C" int fans_set_gradient(fans_ctx *ctx, const double *g0)
+{
+    if (!ctx || !g0) return FANS_ERR_ARG;
+    for (int i = 0; i < ctx->nstr; ++i) ctx->g0[i] = g0[i];
+    return FANS_OK;
+}
+
+extern "C" int fans_get_gradient(fans_ctx *ctx, double *g0)
+{
+    if (!ctx || !g0) return FANS_ERR_ARG;
+    for (int i = 0; i < ctx->nstr; ++i) g0[i] = ctx->g0[i];
+    return FANS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fields
+// ------------------------------------------------------------------------------------------------
+static int ensure_stage(fans_ctx *ctx)
+{
+    if (!ctx->stage_io) CUDA_TRY(ctx, cudaMalloc(&ctx->stage_io, sizeof(double) * ctx->h * ctx->nloc));
+    return FANS_OK;
+}
+
+extern "C" int fans_field_upload(fans_ctx *ctx, int32_t f, const double *host)
+{
+    if (!ctx || !host) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_field(ctx, f));
+    const size_t bytes = sizeof(double) * ctx->h * ctx->nloc;
+    if (ctx->h == 1) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->field[f], host, bytes, cudaMemcpyHostToDevice, ctx->st));
+    } else {
+        FANS_CHECK(ensure_stage(ctx));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_io, host, bytes, cudaMemcpyHostToDevice, ctx->st));
+        FANS_CHECK(vec_aos_to_soa(ctx, ctx->stage_io, ctx->field[f]));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    return FANS_OK;
+}
+
+extern "C" int fans_field_download(fans_ctx *ctx, int32_t f, double *host)
+{
+    if (!ctx || !host) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_field(ctx, f));
+    const size_t bytes = sizeof(double) * ctx->h * ctx->nloc;
+    if (ctx->h == 1) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, ctx->field[f], bytes, cudaMemcpyDeviceToHost, ctx->st));
+    } else {
+        FANS_CHECK(ensure_stage(ctx));
+        FANS_CHECK(vec_soa_to_aos(ctx, ctx->field[f], ctx->stage_io));
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, ctx->stage_io, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    return FANS_OK;
+}
+
+extern "C" int fans_field_zero(fans_ctx *ctx, int32_t f)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_field(ctx, f));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->field[f], 0, sizeof(double) * ctx->h * ctx->nloc, ctx->st));
+    return FANS_OK;
+}
+
+extern "C" int fans_field_copy(fans_ctx *ctx, int32_t dst, int32_t src)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_fields(ctx, {dst, src}));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->field[dst], ctx->field[src], sizeof(double) * ctx->h * ctx->nloc, cudaMemcpyDeviceToDevice, ctx->st));
+    return FANS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// operators
+// ------------------------------------------------------------------------------------------------
+int check_fault(fans_ctx *ctx)
+{
+    int f = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&f, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    if (f == FANS_ERR_NEG_JACOBIAN) {
+        fans_set_error(ctx, f, "Negative Jacobian determinant in CompressibleNeoHookean!");
+        cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->st);
+        return f;
+    }
+    return FANS_OK;
+}
+
+extern "C" int fans_residual(fans_ctx *ctx, int32_t fo, int32_t fu)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_fields(ctx, {fo, fu}));
+    if (fo == fu) {
+        fans_set_error(ctx, FANS_ERR_ARG, "residual: output must differ from input");
+        return FANS_ERR_ARG;
+    }
+    ctx->n_residual_evals++;
+    FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, ctx->field[fu], ctx->field[fo], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    return check_fault(ctx);
+}
+
+extern "C" int fans_apply_linear(fans_ctx *ctx, int32_t fo, int32_t fd)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_fields(ctx, {fo, fd}));
+    if (fo == fd) {
+        fans_set_error(ctx, FANS_ERR_ARG, "apply_linear: output must differ from input");
+        return FANS_ERR_ARG;
+    }
+    if (!ctx->all_linear) {
+        fans_set_error(ctx, FANS_ERR_STATE, "apply_linear requires all phases to be LinearModel (MaterialManager::all_linear)");
+        return FANS_ERR_STATE;
+    }
+    ctx->n_residual_evals++;
+    FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, ctx->field[fd], ctx->field[fo], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    return FANS_OK;
+}
+
+extern "C" int fans_convolution(fans_ctx *ctx, int32_t fi, int32_t fo)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_fields(ctx, {fi, fo}));
+    FANS_CHECK(conv_run(ctx, ctx->field[fi], ctx->field[fo], 1.0, nullptr, nullptr));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    return FANS_OK;
+}
+
+extern "C" int fans_dot(fans_ctx *ctx, int32_t a, int32_t b, double *out)
+{
+    if (!ctx || !out) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_fields(ctx, {a, b}));
+    FANS_CHECK(vec_reduce4(ctx, ctx->field[a], ctx->field[b], ctx->d_red + S_GEN));
+    FANS_CHECK(read_scalars(ctx));
+    *out = ctx->h_red[S_GEN + 2];
+    return FANS_OK;
+}
+
+extern "C" int fans_axpy(fans_ctx *ctx, int32_t y, double alpha, int32_t x)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_fields(ctx, {y, x}));
+    return vec_axpy(ctx, ctx->field[y], alpha, ctx->field[x]);
+}
+
+extern "C" int fans_norm(fans_ctx *ctx, int32_t f, int32_t measure, double *out)
+{
+    if (!ctx || !out) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_field(ctx, f));
+    FANS_CHECK(vec_reduce4(ctx, ctx->field[f], nullptr, ctx->d_red + S_GEN));
+    FANS_CHECK(read_scalars(ctx));
+    if (measure == FANS_MEASURE_L1) *out = ctx->h_red[S_GEN];
+    else if (measure == FANS_MEASURE_L2) *out = std::sqrt(ctx->h_red[S_GEN + 1]);
+    else if (measure == FANS_MEASURE_LINF) *out = ctx->h_red[S_GEN + 3];
+    else {
+        fans_set_error(ctx, FANS_ERR_ARG, "Unknown measure type");
+        return FANS_ERR_ARG;
+    }
+    return FANS_OK;
+}
+
+extern "C" int fans_commit_history(fans_ctx *ctx)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->n_hist > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hist_t, ctx->hist, sizeof(double) * ctx->n_hist * ctx->ngp * ctx->nloc, cudaMemcpyDeviceToDevice, ctx->st));
+    return FANS_OK;
+}
+
+extern "C" int fans_extrapolate_displacement(fans_ctx *ctx)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    FANS_CHECK(ensure_fields(ctx, {FANS_FIELD_U, FANS_FIELD_U_PREV}));
+    return vec_extrapolate(ctx, ctx->field[FANS_FIELD_U], ctx->field[FANS_FIELD_U_PREV]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// postprocess data sources
+// ------------------------------------------------------------------------------------------------
+extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t bytes)
+{
+    if (!ctx || !name || !dst) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const std::string n(name);
+    const size_t N = ctx->nloc;
+    auto need = [&](size_t b) {
+        if (bytes < b) {
+            fans_set_error(ctx, FANS_ERR_ARG, "fans_get_field(" + n + "): buffer too small, need " + std::to_string(b) + " bytes");
+            return false;
+        }
+        return true;
+    };
+    if (n == "strain" || n == "stress") {
+        const int ns = ctx->nstr;
+        if (!need(sizeof(double) * ns * N)) return FANS_ERR_ARG;
+        double *de = nullptr, *ds = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&de, sizeof(double) * ns * N));
+        CUDA_TRY(ctx, cudaMalloc(&ds, sizeof(double) * ns * N));
+        int rc = sweep_run(ctx, SWEEP_STRAINSTRESS, ctx->field[FANS_FIELD_U], nullptr, nullptr, nullptr, nullptr, nullptr, de, ds);
+        std::vector<double> tmp((size_t)ns * N);
+        if (rc == FANS_OK) {
+            cudaMemcpyAsync(tmp.data(), n == "strain" ? de : ds, sizeof(double) * ns * N, cudaMemcpyDeviceToHost, ctx->st);
+            cudaStreamSynchronize(ctx->st);
+            double *o = (double *)dst;
+            for (int i = 0; i < ns; ++i)
+                for (size_t v = 0; v < N; ++v) o[v * ns + i] = tmp[i * N + v];
+        }
+        cudaFree(de);
+        cudaFree(ds);
+        return rc;
+    }
+    if (n == "plastic_flag") {
+        if (!ctx->pflag) {
+            fans_set_error(ctx, FANS_ERR_STATE, "no PseudoPlastic model present");
+            return FANS_ERR_STATE;
+        }
+        if (!need(sizeof(float) * N)) return FANS_ERR_ARG;
+        std::vector<int> tmp((size_t)ctx->ngp * N);
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->pflag, sizeof(int) * ctx->ngp * N, cudaMemcpyDeviceToHost, ctx->st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+        float *o = (float *)dst;
+        for (size_t v = 0; v < N; ++v) {  // PseudoPlastic.h:55-63: mean over the Gauss points, float
+            float s = 0.f;
+            for (int g = 0; g < ctx->ngp; ++g) s += (float)tmp[g * N + v];
+            o[v] = s / (float)ctx->ngp;
+        }
+        return FANS_OK;
+    }
+    if (n == "plastic_strain" || n == "kinematic_hardening_variable" || n == "isotropic_hardening_variable") {
+        if (!ctx->hist_t) {
+            fans_set_error(ctx, FANS_ERR_STATE, "no history-dependent model present");
+            return FANS_ERR_STATE;
+        }
+        const int first = (n == "plastic_strain") ? 0 : (n == "isotropic_hardening_variable" ? 6 : 7);
+        const int cnt = (n == "isotropic_hardening_variable") ? 1 : 6;
+        if (first + cnt > ctx->n_hist) {
+            fans_set_error(ctx, FANS_ERR_STATE, n + " is not a variable of the active model");
+            return FANS_ERR_STATE;
+        }
+        if (!need(sizeof(double) * cnt * N)) return FANS_ERR_ARG;
+        std::vector<double> tmp((size_t)cnt * ctx->ngp * N);
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->hist_t + (size_t)first * ctx->ngp * N, sizeof(double) * cnt * ctx->ngp * N,
+                                      cudaMemcpyDeviceToHost, ctx->st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+        double *o = (double *)dst;  // J2Plasticity.h:245-322: GP mean of the committed (_t) values
+        for (size_t v = 0; v < N; ++v)
+            for (int k = 0; k < cnt; ++k) {
+                double s = 0.0;
+                for (int g = 0; g < ctx->ngp; ++g) s += tmp[((size_t)k * ctx->ngp + g) * N + v];
+                o[v * cnt + k] = s / ctx->ngp;
+            }
+        return FANS_OK;
+    }
+    if (n == "fundamental_solution") {
+        if (!ctx->gamma_ready) {
+            fans_set_error(ctx, FANS_ERR_STATE, "reference stiffness not set");
+            return FANS_ERR_STATE;
+        }
+        const int h = ctx->h, NG = h * (h + 1) / 2, T = ctx->gT, nTiles = (ctx->kzc + T - 1) / T;
+        const size_t cnt = (size_t)ctx->n1 * ctx->nx * ctx->kzc * NG;
+        if (!need(sizeof(double) * cnt)) return FANS_ERR_ARG;
+        const size_t gsz = (size_t)ctx->n1 * nTiles * NG * ctx->nx * T;
+        std::vector<double> tmp(gsz);
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->gamma, sizeof(double) * gsz, cudaMemcpyDeviceToHost, ctx->st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+        double *o = (double *)dst;  // natural order [ky][kx][kz][NG]
+        const size_t NT = (size_t)ctx->nx * T;
+        for (int ky = 0; ky < ctx->ny; ++ky) {
+            const int py = ctx->plany.pos_host[ky];
+            if (py < ctx->y1 || py >= ctx->y1 + ctx->n1) continue;
+            for (int kx = 0; kx < ctx->nx; ++kx) {
+                const int px = ctx->planx.pos_host[kx];
+                for (int kz = 0; kz < ctx->kzc; ++kz) {
+                    const int tile = kz / T, t = kz % T;
+                    for (int k = 0; k < NG; ++k)
+                        o[(((size_t)ky * ctx->nx + kx) * ctx->kzc + kz) * NG + k] =
+                            tmp[((((size_t)(py - ctx->y1)) * nTiles + tile) * NG + k) * NT + (size_t)px * T + t];
+                }
+            }
+        }
+        return FANS_OK;
+    }
+    fans_set_error(ctx, FANS_ERR_ARG, "fans_get_field: unknown field '" + n + "'");
+    return FANS_ERR_ARG;
+}

@@ -1,0 +1,193 @@
+// common.cuh — internal context, error handling and device reduction helpers of libfans_gpu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/fans_gpu.h"
+
+#define FANS_SMS 148  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
+
+#define CUDA_TRY(ctx, expr)                                                                                    \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            fans_set_error((ctx), FANS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+            return FANS_ERR_CUDA;                                                                              \
+        }                                                                                                      \
+    } while (0)
+
+#define FANS_CHECK(call)            \
+    do {                            \
+        int _rc = (call);           \
+        if (_rc != FANS_OK) return _rc; \
+    } while (0)
+
+// ---- mixed-radix power-of-two FFT plan (DIF forward: natural -> digit-reversed; DIT inverse back) ----
+struct FftPlan {
+    int      N      = 0;  // transform length (complex points)
+    int      nst    = 0;  // number of stages
+    int      radix[8];    // radix per stage (8,4,2), forward order
+    int      ntab   = 0;  // length of the twiddle table tw (>= N, multiple of N)
+    double2 *tw     = nullptr;  // device: tw[i] = exp(-2 pi i * i / ntab)
+    int     *pos    = nullptr;  // device: pos[f] = storage row of frequency f after the forward DIF
+    std::vector<int> pos_host;
+};
+
+// stage descriptor passed by value to the kernels
+struct FftStages {
+    int N, logN, nst, twmul;  // twmul = ntab / N
+    int radix[8];
+};
+
+struct PhaseDev {  // device copy of one fans_phase_desc (params trimmed)
+    int    model, local_mat, group_n_mat, k_index;  // k_index: slot of the phase stiffness in the K table (linear) or -1
+    const double *tangent;                          // linear phases: device pointer to C (n_str x n_str, row-major)
+    double params[12];
+};
+
+struct fans_ctx {
+    fans_config cfg;
+    int nx, ny, nz, n0, x0, n1, y1, h, nstr, ngp, fe, P, rank;
+    size_t nloc;  // n0*ny*nz local voxels
+    double L[3], le[3], ve;
+    int device;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    double *field[FANS_N_FIELDS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *d_alt = nullptr;   // ping-pong partner of D (fused d = s + beta d must not update in place)
+    double *stage_io = nullptr; // AoS staging buffer for upload/download
+    uint16_t *ms = nullptr;    // [n0][ny][nz]
+    uint16_t *phidx = nullptr;  // phase id per voxel on the device (== ms values, validated < n_phases), [n0][ny][nz]
+
+    // spectrum + Green operator
+    int kzc = 0, kzp = 0;      // nz/2+1 and padded pitch (complex elements)
+    double2 *spec = nullptr;   // [h][n0][ny][kzp]   (P==1)   /   transposed [h][n1][nx][kzp] (P>1)
+    double *gamma = nullptr;   // tile-major layout, see gamma.cu
+    int gT = 4;                // kz tile width of the fused x pass
+    FftPlan planx, plany, planz;  // planz: half-length complex plan of the r2c/c2r transform (N = nz/2)
+    bool gamma_ready = false;
+
+    // materials
+    int n_phases = 0;
+    std::vector<fans_phase_desc> phases;
+    PhaseDev *d_phase = nullptr;
+    double *d_K = nullptr;      // phase stiffness table [n_k][(8h)^2]
+    double *d_C = nullptr;      // phase tangent table   [n_k][n_str^2]
+    uint16_t ms_max = 0;
+    int n_k = 0;
+    bool k_in_const = false;
+    bool all_linear = false, any_history = false, any_flag = false;
+    int *phase_lut = nullptr;   // device: phase id (ms value) -> dense index, size 65536 only when needed
+    double g0[9];
+    double kapparef[81];
+    std::vector<double> Bgp;    // basic gradient at the GPs: [ngp][3][8] then centre [3][8]
+    bool materials_ready = false, ms_ready = false;
+    uint64_t const_stamp = 0;   // identifies this ctx's content of the __constant__ tables
+
+    // history (dense per element, SoA [var][gp][element])
+    double *hist = nullptr, *hist_t = nullptr;
+    int n_hist = 0;             // doubles per GP
+    int *pflag = nullptr;       // plastic_flag [gp][element]
+
+    // mixed BC
+    bool mixed = false;
+    fans_mixed_bc mbc;
+
+    // reductions / scalars
+    double *d_part = nullptr;   // per-block partial sums
+    double *d_red = nullptr;    // reduced scalars (device)
+    double *h_red = nullptr;    // pinned host mirror
+    unsigned int *d_ticket = nullptr;
+    int neg_jac_flag_host = 0;
+    int *d_flag = nullptr;      // sticky device fault flag (J <= 0)
+
+    std::string err;
+    int64_t launches = 0;
+    int n_residual_evals = 0;
+};
+
+void fans_set_error(fans_ctx *ctx, int code, const std::string &msg);
+
+// ---------------- device helpers ----------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block reduction of NV values (sum for the first NSUM, max for the rest). Result valid in thread 0.
+// scratch must hold NV*32 doubles. All threads of the block must call.
+template <int NV, int NSUM>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *scratch)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = (i < NSUM) ? warp_sum(v[i]) : warp_max(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[i * 32 + wid] = v[i];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < nw) ? scratch[i * 32 + lane] : ((i < NSUM) ? 0.0 : -1.0e300);
+            v[i] = (i < NSUM) ? warp_sum(x) : warp_max(x);
+        }
+    }
+}
+
+// Grid-level deterministic reduce: every block deposits its NV partials, the last block to arrive
+// (ticket counter) folds them in fixed block order and writes out[0..NV). "one grid-level reduce".
+template <int NV, int NSUM>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double *scratch, double *part, unsigned int *ticket,
+                                            double *out)
+{
+    block_reduce<NV, NSUM>(v, scratch);
+    __shared__ bool is_last;
+    const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) part[(size_t)i * nb + bid] = v[i];
+        __threadfence();
+        unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == nb - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = (i < NSUM) ? 0.0 : -1.0e300;
+        // fixed order: thread t sums blocks t, t+blockDim, ... then a block tree
+        for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                double x = __ldcg(&part[(size_t)i * nb + b]);
+                acc[i] = (i < NSUM) ? acc[i] + x : fmax(acc[i], x);
+            }
+        }
+        block_reduce<NV, NSUM>(acc, scratch);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) out[i] = acc[i];
+            *ticket = 0u;
+        }
+    }
+}
+#endif

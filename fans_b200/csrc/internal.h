@@ -1,0 +1,35 @@
+// internal.h — cross-file host entry points of libfans_gpu (not part of the C ABI)
+#pragma once
+#include "common.cuh"
+#include "scalars.h"
+
+// fft.cu
+int  fft_plan_init(fans_ctx *ctx, FftPlan &p, int N, int ntab);
+void fft_plan_free(FftPlan &p);
+int  fft_pass_z_fwd(fans_ctx *ctx, const double *in);
+int  fft_pass_y(fans_ctx *ctx, bool inverse);
+int  fft_pass_x_gamma(fans_ctx *ctx);
+int  fft_pass_z_inv(fans_ctx *ctx, double *out, double scale, const double *dotw, double *red_out);
+
+// gamma.cu
+int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const int *frqy);
+
+// sweep.cu
+enum { SWEEP_LINEAR = 0, SWEEP_RESIDUAL = 1, SWEEP_STRAINSTRESS = 2 };
+uint64_t sweep_new_stamp();
+int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const double *s_in, double *d_new,
+              const double *beta_dev, double *red_out, double *eps_out, double *sig_out);
+
+// vecops.cu
+int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const double *d, const double *s);
+int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev);
+int vec_axpy(fans_ctx *ctx, double *y, double alpha, const double *x);
+int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x);
+int vec_extrapolate(fans_ctx *ctx, double *u, double *up);
+int vec_aos_to_soa(fans_ctx *ctx, const double *aos, double *soa);
+int vec_soa_to_aos(fans_ctx *ctx, const double *soa, double *aos);
+int vec_scalars_after_conv(fans_ctx *ctx);
+
+// solve.cu
+int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out);
+int read_scalars(fans_ctx *ctx);  // d_red -> h_red, synchronises the stream

@@ -1,0 +1,16 @@
+// scalars.h — layout of the device scalar block ctx->d_red (mirrored in pinned host memory ctx->h_red)
+#pragma once
+enum {
+    S_DELTA = 0,     // delta   = <r, s>            (solverCG.h:92)
+    S_DELTA0 = 1,    // delta0                        (solverCG.h:91)
+    S_RS = 2,        // <r, s_new> deposited by the c2r epilogue
+    S_DKD = 3,       // <d, K d>                      (solverCG.h:105)
+    S_BETA = 4,      // fmax(0, (delta - deltamid)/delta0)   (solverCG.h:94)
+    S_L1 = 8,        // sum |r|      -- the next four are written together by k_cg_update / k_reduce4
+    S_L2SQ = 9,      // sum r^2
+    S_DELTAMID = 10, // <r, s>                        (solverCG.h:86)
+    S_LINF = 11,     // max |r|
+    S_GEN = 12,      // 4 generic slots (sum|a|, sum a^2, sum a*b, max|a|)
+    S_STRESS = 16,   // 9 slots: sum of element-averaged stress
+    S_COUNT = 32
+};

@@ -1,0 +1,297 @@
+// solve.cu — drivers: convolution, SolverCG / SolverFP loops, homogenized stress, mixed-BC update.
+//   Solver::convolution            include/solver.h:387-412
+//   Solver::solve / compute_error  include/solver.h:282-300, 414-452
+//   SolverCG::internalSolve / LineSearchSecant   include/solverCG.h:61-160
+//   SolverFP::internalSolve        include/solverFP.h:32-55
+//   Solver::get_homogenized_stress include/solver.h:707-737
+//   MixedBCController::update      include/mixedBCs.h:160-178
+#include "internal.h"
+#include <cmath>
+
+int ensure_fields(fans_ctx *ctx, std::initializer_list<int> ids);
+int ensure_dalt(fans_ctx *ctx);
+int check_fault(fans_ctx *ctx);
+
+int read_scalars(fans_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    return FANS_OK;
+}
+
+static int write_scalar(fans_ctx *ctx, int slot, double v)
+{
+    ctx->h_red[S_COUNT - 1] = v;  // pinned staging slot (never read back from the device)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_red + slot, &ctx->h_red[S_COUNT - 1], sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    return FANS_OK;
+}
+
+// out = scale * Gamma * in ;  optional red_out[0] = <dotw, out>
+int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out)
+{
+    if (!ctx->gamma_ready) {
+        fans_set_error(ctx, FANS_ERR_STATE, "fundamental solution not built: call fans_set_reference_stiffness first");
+        return FANS_ERR_STATE;
+    }
+    FANS_CHECK(fft_pass_z_fwd(ctx, in));
+    FANS_CHECK(fft_pass_y(ctx, false));
+    FANS_CHECK(fft_pass_x_gamma(ctx));
+    FANS_CHECK(fft_pass_y(ctx, true));
+    FANS_CHECK(fft_pass_z_inv(ctx, out, scale, dotw, red_out));
+    return FANS_OK;
+}
+
+// ---- compute_error (solver.h:414-452). Reads the norms the last fused pass left in the scalar block. ----
+struct ErrState {
+    int measure, err_type;
+    double err0;
+    double *hist;
+    int iter;
+};
+
+static double error_from_scalars(fans_ctx *ctx, ErrState &es, int base)
+{
+    double err;
+    if (es.measure == FANS_MEASURE_L1) err = ctx->h_red[base + 0];
+    else if (es.measure == FANS_MEASURE_L2) err = std::sqrt(ctx->h_red[base + 1]);
+    else err = ctx->h_red[base + 3];
+    if (es.hist) es.hist[es.iter] = err;
+    if (es.iter == 0) es.err0 = err;
+    const double err_rel = (es.iter == 0) ? 100.0 : err / es.err0;
+    return es.err_type == FANS_ERR_ABSOLUTE ? err : err_rel;
+}
+
+static int compute_error(fans_ctx *ctx, const double *r, ErrState &es, double *err_out)
+{
+    FANS_CHECK(vec_reduce4(ctx, r, nullptr, ctx->d_red + S_GEN));
+    FANS_CHECK(read_scalars(ctx));
+    *err_out = error_from_scalars(ctx, es, S_GEN);
+    return FANS_OK;
+}
+
+// ---- homogenized stress: one strain/stress sweep + sum (solver.h:707-737) ----
+static int homogenized_stress(fans_ctx *ctx, double *out)
+{
+    FANS_CHECK(ensure_fields(ctx, {FANS_FIELD_U}));
+    FANS_CHECK(sweep_run(ctx, SWEEP_STRAINSTRESS, ctx->field[FANS_FIELD_U], nullptr, nullptr, nullptr, nullptr, ctx->d_red + S_STRESS,
+                         nullptr, nullptr));
+    FANS_CHECK(read_scalars(ctx));
+    const double N = (double)ctx->nx * ctx->ny * ctx->nz;
+    for (int i = 0; i < ctx->nstr; ++i) out[i] = ctx->h_red[S_STRESS + i] / N;
+    return check_fault(ctx);
+}
+
+extern "C" int fans_homogenized_stress(fans_ctx *ctx, double *out)
+{
+    if (!ctx || !out) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return homogenized_stress(ctx, out);
+}
+
+extern "C" int fans_set_mixed_bc(fans_ctx *ctx, const fans_mixed_bc *mbc)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    if (!mbc) {
+        ctx->mixed = false;
+        return FANS_OK;
+    }
+    if (mbc->n_F < 0 || mbc->n_F > ctx->nstr) {
+        fans_set_error(ctx, FANS_ERR_ARG, "mixed BC: invalid number of stress-controlled components");
+        return FANS_ERR_ARG;
+    }
+    ctx->mbc = *mbc;
+    ctx->mixed = true;
+    return FANS_OK;
+}
+
+// g0 += Q_F M (P_target - Q_F^T Pbar)    (mixedBCs.h:160-178)
+extern "C" int fans_update_mixed_bc(fans_ctx *ctx)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    if (!ctx->mixed) return FANS_OK;
+    cudaSetDevice(ctx->device);
+    double Pbar[9];
+    FANS_CHECK(homogenized_stress(ctx, Pbar));
+    const fans_mixed_bc &m = ctx->mbc;
+    if (m.n_F > 0) {
+        double rhs[9], dE[9];
+        for (int i = 0; i < m.n_F; ++i) rhs[i] = m.P_target[i] - Pbar[m.idx_F[i]];
+        for (int i = 0; i < m.n_F; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < m.n_F; ++j) s += m.M[i * m.n_F + j] * rhs[j];
+            dE[i] = s;
+        }
+        for (int i = 0; i < m.n_F; ++i) ctx->g0[m.idx_F[i]] += dE[i];
+    }
+    return FANS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SolverCG::internalSolve, linear fast path (solverCG.h:96-107): everything between two error checks stays on
+// the device; alpha/beta are formed from device scalars. One host poll per iteration (the error).
+// ------------------------------------------------------------------------------------------------
+static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result *res, ErrState &es)
+{
+    FANS_CHECK(ensure_fields(ctx, {FANS_FIELD_U, FANS_FIELD_R, FANS_FIELD_S, FANS_FIELD_D, FANS_FIELD_RNEW}));
+    double *u = ctx->field[FANS_FIELD_U], *r = ctx->field[FANS_FIELD_R], *s = ctx->field[FANS_FIELD_S];
+    double *rnew = ctx->field[FANS_FIELD_RNEW];
+    const size_t fbytes = sizeof(double) * ctx->h * ctx->nloc;
+    const bool linear = ctx->all_linear && !ctx->mixed && !p->force_nonlinear;
+    if (linear) FANS_CHECK(ensure_dalt(ctx));
+    // s = 0, d = 0 (solverCG.h:70-74), alpha_warm = 0.1, delta = 1 (solverCG.h:68,82)
+    CUDA_TRY(ctx, cudaMemsetAsync(s, 0, fbytes, ctx->st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->field[FANS_FIELD_D], 0, fbytes, ctx->st));
+    double alpha_warm = 0.1;
+    ctx->n_residual_evals++;
+    FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, u, r, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    es.iter = 0;
+    double err_rel;
+    FANS_CHECK(compute_error(ctx, r, es, &err_rel));
+    FANS_CHECK(check_fault(ctx));
+    if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
+    FANS_CHECK(write_scalar(ctx, S_DELTA, 1.0));
+    FANS_CHECK(write_scalar(ctx, S_DELTAMID, 0.0));  // <r, s> with s = 0
+    double delta = 1.0;
+    float fft_ms = 0.f;
+    while (es.iter < p->n_it && err_rel > p->tol) {
+        if (linear) {
+            // deltamid already sits in S_DELTAMID (left by k_cg_update, 0 at iter 0)
+            FANS_CHECK(conv_run(ctx, r, s, -1.0, r, ctx->d_red + S_RS));         // s = -Gamma r ; S_RS = <r,s>
+            FANS_CHECK(vec_scalars_after_conv(ctx));                             // delta0, delta, beta
+            double *d_old = ctx->field[FANS_FIELD_D], *d_new = ctx->d_alt;
+            ctx->n_residual_evals++;
+            FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD, nullptr, nullptr));
+            ctx->field[FANS_FIELD_D] = d_new;
+            ctx->d_alt = d_old;
+            FANS_CHECK(vec_cg_update(ctx, r, rnew, u, d_new, s));                // r,u update + norms + deltamid
+            FANS_CHECK(read_scalars(ctx));
+            es.iter++;
+            err_rel = error_from_scalars(ctx, es, S_L1);
+        } else {
+            double *d = ctx->field[FANS_FIELD_D];
+            // deltamid = <r,s> (solverCG.h:86)
+            FANS_CHECK(vec_reduce4(ctx, r, s, ctx->d_red + S_GEN));
+            FANS_CHECK(read_scalars(ctx));
+            const double deltamid = ctx->h_red[S_GEN + 2];
+            FANS_CHECK(conv_run(ctx, r, s, -1.0, r, ctx->d_red + S_RS));
+            FANS_CHECK(read_scalars(ctx));
+            const double delta0 = delta;
+            delta = ctx->h_red[S_RS];
+            const double beta = std::fmax(0.0, (delta - deltamid) / delta0);
+            // d = s + beta d  (solverCG.h:94)
+            FANS_CHECK(vec_xpby(ctx, d, beta, s));
+            // ---- LineSearchSecant (solverCG.h:119-160) ----
+            double err = 10.0;
+            int it = 0;
+            double alpha_prev = 0.0, alpha_curr = alpha_warm;
+            FANS_CHECK(vec_reduce4(ctx, r, d, ctx->d_red + S_GEN));
+            FANS_CHECK(read_scalars(ctx));
+            double rpd = ctx->h_red[S_GEN + 2];
+            FANS_CHECK(vec_axpy(ctx, u, alpha_curr, d));
+            FANS_CHECK(fans_update_mixed_bc(ctx));
+            ctx->n_residual_evals++;
+            FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, u, rnew, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+            FANS_CHECK(vec_reduce4(ctx, rnew, d, ctx->d_red + S_GEN));
+            FANS_CHECK(read_scalars(ctx));
+            double r1pd = ctx->h_red[S_GEN + 2];
+            while (it < p->ls_max_iter && err > p->ls_tol) {
+                const double denom = r1pd - rpd;
+                if (std::fabs(denom) < 1e-14 * (std::fabs(r1pd) + std::fabs(rpd))) break;
+                double alpha_next = alpha_curr - r1pd * (alpha_curr - alpha_prev) / denom;
+                if (alpha_next <= 0.0) alpha_next = 0.5 * (alpha_prev + alpha_curr);
+                err = std::fabs(alpha_next - alpha_curr);
+                FANS_CHECK(vec_axpy(ctx, u, alpha_next - alpha_curr, d));
+                alpha_prev = alpha_curr;
+                rpd = r1pd;
+                alpha_curr = alpha_next;
+                it++;
+                FANS_CHECK(fans_update_mixed_bc(ctx));
+                ctx->n_residual_evals++;
+                FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, u, rnew, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+                FANS_CHECK(vec_reduce4(ctx, rnew, d, ctx->d_red + S_GEN));
+                FANS_CHECK(read_scalars(ctx));
+                r1pd = ctx->h_red[S_GEN + 2];
+            }
+            alpha_warm = (it == p->ls_max_iter && err > p->ls_tol) ? 0.1 : alpha_curr;
+            // v_r = rnew (solverCG.h:157): swap the buffers instead of copying
+            ctx->field[FANS_FIELD_R] = rnew;
+            ctx->field[FANS_FIELD_RNEW] = r;
+            r = ctx->field[FANS_FIELD_R];
+            rnew = ctx->field[FANS_FIELD_RNEW];
+            FANS_CHECK(check_fault(ctx));
+            if (p->verbose) printf("line search iter %i, alpha %f - error %e - ", it, alpha_curr, err);
+            es.iter++;
+            FANS_CHECK(compute_error(ctx, r, es, &err_rel));
+        }
+        if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
+    }
+    res->err_last = err_rel;
+    res->fft_ms = fft_ms;
+    return FANS_OK;
+}
+
+// SolverFP::internalSolve (solverFP.h:32-55): convolution in place on v_r, u -= r
+static int solve_fp(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result *res, ErrState &es)
+{
+    FANS_CHECK(ensure_fields(ctx, {FANS_FIELD_U, FANS_FIELD_R}));
+    double *u = ctx->field[FANS_FIELD_U], *r = ctx->field[FANS_FIELD_R];
+    ctx->n_residual_evals++;
+    FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, u, r, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    es.iter = 0;
+    double err_rel;
+    FANS_CHECK(compute_error(ctx, r, es, &err_rel));
+    FANS_CHECK(check_fault(ctx));
+    if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
+    while (es.iter < p->n_it && err_rel > p->tol) {
+        FANS_CHECK(conv_run(ctx, r, r, 1.0, nullptr, nullptr));
+        FANS_CHECK(vec_axpy(ctx, u, -1.0, r));
+        FANS_CHECK(fans_update_mixed_bc(ctx));
+        ctx->n_residual_evals++;
+        FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, u, r, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        es.iter++;
+        FANS_CHECK(compute_error(ctx, r, es, &err_rel));
+        FANS_CHECK(check_fault(ctx));
+        if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
+    }
+    res->err_last = err_rel;
+    return FANS_OK;
+}
+
+// Solver::solve (solver.h:282-300): err_all = 0, internalSolve, update_internal_variables
+extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result *res, double *err_hist)
+{
+    if (!ctx || !p || !res) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (p->measure < FANS_MEASURE_L1 || p->measure > FANS_MEASURE_LINF) {
+        fans_set_error(ctx, FANS_ERR_ARG, "Unknown measure type");
+        return FANS_ERR_ARG;
+    }
+    if (p->err_type != FANS_ERR_ABSOLUTE && p->err_type != FANS_ERR_RELATIVE) {
+        fans_set_error(ctx, FANS_ERR_ARG, "Unknown error type");
+        return FANS_ERR_ARG;
+    }
+    memset(res, 0, sizeof(*res));
+    if (err_hist)
+        for (int i = 0; i <= p->n_it; ++i) err_hist[i] = 0.0;
+    ErrState es{p->measure, p->err_type, 0.0, err_hist, 0};
+    const int evals0 = ctx->n_residual_evals;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->st));
+    int rc;
+    if (p->method == FANS_METHOD_CG) rc = solve_cg(ctx, p, res, es);
+    else if (p->method == FANS_METHOD_FP) rc = solve_fp(ctx, p, res, es);
+    else {
+        fans_set_error(ctx, FANS_ERR_ARG, "not a valid method");
+        return FANS_ERR_ARG;
+    }
+    if (rc != FANS_OK) return rc;
+    FANS_CHECK(fans_commit_history(ctx));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->st));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res->elapsed_ms = ms;
+    res->iters = es.iter;
+    res->n_residual_evals = ctx->n_residual_evals - evals0;
+    return FANS_OK;
+}

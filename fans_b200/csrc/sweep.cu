@@ -1,0 +1,430 @@
+// sweep.cu — the fused element sweep: gradient stencil -> material law -> B^T sigma -> nodal assembly in ONE pass.
+// Replaces Solver::compute_residual_basic / iterateCubes (include/solver.h:229-385) with Matmodel::element_residual
+// (include/matmodel.h:190-201), the linear-operator lambda of SolverCG (include/solverCG.h:98-103) and
+// Matmodel::getStrainStress (include/matmodel.h:202-225, driven from solver.h:707-737).
+//
+// Decomposition: a CTA owns a (TY x TZ) column of nodes and marches along x.  Per x step it
+//   (a) loads ONE new node plane (with a one-node halo in y,z) into a 2-slot shared-memory ring
+//       [optionally forming d = s + beta*d on the fly and writing the owned part back],
+//   (b) evaluates its (TY+1)x(TZ+1) elements (the low-side halo elements are recomputed by two extra warps so
+//       that no inter-CTA exchange and no atomics are needed) and deposits the 8h element forces in a staging tile,
+//   (c) each node thread gathers its 4 contributions of this element plane, adds the 4 carried in registers from the
+//       previous plane, writes the node force (coalesced along z) and keeps the next carry.
+// The assembly order is fixed => bitwise reproducible results.  Halo voxels are re-read from shared memory only.
+#include "common.cuh"
+#include "materials.cuh"
+
+#define TY 8
+#define TZ 32
+#define NTILE ((TY + 2) * (TZ + 2))       // node tile incl. halo
+#define NELT ((TY + 1) * (TZ + 1))        // elements evaluated per plane
+#define SWEEP_THREADS (TY * TZ + 64)
+
+__constant__ double c_bg[9 * 3 * 8];  // basic gradient dN_a/dx_j at Gauss point g: [(g*3 + j)*8 + a]; g = 8: element centre
+__constant__ double c_K[FANS_CONST_K_DOUBLES];
+
+enum { SW_LINEAR = 0, SW_RESIDUAL = 1, SW_STRAINSTRESS = 2 };
+
+struct SweepParams {
+    int n0, ny, nz;          // local planes, global ny, nz
+    size_t nloc;             // n0*ny*nz = component stride of the SoA fields
+    int xchunk;              // node planes per CTA
+    const double *in;        // u (or d_old when in2 != nullptr)
+    const double *in2;       // s : input becomes in2 + beta*in  (fused CG direction update)
+    double *in_out;          // where the fused input is written (d_new)
+    const double *beta;      // device scalar
+    double *out;             // nodal result
+    const uint16_t *phidx;
+    const PhaseDev *phases;
+    const double *Kglob;     // phase stiffness table in global memory (used when it does not fit __constant__)
+    int n_k, k_const;
+    double g0[9];
+    double vw;               // v_e / n_gp
+    int ngp, bbar;
+    double *hist, *hist_t;
+    int *pflag;
+    int *fault;
+    // reductions
+    double *part;
+    unsigned int *ticket;
+    double *red_out;         // SW_LINEAR: <in_new, out>;  SW_STRAINSTRESS: sum of element stress (n_str values)
+    // strain/stress output (optional)
+    double *eps_out, *sig_out;   // [n_str][nloc] element averages
+};
+
+__device__ __forceinline__ int wrapi(int v, int n)
+{
+    v %= n;
+    return v < 0 ? v + n : v;
+}
+
+template <int H, int NSTR, int MODE, bool KCONST>
+__global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_sweep(const SweepParams p)
+{
+    extern __shared__ double smem[];
+    constexpr int ND = 8 * H;
+    double *ring = smem;                   // [2][H][NTILE]
+    double *stg = smem + 2 * H * NTILE;    // [ND][NELT]
+    __shared__ double scratch[32 * (MODE == SW_STRAINSTRESS ? NSTR : 1)];
+
+    const int tid = threadIdx.x;
+    const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TY;
+    const int xs = blockIdx.z * p.xchunk;
+    const int xe = min(xs + p.xchunk, p.n0);
+    const bool own = tid < TY * TZ;
+    int ely, elz;  // element handled by this thread, tile coordinates in [-1,TY) x [-1,TZ)
+    bool has_el = true;
+    if (own) {
+        ely = tid / TZ;
+        elz = tid % TZ;
+    } else {
+        const int hh = tid - TY * TZ;
+        if (hh < TZ + 1) {
+            ely = -1;
+            elz = hh - 1;
+        } else if (hh < TZ + 1 + TY) {
+            ely = hh - (TZ + 1);
+            elz = -1;
+        } else {
+            ely = 0;
+            elz = 0;
+            has_el = false;
+        }
+    }
+    const int ey = wrapi(y0 + ely, p.ny), ez = wrapi(z0 + elz, p.nz);  // global element y,z (periodic)
+    const bool own_valid = own && (y0 + ely < p.ny) && (z0 + elz < p.nz);
+    const int eidx = (ely + 1) * (TZ + 1) + (elz + 1);
+    const int n00 = (ely + 1) * (TZ + 2) + (elz + 1);  // tile index of the element's node 0
+
+    double beta = 0.0;
+    if (MODE == SW_LINEAR && p.in2) beta = *p.beta;
+
+    double carry[H];
+#pragma unroll
+    for (int c = 0; c < H; ++c) carry[c] = 0.0;
+    double racc[(MODE == SW_STRAINSTRESS) ? NSTR : 1];
+#pragma unroll
+    for (int i = 0; i < ((MODE == SW_STRAINSTRESS) ? NSTR : 1); ++i) racc[i] = 0.0;
+
+    // ---- plane loader: node plane xp (periodic in x) into ring slot `slot`
+    auto load_plane = [&](int xp, int slot, bool owned_plane) {
+        const int xg = wrapi(xp, p.n0);
+        for (int i = tid; i < NTILE; i += SWEEP_THREADS) {
+            const int ry = i / (TZ + 2), rz = i % (TZ + 2);
+            const int y = wrapi(y0 - 1 + ry, p.ny), z = wrapi(z0 - 1 + rz, p.nz);
+            const size_t g = ((size_t)xg * p.ny + y) * p.nz + z;
+#pragma unroll
+            for (int c = 0; c < H; ++c) {
+                double v = p.in[c * p.nloc + g];
+                if (MODE == SW_LINEAR && p.in2) {
+                    v = p.in2[c * p.nloc + g] + beta * v;
+                    if (owned_plane && ry >= 1 && ry <= TY && rz >= 1 && rz <= TZ && (y0 - 1 + ry) < p.ny && (z0 - 1 + rz) < p.nz)
+                        p.in_out[c * p.nloc + g] = v;
+                }
+                ring[(slot * H + c) * NTILE + i] = v;
+            }
+        }
+    };
+
+    int lo = 0;  // ring slot of the lower node plane of the current element plane
+    load_plane(xs - 1, 0, false);
+    for (int x = xs - 1; x < xe; ++x) {  // element plane x uses node planes x (slot lo) and x+1 (slot lo^1)
+        load_plane(x + 1, lo ^ 1, (x + 1) < xe);
+        __syncthreads();
+        double u0[H];
+#pragma unroll
+        for (int c = 0; c < H; ++c) u0[c] = 0.0;
+        // strain/stress sweeps only evaluate owned elements (no assembly => no halo elements, no plane xs-1)
+        const bool do_el = has_el && (MODE != SW_STRAINSTRESS || (own_valid && x >= xs));
+        if (do_el) {
+            // gather the 8 nodes: local node i = bx + 2 by + 4 bz  (include/solver.h:333-340)
+            double ue[ND];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int slot = (i & 1) ? (lo ^ 1) : lo;
+                const int ti = n00 + ((i >> 1) & 1) * (TZ + 2) + ((i >> 2) & 1);
+#pragma unroll
+                for (int c = 0; c < H; ++c) ue[H * i + c] = ring[(slot * H + c) * NTILE + ti];
+            }
+#pragma unroll
+            for (int c = 0; c < H; ++c) u0[c] = ue[c];
+            const int xg = wrapi(x, p.n0);
+            const size_t e = ((size_t)xg * p.ny + ey) * p.nz + ez;
+            const int ph = p.phidx[e];
+            if (MODE == SW_LINEAR) {
+                // ue <- ue - u(node 0)   (solver.h:250-254);  res_e = K_phase ue   (solverCG.h:98-103)
+#pragma unroll
+                for (int i = 1; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < H; ++c) ue[H * i + c] -= u0[c];
+                const int kidx = p.phases[ph].k_index;
+                if (KCONST) {
+                    for (int q = 0; q < p.n_k; ++q) {
+                        if (kidx == q) {
+                            const double *Kq = c_K + q * (ND * ND);
+#pragma unroll
+                            for (int i = 0; i < ND; ++i) {
+                                double a = 0.0;
+#pragma unroll
+                                for (int j = H; j < ND; ++j) a = fma(Kq[i * ND + j], ue[j], a);
+                                stg[i * NELT + eidx] = a;
+                            }
+                        }
+                    }
+                } else {
+                    const double *Kq = p.Kglob + (size_t)kidx * (ND * ND);
+#pragma unroll 1
+                    for (int i = 0; i < ND; ++i) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int j = H; j < ND; ++j) a = fma(__ldg(&Kq[i * ND + j]), ue[j], a);
+                        stg[i * NELT + eidx] = a;
+                    }
+                }
+            } else {
+                if (MODE == SW_RESIDUAL) {
+#pragma unroll
+                    for (int i = 1; i < 8; ++i)
+#pragma unroll
+                        for (int c = 0; c < H; ++c) ue[H * i + c] -= u0[c];
+#pragma unroll
+                    for (int c = 0; c < H; ++c) ue[c] = 0.0;
+                }  // SW_STRAINSTRESS keeps the absolute ue (solver.h:507,723)
+                const PhaseDev &pd = p.phases[ph];
+                double res[ND];
+#pragma unroll
+                for (int i = 0; i < ND; ++i) res[i] = 0.0;
+                double esum[NSTR], ssum[NSTR];
+#pragma unroll
+                for (int i = 0; i < NSTR; ++i) esum[i] = 0.0, ssum[i] = 0.0;
+                // B-bar: centre value of the "volumetric" row (include/matmodel.h:113-140)
+                double mc = 0.0, Qsum = 0.0;
+                if (p.bbar && NSTR > 3) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        if (NSTR == 6) {
+                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], ue[H * a + 0], t);
+                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], ue[H * a + (H > 1 ? 1 : 0)], t);
+                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], ue[H * a + (H > 2 ? 2 : 0)], t);
+                        } else {
+                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], ue[H * a], t);
+                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], ue[H * a], t);
+                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], ue[H * a], t);
+                        }
+                    }
+                    mc = t * (1.0 / 3.0);
+                }
+                const bool wr = own_valid && x >= xs;  // only the owner of an element updates its history / flags
+#pragma unroll 1
+                for (int g = 0; g < p.ngp; ++g) {
+                    const double *bg = c_bg + g * 24;
+                    double Hm[H][3];
+#pragma unroll
+                    for (int c = 0; c < H; ++c)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int a = 0; a < 8; ++a) s = fma(bg[j * 8 + a], ue[H * a + c], s);
+                            Hm[c][j] = s;
+                        }
+                    double eps[NSTR], sig[NSTR];
+                    strain_from_grad<H, NSTR>(Hm, eps);
+                    if (p.bbar && NSTR > 3) {
+                        const double m = (eps[0] + eps[1] + eps[2]) * (1.0 / 3.0);
+                        eps[0] += mc - m;
+                        eps[1] += mc - m;
+                        eps[2] += mc - m;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NSTR; ++i) eps[i] += p.g0[i];
+                    material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.ngp, g, e, wr, p.fault);
+                    if (MODE == SW_STRAINSTRESS) {
+#pragma unroll
+                        for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
+                    } else {
+                        if (p.bbar && NSTR > 3) {
+                            const double qv = (sig[0] + sig[1] + sig[2]) * (1.0 / 3.0);
+                            sig[0] -= qv;
+                            sig[1] -= qv;
+                            sig[2] -= qv;
+                            Qsum += qv;
+                        }
+                        double Tm[H][3];
+                        stress_tensor<H, NSTR>(sig, Tm);
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+#pragma unroll
+                            for (int c = 0; c < H; ++c) {
+                                double s = res[H * a + c];
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) s = fma(bg[j * 8 + a], Tm[c][j], s);
+                                res[H * a + c] = s;
+                            }
+                    }
+                }
+                if (MODE == SW_RESIDUAL) {
+                    if (p.bbar && NSTR > 3) {
+                        double sq[NSTR];
+#pragma unroll
+                        for (int i = 0; i < NSTR; ++i) sq[i] = (i < 3) ? Qsum : 0.0;
+                        double Tm[H][3];
+                        stress_tensor<H, NSTR>(sq, Tm);
+                        const double *bc = c_bg + 8 * 24;
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+#pragma unroll
+                            for (int c = 0; c < H; ++c) {
+                                double s = res[H * a + c];
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) s = fma(bc[j * 8 + a], Tm[c][j], s);
+                                res[H * a + c] = s;
+                            }
+                    }
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) stg[i * NELT + eidx] = res[i] * p.vw;
+                } else {  // SW_STRAINSTRESS: element averages, only for owned elements
+                    if (wr) {
+                        const double inv = 1.0 / (double)p.ngp;
+#pragma unroll
+                        for (int i = 0; i < NSTR; ++i) {
+                            const double ev = esum[i] * inv, sv = ssum[i] * inv;
+                            if (p.eps_out) p.eps_out[i * p.nloc + e] = ev;
+                            if (p.sig_out) p.sig_out[i * p.nloc + e] = sv;
+                            racc[i] += sv;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (MODE != SW_STRAINSTRESS) {
+            if (own) {
+                // assemble: node (ly,lz) is local node (bx, by, bz) of element (ly-by, lz-bz) of plane x (bx=0) / x-1 (bx=1)
+                double outv[H], nxt[H];
+#pragma unroll
+                for (int c = 0; c < H; ++c) outv[c] = carry[c], nxt[c] = 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int by = b & 1, bz = b >> 1;
+                    const int ee = eidx - by * (TZ + 1) - bz;
+                    const int i0 = 2 * by + 4 * bz;
+#pragma unroll
+                    for (int c = 0; c < H; ++c) {
+                        outv[c] += stg[(H * i0 + c) * NELT + ee];
+                        nxt[c] += stg[(H * (i0 + 1) + c) * NELT + ee];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < H; ++c) carry[c] = nxt[c];
+                if (own_valid && x >= xs) {
+                    const size_t g = ((size_t)x * p.ny + ey) * p.nz + ez;
+#pragma unroll
+                    for (int c = 0; c < H; ++c) {
+                        p.out[c * p.nloc + g] = outv[c];
+                        if (MODE == SW_LINEAR) racc[0] += outv[c] * u0[c];
+                    }
+                }
+            }
+        }
+        lo ^= 1;
+    }
+    if (p.red_out) {
+        if constexpr (MODE == SW_STRAINSTRESS) grid_reduce<NSTR, NSTR>(racc, scratch, p.part, p.ticket, p.red_out);
+        else if constexpr (MODE == SW_LINEAR) grid_reduce<1, 1>(racc, scratch, p.part, p.ticket, p.red_out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static uint64_t g_const_stamp = 0;  // which ctx content currently sits in c_bg / c_K
+static uint64_t g_stamp_counter = 0;
+
+uint64_t sweep_new_stamp() { return ++g_stamp_counter; }
+
+static int upload_constants(fans_ctx *ctx)
+{
+    if (g_const_stamp == ctx->const_stamp) return FANS_OK;
+    CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_bg, ctx->Bgp.data(), sizeof(double) * 9 * 24, 0, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->k_in_const && ctx->n_k > 0)
+        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_K, ctx->d_K, sizeof(double) * ctx->n_k * 64 * ctx->h * ctx->h, 0,
+                                              cudaMemcpyDeviceToDevice, ctx->st));
+    g_const_stamp = ctx->const_stamp;
+    return FANS_OK;
+}
+
+template <int H, int NSTR, int MODE>
+static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t smem)
+{
+    if (MODE == SW_LINEAR && ctx->k_in_const) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sweep<H, NSTR, MODE, true><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sweep<H, NSTR, MODE, false><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+// mode: SW_*; in/out device SoA fields. s_in/d_new/beta only for the fused CG direction update.
+int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const double *s_in, double *d_new,
+              const double *beta_dev, double *red_out, double *eps_out, double *sig_out)
+{
+    if (!ctx->ms_ready || !ctx->materials_ready) {
+        fans_set_error(ctx, FANS_ERR_STATE, "microstructure and materials must be set before an element sweep");
+        return FANS_ERR_STATE;
+    }
+    FANS_CHECK(upload_constants(ctx));
+    SweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.n0 = ctx->n0;
+    p.ny = ctx->ny;
+    p.nz = ctx->nz;
+    p.nloc = ctx->nloc;
+    p.in = in;
+    p.in2 = s_in;
+    p.in_out = d_new;
+    p.beta = beta_dev;
+    p.out = out;
+    p.phidx = ctx->phidx;
+    p.phases = ctx->d_phase;
+    p.Kglob = ctx->d_K;
+    p.n_k = ctx->n_k;
+    p.k_const = ctx->k_in_const;
+    for (int i = 0; i < 9; ++i) p.g0[i] = ctx->g0[i];
+    p.vw = ctx->ve / ctx->ngp;
+    p.ngp = ctx->ngp;
+    p.bbar = (ctx->fe == FANS_FE_BBAR);
+    p.hist = ctx->hist;
+    p.hist_t = ctx->hist_t;
+    p.pflag = ctx->pflag;
+    p.fault = ctx->d_flag;
+    p.part = ctx->d_part;
+    p.ticket = ctx->d_ticket;
+    p.red_out = red_out;
+    p.eps_out = eps_out;
+    p.sig_out = sig_out;
+    // x chunking: enough CTAs to fill 148 SMs a few times over, at most ~6% redundant plane loads
+    const int gy = (ctx->ny + TY - 1) / TY, gz = (ctx->nz + TZ - 1) / TZ;
+    int xchunk = ctx->n0;
+    while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < 4L * FANS_SMS) xchunk = (xchunk + 1) / 2;
+    p.xchunk = xchunk;
+    dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
+    const size_t smem = sizeof(double) * (2 * ctx->h * NTILE + 8 * ctx->h * NELT);
+#define SW_DISPATCH(H_, N_)                                                                  \
+    do {                                                                                     \
+        if (mode == SW_LINEAR) return launch_sweep<H_, N_, SW_LINEAR>(ctx, p, grid, smem);   \
+        if (mode == SW_RESIDUAL) return launch_sweep<H_, N_, SW_RESIDUAL>(ctx, p, grid, smem); \
+        return launch_sweep<H_, N_, SW_STRAINSTRESS>(ctx, p, grid, smem);                    \
+    } while (0)
+    if (ctx->h == 1 && ctx->nstr == 3) SW_DISPATCH(1, 3);
+    if (ctx->h == 3 && ctx->nstr == 6) SW_DISPATCH(3, 6);
+    if (ctx->h == 3 && ctx->nstr == 9) SW_DISPATCH(3, 9);
+#undef SW_DISPATCH
+    fans_set_error(ctx, FANS_ERR_ARG, "unsupported (howmany, n_str) combination");
+    return FANS_ERR_ARG;
+}

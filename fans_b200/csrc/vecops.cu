@@ -1,0 +1,199 @@
+// vecops.cu — CG / fixed-point vector updates, dot products and error norms as fused HBM passes.
+// Replaces the Eigen array expressions of SolverCG::internalSolve / LineSearchSecant (include/solverCG.h:86-107,
+// 119-160), SolverFP::internalSolve (include/solverFP.h:46), Solver::compute_error (include/solver.h:414-431) and
+// Solver::extrapolateDisplacement (include/solver.h:302-311).  All fields are flat SoA arrays of h*nloc doubles.
+#include "common.cuh"
+#include "scalars.h"
+
+#define VEC_THREADS 256
+
+static inline unsigned vec_grid(size_t n2)
+{
+    size_t nb = (n2 + VEC_THREADS - 1) / VEC_THREADS;
+    const size_t cap = (size_t)FANS_SMS * 16;  // 16 resident CTAs of 256 threads per SM would exceed the SM; 8 fit, x2 waves
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    return (unsigned)nb;
+}
+
+// r -= alpha*Kd ; u -= alpha*d ; norms of the new r ; deltamid = <r_new, s>      (solverCG.h:105-107, :86, solver.h:419-425)
+// alpha = delta / <d,Kd> is formed from the device scalars (no host round trip).
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_update(double2 *__restrict__ r, const double2 *__restrict__ kd,
+                                                            double2 *__restrict__ u, const double2 *__restrict__ d,
+                                                            const double2 *__restrict__ s, size_t n2, double *S,
+                                                            double *part, unsigned int *ticket)
+{
+    __shared__ double scratch[4 * 32];
+    const double alpha = S[S_DELTA] / S[S_DKD];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // L1, L2^2, <r,s>, Linf
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 rv = r[i];
+        const double2 kv = kd[i], dv = d[i], sv = s[i];
+        double2 uv = u[i];
+        rv.x -= alpha * kv.x;
+        rv.y -= alpha * kv.y;
+        uv.x -= alpha * dv.x;
+        uv.y -= alpha * dv.y;
+        r[i] = rv;
+        u[i] = uv;
+        acc[0] += fabs(rv.x) + fabs(rv.y);
+        acc[1] += rv.x * rv.x + rv.y * rv.y;
+        acc[2] += rv.x * sv.x + rv.y * sv.y;
+        acc[3] = fmax(acc[3], fmax(fabs(rv.x), fabs(rv.y)));
+    }
+    grid_reduce<4, 3>(acc, scratch, part, ticket, S + S_L1);  // -> S_L1, S_L2SQ, S_DELTAMID, S_LINF
+}
+
+// generic fused reductions: out[0]=sum|a|, out[1]=sum a^2, out[2]=sum a*b (b may be null), out[3]=max|a|
+__global__ void __launch_bounds__(VEC_THREADS) k_reduce4(const double2 *__restrict__ a, const double2 *__restrict__ b, size_t n2,
+                                                          double *part, unsigned int *ticket, double *out)
+{
+    __shared__ double scratch[4 * 32];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 av = a[i];
+        acc[0] += fabs(av.x) + fabs(av.y);
+        acc[1] += av.x * av.x + av.y * av.y;
+        if (b) {
+            const double2 bv = b[i];
+            acc[2] += av.x * bv.x + av.y * bv.y;
+        }
+        acc[3] = fmax(acc[3], fmax(fabs(av.x), fabs(av.y)));
+    }
+    grid_reduce<4, 3>(acc, scratch, part, ticket, out);
+}
+
+__global__ void __launch_bounds__(VEC_THREADS) k_axpy(double2 *__restrict__ y, double alpha, const double2 *__restrict__ x, size_t n2)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 yv = y[i];
+        const double2 xv = x[i];
+        yv.x += alpha * xv.x;
+        yv.y += alpha * xv.y;
+        y[i] = yv;
+    }
+}
+
+// y = x + beta*y     (d = s + beta d, solverCG.h:94)
+__global__ void __launch_bounds__(VEC_THREADS) k_xpby(double2 *__restrict__ y, double beta, const double2 *__restrict__ x, size_t n2)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 yv = y[i];
+        const double2 xv = x[i];
+        yv.x = xv.x + beta * yv.x;
+        yv.y = xv.y + beta * yv.y;
+        y[i] = yv;
+    }
+}
+
+// delta = u - u_prev; u_prev = u; u += delta          (solver.h:302-311)
+__global__ void __launch_bounds__(VEC_THREADS) k_extrapolate(double2 *__restrict__ u, double2 *__restrict__ up, size_t n2)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 uv = u[i], pv = up[i];
+        up[i] = uv;
+        u[i] = make_double2(uv.x + (uv.x - pv.x), uv.y + (uv.y - pv.y));
+    }
+}
+
+// interleaved host order [voxel][h]  <->  component planes [h][voxel]
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, size_t nloc, int h)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nloc * h; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = i / h;
+        const int c = (int)(i % h);
+        soa[c * nloc + v] = aos[i];
+    }
+}
+__global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict__ aos, size_t nloc, int h)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nloc * h; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = i / h;
+        const int c = (int)(i % h);
+        aos[i] = soa[c * nloc + v];
+    }
+}
+
+// scalar bookkeeping of one CG iteration after the convolution (solverCG.h:91-94):
+//   delta0 = delta ; delta = <r,s> ; beta = fmax(0, (delta - deltamid)/delta0)
+__global__ void k_scalars_after_conv(double *S)
+{
+    const double delta0 = S[S_DELTA];
+    const double delta = S[S_RS];
+    S[S_DELTA0] = delta0;
+    S[S_DELTA] = delta;
+    S[S_BETA] = fmax(0.0, (delta - S[S_DELTAMID]) / delta0);
+}
+
+// ------------------------------------------------------------------------------------------------
+int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const double *d, const double *s)
+{
+    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    k_cg_update<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)r, (const double2 *)kd, (double2 *)u, (const double2 *)d,
+                                                          (const double2 *)s, n2, ctx->d_red, ctx->d_part, ctx->d_ticket);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev)
+{
+    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    k_reduce4<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((const double2 *)a, (const double2 *)b, n2, ctx->d_part, ctx->d_ticket, out_dev);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_axpy(fans_ctx *ctx, double *y, double alpha, const double *x)
+{
+    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    k_axpy<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, alpha, (const double2 *)x, n2);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x)
+{
+    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    k_xpby<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, beta, (const double2 *)x, n2);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_extrapolate(fans_ctx *ctx, double *u, double *up)
+{
+    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    k_extrapolate<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)u, (double2 *)up, n2);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_aos_to_soa(fans_ctx *ctx, const double *aos, double *soa)
+{
+    const size_t n = (size_t)ctx->h * ctx->nloc;
+    k_aos_to_soa<<<vec_grid(n), VEC_THREADS, 0, ctx->st>>>(aos, soa, ctx->nloc, ctx->h);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_soa_to_aos(fans_ctx *ctx, const double *soa, double *aos)
+{
+    const size_t n = (size_t)ctx->h * ctx->nloc;
+    k_soa_to_aos<<<vec_grid(n), VEC_THREADS, 0, ctx->st>>>(soa, aos, ctx->nloc, ctx->h);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_scalars_after_conv(fans_ctx *ctx)
+{
+    k_scalars_after_conv<<<1, 1, 0, ctx->st>>>(ctx->d_red);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}

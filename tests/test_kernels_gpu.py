@@ -1,0 +1,137 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (include/fans_gpu.h) against the oracle.
+Tolerances: per-voxel fields 1e-8 relative (max norm), scalars 1e-9 relative — BASELINE.json north_star."""
+import numpy as np
+import pytest
+
+import fans_oracle as fo
+import util
+from util import THERMAL, ELASTIC, EP, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-8
+SCALAR_TOL = 1e-9
+
+
+def make(problem, materials, fe, shape=(16, 32, 64), strain_type="small", seed=1):
+    ms = util.two_phase_ms(0, seed, shape)
+    sol = fo.OracleSolver(ms, [1.0, 2.0, 1.5], problem, materials, fe, "cg", strain_type, EP, 100)
+    return sol, util.ctx_from_oracle(sol)
+
+
+@pytest.mark.parametrize("problem,materials,fe", [("thermal", THERMAL, "HEX8"), ("thermal", THERMAL, "HEX8R"),
+                                                   ("mechanical", ELASTIC, "HEX8"), ("mechanical", ELASTIC, "HEX8R"),
+                                                   ("mechanical", ELASTIC, "BBAR")])
+def test_fundamental_solution(problem, materials, fe):
+    sol, ctx = make(problem, materials, fe)
+    g = ctx.get_field("fundamental_solution")  # [ky][kx][kz][NG]
+    G = sol.gamma_hat  # [kx][ky][kz][h][h]
+    h = sol.h
+    k = 0
+    for i in range(h):
+        for j in range(i, h):
+            ref = np.transpose(G[..., i, j], (1, 0, 2))
+            assert rel_err(g[..., k], ref) < 1e-9, (i, j)
+            k += 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 64), (64, 16, 8), (8, 8, 128), (32, 32, 32)])
+@pytest.mark.parametrize("problem,materials", [("thermal", THERMAL), ("mechanical", ELASTIC)])
+def test_convolution(problem, materials, shape):
+    sol, ctx = make(problem, materials, "HEX8", shape)
+    rng = np.random.default_rng(3)
+    r = rng.standard_normal(ctx.field_shape)
+    ctx.upload("r", r)
+    ctx.convolution("r", "s")
+    got = ctx.download("s")
+    ref = sol.convolution(r)
+    assert rel_err(got, ref) < FIELD_TOL
+    # in place (SolverFP uses the same buffer, include/solverFP.h:29)
+    ctx.convolution("r", "r")
+    assert rel_err(ctx.download("r"), ref) < FIELD_TOL
+    ctx.close()
+
+
+def test_upload_download_roundtrip():
+    sol, ctx = make("mechanical", ELASTIC, "HEX8", (8, 16, 32))
+    a = np.random.default_rng(0).standard_normal(ctx.field_shape)
+    ctx.upload("u", a)
+    assert np.array_equal(ctx.download("u"), a)
+    ctx.copy("d", "u")
+    assert np.array_equal(ctx.download("d"), a)
+    ctx.zero("d")
+    assert not ctx.download("d").any()
+    ctx.close()
+
+
+def test_vector_ops():
+    sol, ctx = make("mechanical", ELASTIC, "HEX8", (8, 16, 32))
+    rng = np.random.default_rng(5)
+    a, b = rng.standard_normal(ctx.field_shape), rng.standard_normal(ctx.field_shape)
+    ctx.upload("r", a)
+    ctx.upload("s", b)
+    assert abs(ctx.dot("r", "s") - (a * b).sum()) <= 1e-12 * np.abs(a * b).sum()
+    assert abs(ctx.norm("r", "L1") - np.abs(a).sum()) <= 1e-12 * np.abs(a).sum()
+    assert abs(ctx.norm("r", "L2") - np.sqrt((a * a).sum())) <= 1e-12 * np.sqrt((a * a).sum())
+    assert ctx.norm("r", "Linfinity") == np.abs(a).max()
+    ctx.axpy("r", -0.37, "s")
+    assert rel_err(ctx.download("r"), a - 0.37 * b) < 1e-15
+    ctx.upload("u", a)
+    ctx.upload("u_prev", b)
+    ctx.extrapolate_displacement()
+    assert rel_err(ctx.download("u"), a + (a - b)) < 1e-15
+    assert np.array_equal(ctx.download("u_prev"), a)
+    ctx.close()
+
+
+G0 = {3: [0.01, 0.02, -0.01], 6: [0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001]}
+
+
+@pytest.mark.parametrize("problem,materials,fe", [("thermal", THERMAL, "HEX8"), ("thermal", THERMAL, "HEX8R"),
+                                                   ("thermal", THERMAL, "BBAR"), ("mechanical", ELASTIC, "HEX8"),
+                                                   ("mechanical", ELASTIC, "HEX8R"), ("mechanical", ELASTIC, "BBAR")])
+@pytest.mark.parametrize("shape", [(16, 32, 64), (8, 8, 8), (32, 16, 32)])
+def test_residual_and_linear_operator(problem, materials, fe, shape):
+    sol, ctx = make(problem, materials, fe, shape)
+    rng = np.random.default_rng(7)
+    u = rng.standard_normal(ctx.field_shape) * 1e-3
+    g0 = np.array(G0[sol.n_str])
+    sol.set_gradient(g0)
+    ctx.set_gradient(g0)
+    ctx.upload("u", u)
+    ctx.residual("r", "u")
+    assert rel_err(ctx.download("r"), sol.compute_residual(u)) < FIELD_TOL
+    ctx.apply_linear("rnew", "u")
+    assert rel_err(ctx.download("rnew"), sol.apply_linear(u)) < FIELD_TOL
+    # homogenized stress with the absolute-ue strain/stress sweep
+    sol.u = u
+    assert rel_err(ctx.homogenized_stress(), sol.get_homogenized_stress()) < SCALAR_TOL
+    strain, stress, _, _ = sol.strain_stress()
+    assert rel_err(ctx.get_field("strain").reshape(-1, sol.n_str), strain) < FIELD_TOL
+    assert rel_err(ctx.get_field("stress").reshape(-1, sol.n_str), stress) < FIELD_TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("problem,materials,fe,g0", [
+    ("thermal", THERMAL, "HEX8R", [0.01, 0.02, -0.01]),
+    ("thermal", THERMAL, "HEX8", [0.01, 0.02, -0.01]),
+    ("mechanical", ELASTIC, "HEX8R", [0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001]),
+    ("mechanical", ELASTIC, "HEX8", [0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001]),
+    ("mechanical", ELASTIC, "BBAR", [0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001]),
+])
+def test_linear_cg_solve_sphere32(problem, materials, fe, g0):
+    """test/input_files/test_LinearThermal.json / test_LinearElastic.json on the sphere32 microstructure."""
+    ms = fo.sphere_microstructure(32)
+    sol = fo.OracleSolver(ms, [1.0, 1.0, 1.0], problem, materials, fe, "cg", "small", EP, 100)
+    ctx = util.ctx_from_oracle(sol)
+    sol.set_gradient(g0)
+    ctx.set_gradient(g0)
+    sol.solve()
+    res = ctx.solve("cg", 100, 1e-10, "Linfinity", "absolute")
+    assert abs(res["iters"] - sol.iter) <= 1
+    n = min(res["iters"], sol.iter)
+    assert rel_err(res["err_all"][: n + 1], sol.err_all[: n + 1]) < 1e-6
+    assert rel_err(ctx.homogenized_stress(), sol.get_homogenized_stress()) < SCALAR_TOL
+    assert rel_err(ctx.download("u"), sol.u) < FIELD_TOL
+    ctx.close()
