@@ -1,0 +1,473 @@
+// matmodel.hpp — host-side mirror of the reference's material plug-in interface.
+//   Matmodel<howmany,n_str>           include/matmodel.h:10-75
+//   LinearModel<howmany,n_str>        include/matmodel.h:306-310
+//   createMatmodel (string registry)  include/setup.h:21-73
+// The host classes only parse `material_properties`, pre-compute the same per-material constants the reference
+// constructors compute, and export one POD fans_phase_desc per local material; get_sigma itself runs on the GPU
+// (fans_b200/csrc/materials.cuh).  Errors are C++ exceptions with the reference's messages.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <memory>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fans_gpu.h"
+#include "json.hpp"
+
+namespace fans {
+
+using std::string;
+using std::vector;
+
+// dense row-major matrix, tiny
+struct Mat {
+    int r = 0, c = 0;
+    vector<double> a;
+    Mat() {}
+    Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, 0.0) {}
+    double &operator()(int i, int j) { return a[(size_t)i * c + j]; }
+    double operator()(int i, int j) const { return a[(size_t)i * c + j]; }
+    static Mat identity(int n)
+    {
+        Mat m(n, n);
+        for (int i = 0; i < n; ++i) m(i, i) = 1.0;
+        return m;
+    }
+};
+
+static inline vector<double> prop_vector(const Json &props, const string &key)
+{
+    try {
+        return props.at(key).as_vector();
+    } catch (const std::exception &) {
+        throw std::runtime_error("Missing material properties for the requested material model.");
+    }
+}
+
+class Matmodel {
+  public:
+    int howmany, num_str;
+    int n_mat = 0;
+    virtual ~Matmodel() {}
+    Matmodel(int h, int n) : howmany(h), num_str(n) {}
+    virtual bool is_linear() const { return false; }
+    virtual Mat get_reference_stiffness() const = 0;
+    virtual void fill_desc(int mat_index, fans_phase_desc &d) const = 0;
+    virtual bool is_j2() const { return false; }
+};
+
+// ---------------- linear models: export the phase tangent, the GPU builds phase_stiffness ----------------
+class LinearModelBase : public Matmodel {
+  public:
+    using Matmodel::Matmodel;
+    bool is_linear() const override { return true; }
+    virtual Mat phase_kappa(int i) const = 0;
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_LINEAR;
+        const Mat k = phase_kappa(i);
+        for (int q = 0; q < num_str * num_str; ++q) d.params[q] = k.a[q];
+    }
+};
+
+class LinearThermalIsotropic : public LinearModelBase {  // LinearThermal.h:7-46
+  public:
+    vector<double> conductivity;
+    explicit LinearThermalIsotropic(const Json &props) : LinearModelBase(1, 3)
+    {
+        conductivity = prop_vector(props, "conductivity");
+        n_mat = (int)conductivity.size();
+    }
+    Mat phase_kappa(int i) const override
+    {
+        Mat k = Mat::identity(3);
+        for (auto &v : k.a) v *= conductivity[i];
+        return k;
+    }
+    Mat get_reference_stiffness() const override
+    {
+        Mat k(3, 3);
+        for (int i = 0; i < n_mat; ++i)
+            for (int d = 0; d < 3; ++d) k(d, d) += conductivity[i];
+        for (auto &v : k.a) v /= n_mat;
+        return k;
+    }
+};
+
+class LinearThermalTriclinic : public LinearModelBase {  // LinearThermal.h:48-118
+  public:
+    vector<Mat> K_mats;
+    explicit LinearThermalTriclinic(const Json &props) : LinearModelBase(1, 3)
+    {
+        const char *keys[6] = {"K_11", "K_12", "K_13", "K_22", "K_23", "K_33"};
+        vector<vector<double>> c;
+        try {
+            n_mat = (int)props.at("K_11").as_vector().size();
+            for (auto k : keys) {
+                c.push_back(props.at(k).as_vector());
+                if ((int)c.back().size() != n_mat) throw std::runtime_error("Inconsistent size for material property: " + string(k));
+            }
+        } catch (const std::exception &) {
+            throw std::runtime_error("Missing or inconsistent material properties for the requested material model.");
+        }
+        for (int i = 0; i < n_mat; ++i) {
+            Mat K(3, 3);
+            K(0, 0) = c[0][i], K(0, 1) = c[1][i], K(0, 2) = c[2][i];
+            K(1, 0) = c[1][i], K(1, 1) = c[3][i], K(1, 2) = c[4][i];
+            K(2, 0) = c[2][i], K(2, 1) = c[4][i], K(2, 2) = c[5][i];
+            K_mats.push_back(K);
+        }
+    }
+    Mat phase_kappa(int i) const override { return K_mats[i]; }
+    Mat get_reference_stiffness() const override
+    {
+        Mat k(3, 3);
+        for (const auto &m : K_mats)
+            for (int q = 0; q < 9; ++q) k.a[q] += m.a[q];
+        for (auto &v : k.a) v /= n_mat;
+        return k;
+    }
+};
+
+static inline Mat iso_tangent(double lambda, double mu)
+{
+    Mat k(6, 6);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) k(i, j) = lambda;
+    for (int i = 0; i < 6; ++i) k(i, i) += 2 * mu;
+    return k;
+}
+
+class LinearElasticIsotropic : public LinearModelBase {  // LinearElastic.h:7-75
+  public:
+    vector<double> bulk_modulus, mu, lambda;
+    explicit LinearElasticIsotropic(const Json &props) : LinearModelBase(3, 6)
+    {
+        bulk_modulus = prop_vector(props, "bulk_modulus");
+        mu = prop_vector(props, "shear_modulus");
+        n_mat = (int)bulk_modulus.size();
+        lambda.resize(n_mat);
+        mu.resize(n_mat);
+        for (int i = 0; i < n_mat; ++i) lambda[i] = bulk_modulus[i] - (2.0 / 3.0) * mu[i];
+    }
+    Mat phase_kappa(int i) const override { return iso_tangent(lambda[i], mu[i]); }
+    Mat get_reference_stiffness() const override  // LinearElastic.h:55-69: (max+min)/2
+    {
+        const double lambda_ref = (*std::max_element(lambda.begin(), lambda.end()) + *std::min_element(lambda.begin(), lambda.end())) / 2;
+        const double mu_ref = (*std::max_element(mu.begin(), mu.end()) + *std::min_element(mu.begin(), mu.end())) / 2;
+        return iso_tangent(lambda_ref, mu_ref);
+    }
+};
+
+class LinearElasticTriclinic : public LinearModelBase {  // LinearElastic.h:77-159
+  public:
+    vector<Mat> C_mats;
+    explicit LinearElasticTriclinic(const Json &props) : LinearModelBase(3, 6)
+    {
+        vector<vector<double>> c;
+        try {
+            n_mat = (int)props.at("C_11").as_vector().size();
+            for (int r = 0; r < 6; ++r)
+                for (int q = r; q < 6; ++q) {
+                    const string k = "C_" + std::to_string(r + 1) + std::to_string(q + 1);
+                    c.push_back(props.at(k).as_vector());
+                    if ((int)c.back().size() != n_mat) throw std::runtime_error("Inconsistent size for material property: " + k);
+                }
+        } catch (const std::exception &) {
+            throw std::runtime_error("Missing or inconsistent material properties for the requested material model.");
+        }
+        for (int i = 0; i < n_mat; ++i) {
+            Mat C(6, 6);
+            int k = 0;
+            for (int r = 0; r < 6; ++r)
+                for (int q = r; q < 6; ++q) {
+                    C(r, q) = c[k][i];
+                    C(q, r) = c[k][i];
+                    ++k;
+                }
+            C_mats.push_back(C);
+        }
+    }
+    Mat phase_kappa(int i) const override { return C_mats[i]; }
+    Mat get_reference_stiffness() const override
+    {
+        Mat k(6, 6);
+        for (const auto &m : C_mats)
+            for (int q = 0; q < 36; ++q) k.a[q] += m.a[q];
+        for (auto &v : k.a) v /= n_mat;
+        return k;
+    }
+};
+
+// arithmetic-mean isotropic reference (PseudoPlastic.h:43-53, J2Plasticity.h:113-123, J2PlasticityNew.h)
+static inline Mat mean_iso_reference(const vector<double> &K, const vector<double> &G)
+{
+    const double Kbar = std::accumulate(K.begin(), K.end(), 0.0) / (double)K.size();
+    const double Gbar = std::accumulate(G.begin(), G.end(), 0.0) / (double)G.size();
+    return iso_tangent(Kbar - 2.0 * Gbar / 3.0, Gbar);
+}
+
+class PseudoPlastic : public Matmodel {  // PseudoPlastic.h:22-76
+  public:
+    vector<double> bulk_modulus, shear_modulus, yield_stress, eps_crit;
+    explicit PseudoPlastic(const Json &props) : Matmodel(3, 6)
+    {
+        bulk_modulus = prop_vector(props, "bulk_modulus");
+        shear_modulus = prop_vector(props, "shear_modulus");
+        yield_stress = prop_vector(props, "yield_stress");
+        n_mat = (int)bulk_modulus.size();
+    }
+    Mat get_reference_stiffness() const override { return mean_iso_reference(bulk_modulus, shear_modulus); }
+};
+
+class PseudoPlasticLinearHardening : public PseudoPlastic {  // PseudoPlastic.h:78-124
+  public:
+    vector<double> hardening_parameter, E_s;
+    explicit PseudoPlasticLinearHardening(const Json &props) : PseudoPlastic(props)
+    {
+        hardening_parameter = prop_vector(props, "hardening_parameter");
+        E_s.resize(n_mat);
+        eps_crit.resize(n_mat);
+        for (int i = 0; i < n_mat; ++i) {
+            eps_crit[i] = std::sqrt(2. / 3.) * yield_stress[i] / (2. * shear_modulus[i]);
+            E_s[i] = (3. * shear_modulus[i]) / (3. * shear_modulus[i] + hardening_parameter[i]);
+        }
+    }
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_PSEUDOPLASTIC_LINEAR;
+        const double p[6] = {bulk_modulus[i], shear_modulus[i], yield_stress[i], hardening_parameter[i], eps_crit[i], E_s[i]};
+        std::copy(p, p + 6, d.params);
+    }
+};
+
+class PseudoPlasticNonLinearHardening : public PseudoPlastic {  // PseudoPlastic.h:126-173
+  public:
+    vector<double> hardening_exponent, eps_0;
+    explicit PseudoPlasticNonLinearHardening(const Json &props) : PseudoPlastic(props)
+    {
+        hardening_exponent = prop_vector(props, "hardening_exponent");
+        eps_0 = prop_vector(props, "eps_0");
+        eps_crit.resize(n_mat);
+        for (int i = 0; i < n_mat; ++i)
+            eps_crit[i] = eps_0[i] * std::pow(yield_stress[i] / (3.0 * shear_modulus[i] * eps_0[i]), 1.0 / (1.0 - hardening_exponent[i]));
+    }
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_PSEUDOPLASTIC_NONLIN;
+        const double p[6] = {bulk_modulus[i], shear_modulus[i], yield_stress[i], hardening_exponent[i], eps_0[i], eps_crit[i]};
+        std::copy(p, p + 6, d.params);
+    }
+};
+
+class J2Plasticity : public Matmodel {  // J2Plasticity.h:7-163
+  public:
+    vector<double> bulk_modulus, shear_modulus, yield_stress, K, H, eta;
+    double dt = 0.0;
+    explicit J2Plasticity(const Json &props) : Matmodel(3, 6)
+    {
+        bulk_modulus = prop_vector(props, "bulk_modulus");
+        shear_modulus = prop_vector(props, "shear_modulus");
+        yield_stress = prop_vector(props, "yield_stress");
+        K = prop_vector(props, "isotropic_hardening_parameter");
+        H = prop_vector(props, "kinematic_hardening_parameter");
+        eta = prop_vector(props, "viscosity");
+        try {
+            dt = props.at("time_step").as_double();
+        } catch (const std::exception &) {
+            throw std::runtime_error("Missing material properties for the requested material model.");
+        }
+        n_mat = (int)bulk_modulus.size();
+    }
+    bool is_j2() const override { return true; }
+    Mat get_reference_stiffness() const override { return mean_iso_reference(bulk_modulus, shear_modulus); }
+};
+
+class J2ViscoPlastic_LinearIsotropicHardening : public J2Plasticity {  // J2Plasticity.h:165-178
+  public:
+    using J2Plasticity::J2Plasticity;
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_J2_LINEAR_ISO;
+        const double p[7] = {bulk_modulus[i], shear_modulus[i], yield_stress[i], K[i], H[i], eta[i], dt};
+        std::copy(p, p + 7, d.params);
+    }
+};
+
+class J2ViscoPlastic_NonLinearIsotropicHardening : public J2Plasticity {  // J2Plasticity.h:180-243
+  public:
+    vector<double> sigma_inf, delta;
+    explicit J2ViscoPlastic_NonLinearIsotropicHardening(const Json &props) : J2Plasticity(props)
+    {
+        sigma_inf = prop_vector(props, "saturation_stress");
+        delta = prop_vector(props, "saturation_exponent");
+    }
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_J2_NONLIN_ISO;
+        const double p[9] = {bulk_modulus[i], shear_modulus[i], yield_stress[i], K[i], H[i], eta[i], dt, sigma_inf[i], delta[i]};
+        std::copy(p, p + 9, d.params);
+    }
+};
+
+class J2PlasticityNew_LinearIsotropicHardening : public Matmodel {  // J2PlasticityNew.h:7-150
+  public:
+    vector<double> bulk_modulus, shear_modulus, yield_stress, K;
+    explicit J2PlasticityNew_LinearIsotropicHardening(const Json &props) : Matmodel(3, 6)
+    {
+        bulk_modulus = prop_vector(props, "bulk_modulus");
+        shear_modulus = prop_vector(props, "shear_modulus");
+        yield_stress = prop_vector(props, "yield_stress");
+        K = prop_vector(props, "isotropic_hardening_parameter");
+        n_mat = (int)bulk_modulus.size();
+    }
+    Mat get_reference_stiffness() const override { return mean_iso_reference(bulk_modulus, shear_modulus); }
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_J2NEW_LINEAR_ISO;
+        const double p[4] = {bulk_modulus[i], shear_modulus[i], yield_stress[i], K[i]};
+        std::copy(p, p + 4, d.params);
+    }
+};
+
+// ---------------- finite strain (LargeStrainMechModel.h) ----------------
+static const int MANDEL_IJ[6][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 1}, {0, 2}, {1, 2}};
+
+// LargeStrainMechModel.h:105-180 verbatim, including the Q >= P-only sum
+static inline Mat compute_spatial_tangent(const double F[3][3], const double S[3][3], const Mat &C_mandel)
+{
+    Mat A(9, 9);
+    auto mandel = [](int a, int b) {
+        for (int idx = 0; idx < 6; ++idx)
+            if ((MANDEL_IJ[idx][0] == a && MANDEL_IJ[idx][1] == b) || (MANDEL_IJ[idx][0] == b && MANDEL_IJ[idx][1] == a)) return idx;
+        return -1;
+    };
+    for (int i = 0; i < 3; ++i)
+        for (int J = 0; J < 3; ++J) {
+            const int row = 3 * i + J;
+            for (int k = 0; k < 3; ++k)
+                for (int L = 0; L < 3; ++L) {
+                    const int col = 3 * k + L;
+                    if (i == k) A(row, col) += S[L][J];
+                    for (int M = 0; M < 3; ++M) {
+                        const int MJ = mandel(M, J);
+                        if (MJ < 0) continue;
+                        for (int P = 0; P < 3; ++P)
+                            for (int Q = P; Q < 3; ++Q) {
+                                const int PQ = mandel(P, Q);
+                                if (PQ < 0) continue;
+                                double C_val = C_mandel(MJ, PQ);
+                                if (MJ >= 3) C_val /= std::sqrt(2.0);
+                                if (PQ >= 3) C_val /= std::sqrt(2.0);
+                                double dE = 0.0;
+                                if (Q == L) dE += 0.5 * F[k][P];
+                                if (P == L) dE += 0.5 * F[k][Q];
+                                A(row, col) += F[i][M] * C_val * dE;
+                            }
+                    }
+                }
+        }
+    return A;
+}
+
+class LargeStrainMechModel : public Matmodel {
+  public:
+    vector<double> bulk_modulus, shear_modulus, lambda, mu;
+    explicit LargeStrainMechModel(const Json &props) : Matmodel(3, 9)
+    {
+        bulk_modulus = prop_vector(props, "bulk_modulus");
+        shear_modulus = prop_vector(props, "shear_modulus");
+        n_mat = (int)bulk_modulus.size();
+        lambda.resize(n_mat);
+        mu.resize(n_mat);
+        for (int i = 0; i < n_mat; ++i) {
+            mu[i] = shear_modulus[i];
+            lambda[i] = bulk_modulus[i] - (2.0 / 3.0) * mu[i];
+        }
+    }
+    // both hyperelastic laws of the reference have S(F=I) = 0 and the isotropic tangent at F = I
+    // (SaintVenantKirchhoff.h:40-66; CompressibleNeoHookean.h:50-108 with C^-1 = I, log J = 0:
+    //  lambda PP1 + mu PP2 = lambda 1x1 + 2 mu I in Mandel notation)
+    Mat get_reference_stiffness() const override
+    {
+        Mat kapparef(9, 9);
+        const double I3[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        const double S0[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int m = 0; m < n_mat; ++m) {
+            const Mat A = compute_spatial_tangent(I3, S0, material_tangent_at_identity(m));
+            for (int q = 0; q < 81; ++q) kapparef.a[q] += A.a[q];
+        }
+        for (auto &v : kapparef.a) v /= (double)n_mat;
+        return kapparef;
+    }
+    virtual Mat material_tangent_at_identity(int m) const { return iso_tangent(lambda[m], mu[m]); }
+};
+
+class SaintVenantKirchhoff : public LargeStrainMechModel {  // SaintVenantKirchhoff.h
+  public:
+    using LargeStrainMechModel::LargeStrainMechModel;
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_SVK;
+        d.params[0] = lambda[i];
+        d.params[1] = mu[i];
+    }
+};
+
+class CompressibleNeoHookean : public LargeStrainMechModel {  // CompressibleNeoHookean.h
+  public:
+    using LargeStrainMechModel::LargeStrainMechModel;
+    Mat material_tangent_at_identity(int m) const override  // CompressibleNeoHookean.h:50-92 evaluated at F = I
+    {
+        const double f[6] = {1.0, 1.0, 1.0, std::sqrt(2.0), std::sqrt(2.0), std::sqrt(2.0)};
+        const double Ci[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        const double cm[6] = {1.0, 1.0, 1.0, 0.0, 0.0, 0.0};
+        Mat C(6, 6);
+        for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < 6; ++b) {
+                const int I = MANDEL_IJ[a][0], J = MANDEL_IJ[a][1], K = MANDEL_IJ[b][0], L = MANDEL_IJ[b][1];
+                const double pp1 = cm[a] * cm[b];
+                const double pp2 = (Ci[I][K] * Ci[J][L] + Ci[I][L] * Ci[J][K]) * f[a] * f[b];
+                C(a, b) = lambda[m] * pp1 + (mu[m] - lambda[m] * 0.0) * pp2;
+            }
+        return C;
+    }
+    void fill_desc(int i, fans_phase_desc &d) const override
+    {
+        d.model = FANS_MAT_NEOHOOKE;
+        d.params[0] = lambda[i];
+        d.params[1] = mu[i];
+    }
+};
+
+// createMatmodel: include/setup.h:21-73
+static inline std::unique_ptr<Matmodel> createMatmodel(int howmany, int n_str, const string &name, const Json &props)
+{
+    if (howmany == 1 && n_str == 3) {
+        if (name == "LinearThermalIsotropic") return std::make_unique<LinearThermalIsotropic>(props);
+        if (name == "LinearThermalTriclinic") return std::make_unique<LinearThermalTriclinic>(props);
+        throw std::invalid_argument(name + " is not a valid matmodel for thermal problem");
+    }
+    if (howmany == 3 && n_str == 6) {
+        if (name == "LinearElasticIsotropic") return std::make_unique<LinearElasticIsotropic>(props);
+        if (name == "LinearElasticTriclinic") return std::make_unique<LinearElasticTriclinic>(props);
+        if (name == "PseudoPlasticLinearHardening") return std::make_unique<PseudoPlasticLinearHardening>(props);
+        if (name == "PseudoPlasticNonLinearHardening") return std::make_unique<PseudoPlasticNonLinearHardening>(props);
+        if (name == "J2ViscoPlastic_LinearIsotropicHardening") return std::make_unique<J2ViscoPlastic_LinearIsotropicHardening>(props);
+        if (name == "J2ViscoPlastic_NonLinearIsotropicHardening") return std::make_unique<J2ViscoPlastic_NonLinearIsotropicHardening>(props);
+        if (name == "J2PlasticityNew_LinearIsotropicHardening") return std::make_unique<J2PlasticityNew_LinearIsotropicHardening>(props);
+        throw std::invalid_argument(name + " is not a valid small strain material model");
+    }
+    if (howmany == 3 && n_str == 9) {
+        if (name == "SaintVenantKirchhoff") return std::make_unique<SaintVenantKirchhoff>(props);
+        if (name == "CompressibleNeoHookean") return std::make_unique<CompressibleNeoHookean>(props);
+        throw std::invalid_argument(name + " is not a valid large strain material model");
+    }
+    throw std::invalid_argument("invalid (howmany, n_str)");
+}
+
+}  // namespace fans

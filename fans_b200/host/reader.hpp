@@ -1,0 +1,174 @@
+// reader.hpp — input side of the host: mirror of the reference Reader (include/reader.h, src/reader.cpp).
+//   ReadInputFile   src/reader.cpp:63-183     (same JSON keys, defaults and error messages)
+//   ReadMS          src/reader.cpp:227-411    (microstructure -> memory order [x][y][z], slab sizes, volume fractions)
+// HDF5 is not available in this image: microstructures come from a minimal built-in HDF5 reader (h5mini.hpp),
+// from .npy files, or are handed over in memory (SetMicrostructure) by an embedding application.
+#pragma once
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "json.hpp"
+#include "mixedbc.hpp"
+
+namespace fans {
+
+bool h5mini_read_dataset(const std::string &file, const std::string &dataset, std::vector<int> &dims, std::vector<uint16_t> &data,
+                         std::string &permute_order, std::string &err);
+
+class Reader {
+  public:
+    // contents of input file (src/reader.cpp:63-183)
+    std::string ms_filename, ms_datasetname, results_prefix, dataset_name;
+    int n_it = 0;
+    double TOL = 0.0;
+    std::string measure, error_type;  // errorParameters["measure"], ["type"]
+    Json inputJson, microstructure;
+    std::string problemType, matmodel, method, strain_type = "small", FE_type = "HEX8";
+    std::vector<std::string> resultsToWrite;
+    std::vector<LoadCase> load_cases;
+    bool extrapolate_displacement = true;  // include/reader.h:35
+    int ls_max_iter = 5;                   // include/reader.h (linesearch defaults 5 / 1e-2)
+    double ls_tol = 1e-2;
+
+    // contents of microstructure file
+    std::vector<int> dims;      // n_x, n_y, n_z
+    std::vector<double> l_e, L;
+    std::vector<uint16_t> ms;   // [x][y][z]
+    int n_mat = 0;
+
+    int world_rank = 0, world_size = 1;
+    int local_n0 = 0, local_0_start = 0, local_n1 = 0, local_1_start = 0;
+
+    int howmany() const { return problemType == "thermal" ? 1 : 3; }
+    int n_str() const { return problemType == "thermal" ? 3 : (strain_type == "large" ? 9 : 6); }
+
+    void ReadInputFile(const std::string &fn)
+    {
+        std::ifstream f(fn);
+        if (!f) throw std::runtime_error("cannot open input file '" + fn + "'");
+        std::stringstream ss;
+        ss << f.rdbuf();
+        ReadInputString(ss.str());
+    }
+
+    void ReadInputString(const std::string &text)
+    {
+        const Json j = Json::parse(text);
+        inputJson = j;
+        microstructure = j["microstructure"];
+        ms_filename = microstructure.contains("filepath") ? microstructure["filepath"].as_string() : "";
+        const std::string tmp = microstructure["datasetname"].as_string();
+        if (tmp.empty()) throw std::invalid_argument("datasetname must not be empty and must refer to a valid HDF5 path");
+        ms_datasetname = (tmp.front() == '/' ? "" : "/") + tmp;
+        L = microstructure["L"].as_vector();
+        results_prefix = j.contains("results_prefix") ? j["results_prefix"].as_string() : "";
+        dataset_name = ms_datasetname + "_results/" + results_prefix;
+
+        const Json &ep = j["error_parameters"];
+        TOL = ep["tolerance"].as_double();
+        measure = ep["measure"].as_string();
+        error_type = ep["type"].as_string();
+        n_it = j["n_it"].as_int();
+        extrapolate_displacement = j.value("extrapolate_displacement", extrapolate_displacement);
+        if (j.contains("linesearch_parameters")) {
+            ls_max_iter = j["linesearch_parameters"].value("max_iter", ls_max_iter);
+            ls_tol = j["linesearch_parameters"].value("tol", ls_tol);
+            if (ls_max_iter < 1 || ls_tol <= 0.0) throw std::invalid_argument("linesearch_parameters: max_iter >= 1 and tol > 0 required");
+        }
+        problemType = j["problem_type"].as_string();
+        method = j["method"].as_string();
+        if (j.contains("strain_type")) {
+            strain_type = j["strain_type"].as_string();
+            if (strain_type != "small" && strain_type != "large") throw std::invalid_argument("strain_type must be either 'small' or 'large'");
+        } else {
+            strain_type = "small";
+        }
+        if (j.contains("FE_type")) {
+            FE_type = j["FE_type"].as_string();
+            if (FE_type != "HEX8" && FE_type != "HEX8R" && FE_type != "BBAR")
+                throw std::invalid_argument("FE_type must be one of: 'HEX8', 'HEX8R', or 'BBAR'");
+        } else {
+            FE_type = "HEX8";
+        }
+        if (problemType != "thermal" && problemType != "mechanical") throw std::invalid_argument(problemType + " is not a valid problem type");
+        resultsToWrite = j["results"].as_string_vector();
+
+        load_cases.clear();
+        const Json &ml = j["macroscale_loading"];
+        if (!ml.is_array()) throw std::runtime_error("macroscale_loading must be an array");
+        const int ns = n_str();
+        for (const Json &entry : ml.arr) {
+            LoadCase lc;
+            if (entry.is_array()) {  // legacy pure-strain
+                lc.mixed = false;
+                lc.g0_path = entry.as_matrix();
+                lc.n_steps = lc.g0_path.size();
+                if (lc.g0_path.empty() || lc.g0_path[0].size() != (size_t)ns)
+                    throw std::invalid_argument("Invalid length of loading vector: expected " + std::to_string(ns) + " components but got " +
+                                                std::to_string(lc.g0_path.empty() ? 0 : lc.g0_path[0].size()));
+            } else {
+                lc.mixed = true;
+                lc.mbc = MixedBC::from_json(entry, ns);
+                lc.n_steps = lc.mbc.n_rows;
+            }
+            load_cases.push_back(std::move(lc));
+        }
+    }
+
+    // microstructure handed over in memory, already in the solver's [x][y][z] order
+    void SetMicrostructure(const int d[3], const uint16_t *data)
+    {
+        dims.assign(d, d + 3);
+        ms.assign(data, data + (size_t)d[0] * d[1] * d[2]);
+        finish_ms();
+    }
+
+    // src/reader.cpp:227-411.  On disk the array is [z][y][x] unless the attribute permute_order says "xyz".
+    void ReadMS(int /*hm*/)
+    {
+        if (!ms.empty()) return;  // provided in memory
+        std::vector<int> fdims;
+        std::vector<uint16_t> raw;
+        std::string order = "zyx", err;
+        if (!h5mini_read_dataset(ms_filename, ms_datasetname, fdims, raw, order, err))
+            throw std::runtime_error("cannot read microstructure '" + ms_filename + "':'" + ms_datasetname + "': " + err);
+        if (fdims.size() != 3) throw std::runtime_error("microstructure dataset must be 3-dimensional");
+        if (order == "xyz") {
+            dims = fdims;
+            ms = raw;
+        } else {  // zyx on disk -> xyz in memory (src/reader.cpp:385-394)
+            dims = {fdims[2], fdims[1], fdims[0]};
+            ms.resize(raw.size());
+            const int nx = dims[0], ny = dims[1], nz = dims[2];
+            for (int z = 0; z < nz; ++z)
+                for (int y = 0; y < ny; ++y)
+                    for (int x = 0; x < nx; ++x) ms[((size_t)x * ny + y) * nz + z] = raw[((size_t)z * ny + y) * nx + x];
+        }
+        finish_ms();
+    }
+
+    std::vector<double> volume_fractions;
+
+  private:
+    void finish_ms()
+    {
+        if (L.size() != 3) throw std::runtime_error("microstructure.L must have 3 entries");
+        l_e = {L[0] / dims[0], L[1] / dims[1], L[2] / dims[2]};
+        // slab sizes of a single rank (src/reader.cpp:311-331); multi-rank contexts are set up by the launcher
+        local_n0 = dims[0], local_0_start = 0, local_n1 = dims[1], local_1_start = 0;
+        if (dims[0] / 4 < world_size) throw std::runtime_error("[ERROR] Number of processes * 4 must be <= n_x");
+        // ComputeVolumeFractions (src/reader.cpp:13-61)
+        uint16_t mx = 0, mn = 65535;
+        for (uint16_t v : ms) mx = std::max(mx, v), mn = std::min(mn, v);
+        n_mat = (int)mx - (int)mn + 1;
+        volume_fractions.assign(n_mat, 0.0);
+        for (uint16_t v : ms) volume_fractions[v - mn] += 1.0;
+        for (double &v : volume_fractions) v /= (double)ms.size();
+    }
+};
+
+}  // namespace fans

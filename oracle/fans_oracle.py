@@ -846,6 +846,7 @@ class OracleSolver:
         G = np.einsum("...ji,...j,...kj->...ik", Vt, sinv, U)  # V diag(sinv) U^T
         G[0, 0, 0] = 0.0
         self.n_singular = int((s <= 1e-14).any(-1).sum())
+        self.gamma_sv = s  # singular values per frequency (tests use them to spot blocks sitting ON the 1e-14 cut)
         return G / float(self.N)
 
     def convolution(self, r):
