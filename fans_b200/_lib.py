@@ -48,7 +48,7 @@ class SolveParams(C.Structure):
 
 class SolveResult(C.Structure):
     _fields_ = [("iters", C.c_int32), ("n_residual_evals", C.c_int32), ("err_last", C.c_double),
-                ("elapsed_ms", C.c_double), ("fft_ms", C.c_double)]
+                ("elapsed_ms", C.c_double), ("fft_ms", C.c_double), ("loop_ms", C.c_double)]
 
 
 # every symbol include/fans_gpu.h declares (tests check that the library exports all of them)
@@ -57,7 +57,7 @@ EXPORTS = [
     "fans_set_reference_stiffness", "fans_set_gradient", "fans_get_gradient", "fans_set_mixed_bc", "fans_update_mixed_bc",
     "fans_field_upload", "fans_field_download", "fans_field_zero", "fans_field_copy", "fans_residual", "fans_apply_linear",
     "fans_convolution", "fans_dot", "fans_axpy", "fans_norm", "fans_solve", "fans_homogenized_stress", "fans_commit_history",
-    "fans_extrapolate_displacement", "fans_get_field", "fans_launch_count",
+    "fans_extrapolate_displacement", "fans_get_field", "fans_launch_count", "fans_set_profiling", "fans_get_profile",
 ]
 
 _lib = None
@@ -105,6 +105,8 @@ def load():
     lib.fans_commit_history.argtypes = [P]
     lib.fans_extrapolate_displacement.argtypes = [P]
     lib.fans_get_field.argtypes = [P, C.c_char_p, C.c_void_p, C.c_size_t]
+    lib.fans_set_profiling.argtypes = [P, C.c_int32]
+    lib.fans_get_profile.argtypes = [P, C.c_int32, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_int64)]
     lib.fans_launch_count.argtypes = [P]
     lib.fans_launch_count.restype = C.c_int64
     _lib = lib
@@ -261,7 +263,7 @@ class Context:
         hist = np.zeros(int(n_it) + 1)
         self._ck(self.lib.fans_solve(self.ptr, C.byref(p), C.byref(r), _dptr(hist)))
         return {"iters": r.iters, "n_residual_evals": r.n_residual_evals, "err_last": r.err_last, "elapsed_ms": r.elapsed_ms,
-                "err_all": hist[: r.iters + 1].copy()}
+                "loop_ms": r.loop_ms, "fft_ms": r.fft_ms, "err_all": hist[: r.iters + 1].copy()}
 
     def homogenized_stress(self):
         out = np.zeros(self.n_str)
@@ -289,6 +291,19 @@ class Context:
         else:
             raise FansError("unknown field " + name)
         self._ck(self.lib.fans_get_field(self.ptr, name.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.fans_set_profiling(self.ptr, int(bool(on))))
+
+    def profile(self):
+        """{kernel class: (total device ms, launches)} since set_profiling(True)"""
+        out = {}
+        for cls in range(16):
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_int64()
+            self._ck(self.lib.fans_get_profile(self.ptr, cls, C.byref(name), C.byref(ms), C.byref(n)))
+            if name.value and n.value:
+                out[name.value.decode()] = (ms.value, n.value)
         return out
 
     def launch_count(self):

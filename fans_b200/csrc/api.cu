@@ -12,6 +12,70 @@ void fans_set_error(fans_ctx *ctx, int code, const std::string &msg)
     else g_create_error = msg;
 }
 
+static cudaEvent_t prof_get_event(fans_ctx *ctx)
+{
+    if (!ctx->prof_pool.empty()) {
+        cudaEvent_t e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(fans_ctx *ctx, int cls)
+{
+    if (!ctx->prof) return;
+    fans_ctx::ProfRec r{prof_get_event(ctx), prof_get_event(ctx), cls};
+    cudaEventRecord(r.a, ctx->st);
+    ctx->prof_pending.push_back(r);
+}
+void prof_end(fans_ctx *ctx)
+{
+    if (!ctx->prof || ctx->prof_pending.empty()) return;
+    cudaEventRecord(ctx->prof_pending.back().b, ctx->st);
+}
+void prof_resolve(fans_ctx *ctx)
+{
+    for (auto &r : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ctx->prof_ms[r.cls] += ms;
+            ctx->prof_n[r.cls] += 1;
+        }
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+}
+
+static const char *PROF_NAMES[FANS_PROF_CLASSES] = {"fft_z_fwd", "fft_y_fwd", "fft_x_gamma", "fft_y_inv", "fft_z_inv", "sweep_linear",
+                                                    "sweep_residual", "sweep_strainstress", "cg_update", "reduce", "axpy", "other",
+                                                    "", "", "", ""};
+
+extern "C" int fans_set_profiling(fans_ctx *ctx, int32_t on)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    prof_resolve(ctx);
+    ctx->prof = on != 0;
+    for (int i = 0; i < FANS_PROF_CLASSES; ++i) ctx->prof_ms[i] = 0.0, ctx->prof_n[i] = 0;
+    return FANS_OK;
+}
+
+extern "C" int fans_get_profile(fans_ctx *ctx, int32_t cls, const char **name, double *ms, int64_t *count)
+{
+    if (!ctx || cls < 0 || cls >= FANS_PROF_CLASSES) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    prof_resolve(ctx);
+    if (name) *name = PROF_NAMES[cls];
+    if (ms) *ms = ctx->prof_ms[cls];
+    if (count) *count = ctx->prof_n[cls];
+    return FANS_OK;
+}
+
 extern "C" const char *fans_last_error(const fans_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" int fans_version(void) { return 100; }
 extern "C" int64_t fans_launch_count(const fans_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -234,6 +298,8 @@ static int create_rest(fans_ctx *ctx)
 {
     CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
     CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(ctx, cudaEventCreate(&ctx->ev_loop0));
+    CUDA_TRY(ctx, cudaEventCreate(&ctx->ev_loop1));
 
     ctx->kzc = ctx->nz / 2 + 1;
     ctx->kzp = (ctx->kzc + 7) / 8 * 8;
@@ -277,8 +343,12 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     fft_plan_free(ctx->planx);
     fft_plan_free(ctx->plany);
     fft_plan_free(ctx->planz);
+    prof_resolve(ctx);
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_loop0) cudaEventDestroy(ctx->ev_loop0);
+    if (ctx->ev_loop1) cudaEventDestroy(ctx->ev_loop1);
     if (ctx->own_stream && ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }

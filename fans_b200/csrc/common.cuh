@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/fans_gpu.h"
 
+#define FANS_PROF_CLASSES 16
 #define FANS_SMS 148  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
 
 #define CUDA_TRY(ctx, expr)                                                                                    \
@@ -56,7 +57,7 @@ struct fans_ctx {
     int device;
     cudaStream_t st = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_loop0 = nullptr, ev_loop1 = nullptr;
 
     double *field[FANS_N_FIELDS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_alt = nullptr;   // ping-pong partner of D (fused d = s + beta d must not update in place)
@@ -106,12 +107,27 @@ struct fans_ctx {
     int neg_jac_flag_host = 0;
     int *d_flag = nullptr;      // sticky device fault flag (J <= 0)
 
+    // optional per-kernel-class device timing (bench.py roofline): event pairs resolved at the next stream sync
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_pool;
+    struct ProfRec { cudaEvent_t a, b; int cls; };
+    std::vector<ProfRec> prof_pending;
+    double prof_ms[FANS_PROF_CLASSES] = {0};
+    int64_t prof_n[FANS_PROF_CLASSES] = {0};
+
     std::string err;
     int64_t launches = 0;
     int n_residual_evals = 0;
 };
 
 void fans_set_error(fans_ctx *ctx, int code, const std::string &msg);
+
+// kernel classes for profiling (index into prof_ms / prof_n); names in api.cu
+enum { PC_FFT_Z_FWD = 0, PC_FFT_Y_FWD, PC_FFT_X_GAMMA, PC_FFT_Y_INV, PC_FFT_Z_INV, PC_SWEEP_LINEAR, PC_SWEEP_RESIDUAL,
+       PC_SWEEP_STRAINSTRESS, PC_CG_UPDATE, PC_REDUCE, PC_AXPY, PC_OTHER };
+void prof_begin(fans_ctx *ctx, int cls);
+void prof_end(fans_ctx *ctx);
+void prof_resolve(fans_ctx *ctx);  // call after a stream synchronisation
 
 // ---------------- device helpers ----------------
 #ifdef __CUDACC__

@@ -312,6 +312,7 @@ static int set_smem(fans_ctx *ctx, K kernel, size_t bytes)
 // y pass (forward or inverse) on the local slab: lines along y for every (c, x, kz tile)
 int fft_pass_y(fans_ctx *ctx, bool inverse)
 {
+    prof_begin(ctx, inverse ? PC_FFT_Y_INV : PC_FFT_Y_FWD);
     const FftStages st = make_stages(ctx->plany);
     const int ny = ctx->ny;
     // T = 8 keeps 128 B segments; very long lines fall back to T = 4 to keep >= 2 CTAs per SM
@@ -339,6 +340,7 @@ int fft_pass_y(fans_ctx *ctx, bool inverse)
             k_fft_strided<4, true><<<grid, nthr, smem, ctx->st>>>(ctx->spec, st, ctx->plany.tw, cStride, oStride, ctx->n0, nTiles, ctx->kzp);
         }
     }
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -347,6 +349,7 @@ int fft_pass_y(fans_ctx *ctx, bool inverse)
 // fused x pass with the Green operator (single-GPU layout [c][x][y][kz]: x stride = ny*kzp)
 int fft_pass_x_gamma(fans_ctx *ctx)
 {
+    prof_begin(ctx, PC_FFT_X_GAMMA);
     const FftStages st = make_stages(ctx->planx);
     const int nx = ctx->nx, T = ctx->gT;
     const int nTiles = (ctx->kzc + T - 1) / T;
@@ -370,6 +373,7 @@ int fft_pass_x_gamma(fans_ctx *ctx)
         return FANS_ERR_ARG;
     }
 #undef LAUNCH_XG
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -377,6 +381,7 @@ int fft_pass_x_gamma(fans_ctx *ctx)
 
 int fft_pass_z_fwd(fans_ctx *ctx, const double *in)
 {
+    prof_begin(ctx, PC_FFT_Z_FWD);
     const FftStages st = make_stages(ctx->planz);
     const int Nh = ctx->nz / 2;
     const size_t nlines = (size_t)ctx->h * ctx->n0 * ctx->ny;
@@ -385,6 +390,7 @@ int fft_pass_z_fwd(fans_ctx *ctx, const double *in)
     FANS_CHECK(set_smem(ctx, k_fft_z_fwd, smem));
     const unsigned grid = (unsigned)((nlines + 7) / 8);
     k_fft_z_fwd<<<grid, nthr, smem, ctx->st>>>(in, ctx->spec, st, ctx->planz.tw, ctx->planz.pos, nlines, ctx->kzp);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -392,6 +398,7 @@ int fft_pass_z_fwd(fans_ctx *ctx, const double *in)
 
 int fft_pass_z_inv(fans_ctx *ctx, double *out, double scale, const double *dotw, double *red_out)
 {
+    prof_begin(ctx, PC_FFT_Z_INV);
     const FftStages st = make_stages(ctx->planz);
     const int Nh = ctx->nz / 2;
     const size_t nlines = (size_t)ctx->h * ctx->n0 * ctx->ny;
@@ -401,6 +408,7 @@ int fft_pass_z_inv(fans_ctx *ctx, double *out, double scale, const double *dotw,
     const unsigned grid = (unsigned)((nlines + 7) / 8);
     k_fft_z_inv<<<grid, nthr, smem, ctx->st>>>(ctx->spec, out, st, ctx->planz.tw, ctx->planz.pos, nlines, ctx->kzp, scale,
                                                dotw, ctx->d_part, ctx->d_ticket, red_out);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;

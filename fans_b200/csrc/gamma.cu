@@ -120,6 +120,7 @@ __global__ void k_build_gamma(double *__restrict__ gamma, const double *__restri
 
 int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const int *frqy)
 {
+    prof_begin(ctx, PC_OTHER);
     const int T = ctx->gT;
     const int nTiles = (ctx->kzc + T - 1) / T;
     const size_t total = (size_t)ctx->n1 * nTiles * ctx->nx * T;
@@ -133,6 +134,7 @@ int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const in
     else
         k_build_gamma<3><<<(unsigned)nb, nthr, 0, ctx->st>>>(ctx->gamma, Ker0_dev, frqx, frqy, ctx->nx, ctx->ny, ctx->nz, ctx->n1, ctx->y1,
                                                            ctx->kzc, T, nTiles, invN);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;

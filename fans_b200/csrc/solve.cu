@@ -16,6 +16,7 @@ int read_scalars(fans_ctx *ctx)
 {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->st));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    prof_resolve(ctx);
     return FANS_OK;
 }
 
@@ -153,7 +154,7 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
     FANS_CHECK(write_scalar(ctx, S_DELTA, 1.0));
     FANS_CHECK(write_scalar(ctx, S_DELTAMID, 0.0));  // <r, s> with s = 0
     double delta = 1.0;
-    float fft_ms = 0.f;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
     while (es.iter < p->n_it && err_rel > p->tol) {
         if (linear) {
             // deltamid already sits in S_DELTAMID (left by k_cg_update, 0 at iter 0)
@@ -226,8 +227,8 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
         }
         if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
     }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop1, ctx->st));
     res->err_last = err_rel;
-    res->fft_ms = fft_ms;
     return FANS_OK;
 }
 
@@ -243,6 +244,7 @@ static int solve_fp(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
     FANS_CHECK(compute_error(ctx, r, es, &err_rel));
     FANS_CHECK(check_fault(ctx));
     if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
     while (es.iter < p->n_it && err_rel > p->tol) {
         FANS_CHECK(conv_run(ctx, r, r, 1.0, nullptr, nullptr));
         FANS_CHECK(vec_axpy(ctx, u, -1.0, r));
@@ -254,6 +256,7 @@ static int solve_fp(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
         FANS_CHECK(check_fault(ctx));
         if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
     }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop1, ctx->st));
     res->err_last = err_rel;
     return FANS_OK;
 }
@@ -291,6 +294,11 @@ extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     res->elapsed_ms = ms;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_loop0, ctx->ev_loop1));
+    res->loop_ms = ms;
+    prof_resolve(ctx);
+    res->fft_ms = ctx->prof_ms[PC_FFT_Z_FWD] + ctx->prof_ms[PC_FFT_Y_FWD] + ctx->prof_ms[PC_FFT_X_GAMMA] + ctx->prof_ms[PC_FFT_Y_INV] +
+                  ctx->prof_ms[PC_FFT_Z_INV];
     res->iters = es.iter;
     res->n_residual_evals = ctx->n_residual_evals - evals0;
     return FANS_OK;

@@ -358,6 +358,7 @@ static int upload_constants(fans_ctx *ctx)
 template <int H, int NSTR, int MODE>
 static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t smem)
 {
+    prof_begin(ctx, MODE == SW_LINEAR ? PC_SWEEP_LINEAR : (MODE == SW_RESIDUAL ? PC_SWEEP_RESIDUAL : PC_SWEEP_STRAINSTRESS));
     if (MODE == SW_LINEAR && ctx->k_in_const) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_sweep<H, NSTR, MODE, true><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
@@ -365,6 +366,7 @@ static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t s
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_sweep<H, NSTR, MODE, false><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
     }
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;

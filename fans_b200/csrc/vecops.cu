@@ -128,9 +128,11 @@ __global__ void k_scalars_after_conv(double *S)
 // ------------------------------------------------------------------------------------------------
 int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const double *d, const double *s)
 {
+    prof_begin(ctx, PC_CG_UPDATE);
     const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
     k_cg_update<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)r, (const double2 *)kd, (double2 *)u, (const double2 *)d,
                                                           (const double2 *)s, n2, ctx->d_red, ctx->d_part, ctx->d_ticket);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -138,8 +140,10 @@ int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const d
 
 int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev)
 {
+    prof_begin(ctx, PC_REDUCE);
     const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
     k_reduce4<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((const double2 *)a, (const double2 *)b, n2, ctx->d_part, ctx->d_ticket, out_dev);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -147,8 +151,10 @@ int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev
 
 int vec_axpy(fans_ctx *ctx, double *y, double alpha, const double *x)
 {
+    prof_begin(ctx, PC_AXPY);
     const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
     k_axpy<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, alpha, (const double2 *)x, n2);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -156,8 +162,10 @@ int vec_axpy(fans_ctx *ctx, double *y, double alpha, const double *x)
 
 int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x)
 {
+    prof_begin(ctx, PC_AXPY);
     const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
     k_xpby<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, beta, (const double2 *)x, n2);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -165,8 +173,10 @@ int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x)
 
 int vec_extrapolate(fans_ctx *ctx, double *u, double *up)
 {
+    prof_begin(ctx, PC_OTHER);
     const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
     k_extrapolate<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)u, (double2 *)up, n2);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -174,8 +184,10 @@ int vec_extrapolate(fans_ctx *ctx, double *u, double *up)
 
 int vec_aos_to_soa(fans_ctx *ctx, const double *aos, double *soa)
 {
+    prof_begin(ctx, PC_OTHER);
     const size_t n = (size_t)ctx->h * ctx->nloc;
     k_aos_to_soa<<<vec_grid(n), VEC_THREADS, 0, ctx->st>>>(aos, soa, ctx->nloc, ctx->h);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -183,8 +195,10 @@ int vec_aos_to_soa(fans_ctx *ctx, const double *aos, double *soa)
 
 int vec_soa_to_aos(fans_ctx *ctx, const double *soa, double *aos)
 {
+    prof_begin(ctx, PC_OTHER);
     const size_t n = (size_t)ctx->h * ctx->nloc;
     k_soa_to_aos<<<vec_grid(n), VEC_THREADS, 0, ctx->st>>>(soa, aos, ctx->nloc, ctx->h);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;
@@ -192,7 +206,9 @@ int vec_soa_to_aos(fans_ctx *ctx, const double *soa, double *aos)
 
 int vec_scalars_after_conv(fans_ctx *ctx)
 {
+    prof_begin(ctx, PC_OTHER);
     k_scalars_after_conv<<<1, 1, 0, ctx->st>>>(ctx->d_red);
+    prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FANS_OK;

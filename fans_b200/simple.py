@@ -1,0 +1,60 @@
+"""Convenience constructors above the C ABI for the headline workload (two-phase linear elasticity / conduction).
+Host-side restatement of what the reference's LinearElasticIsotropic / LinearThermalIsotropic constructors and
+MaterialManager::compute_reference_stiffness do (include/material_models/LinearElastic.h:7-75,
+LinearThermal.h:7-46, MaterialManager.h:177-205) — parameter bookkeeping only, all numerics run in libfans_gpu."""
+import numpy as np
+
+from . import _lib as L
+
+
+def sphere_microstructure(n, radius_frac=0.4):
+    """Synthetic config-2/-headline image: phase 1 inside a centred sphere of radius 0.4 n."""
+    c = (n - 1) / 2.0
+    i = (np.arange(n) - c) ** 2
+    ms = np.empty((n, n, n), dtype=np.uint16)
+    r2 = (radius_frac * n) ** 2
+    for x in range(n):  # plane by plane keeps the temporary small at 512^3
+        ms[x] = (i[x] + i[:, None] + i[None, :]) <= r2
+    return ms
+
+
+def elastic_tangent(lam, mu):
+    k = np.zeros((6, 6))
+    k[:3, :3] = lam
+    k += 2.0 * mu * np.eye(6)
+    return k
+
+
+def linear_elastic_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1):
+    """LinearElasticIsotropic on phases 0..len(bulk)-1; reference stiffness = (max+min)/2 of lambda and mu."""
+    bulk = np.asarray(bulk, dtype=np.float64)
+    mu = np.asarray(shear, dtype=np.float64)
+    lam = bulk - (2.0 / 3.0) * mu
+    ctx = L.Context(ms.shape, Lbox, 3, 6, fe_type, device)
+    descs = []
+    for i in range(len(bulk)):
+        d = L.PhaseDesc()
+        d.model, d.local_mat, d.group_n_mat = L.MAT_LINEAR, i, len(bulk)
+        for k, v in enumerate(elastic_tangent(lam[i], mu[i]).reshape(-1)):
+            d.params[k] = v
+        descs.append(d)
+    ctx.set_materials(descs)
+    ctx.set_microstructure(ms)
+    ctx.set_reference_stiffness(elastic_tangent((lam.max() + lam.min()) / 2, (mu.max() + mu.min()) / 2))
+    return ctx
+
+
+def linear_thermal_context(ms, Lbox, conductivity, fe_type="HEX8", device=-1):
+    k = np.asarray(conductivity, dtype=np.float64)
+    ctx = L.Context(ms.shape, Lbox, 1, 3, fe_type, device)
+    descs = []
+    for i in range(len(k)):
+        d = L.PhaseDesc()
+        d.model, d.local_mat, d.group_n_mat = L.MAT_LINEAR, i, len(k)
+        for q, v in enumerate((k[i] * np.eye(3)).reshape(-1)):
+            d.params[q] = v
+        descs.append(d)
+    ctx.set_materials(descs)
+    ctx.set_microstructure(ms)
+    ctx.set_reference_stiffness(np.eye(3) * k.mean())
+    return ctx

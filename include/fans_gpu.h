@@ -112,7 +112,8 @@ typedef struct {
     int32_t n_residual_evals; /* number of compute_residual / K.d sweeps */
     double  err_last;         /* last value returned by compute_error */
     double  elapsed_ms;       /* device time of internalSolve (CUDA events) */
-    double  fft_ms;           /* device time inside convolution() (solver.h:293 "Total FFT Time"), 0 if not measured */
+    double  fft_ms;           /* device time inside convolution() (solver.h:293 "Total FFT Time"); needs fans_set_profiling */
+    double  loop_ms;          /* device time of the iteration loop alone (after the initial residual), CUDA events */
 } fans_solve_result;
 
 /* ---- lifetime: Solver ctor/dtor include/solver.h:105-142, 780-805 ---- */
@@ -158,6 +159,10 @@ int fans_extrapolate_displacement(fans_ctx *ctx);                           /* e
  *   "plastic_strain","kinematic_hardening_variable"   double [x][y][z][6], "isotropic_hardening_variable" double [x][y][z]
  *   "fundamental_solution"       double [y_local][x][kz][h*(h+1)/2]  natural frequency order (debug / tests) */
 int fans_get_field(fans_ctx *ctx, const char *name, void *host_dst, size_t bytes);
+
+/* per-kernel-class device timing (CUDA events on the library's stream). cls = 0.. until *name is "" */
+int fans_set_profiling(fans_ctx *ctx, int32_t on);  /* resets the accumulators */
+int fans_get_profile(fans_ctx *ctx, int32_t cls, const char **name, double *ms, int64_t *count);
 
 /* number of CUDA kernel launches issued by this ctx since creation (bench.py gpu_launches) */
 int64_t fans_launch_count(const fans_ctx *ctx);
