@@ -1,5 +1,7 @@
 // api.cu — C ABI of libfans_gpu (include/fans_gpu.h): context lifetime, problem data, fields, operators.
 #include "internal.h"
+#include "stencil.h"
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 
@@ -435,6 +437,7 @@ extern "C" int fans_set_materials(fans_ctx *ctx, int32_t n_phases, const fans_ph
         if (ph[i].model != FANS_MAT_LINEAR) all_lin = false;
     }
     ctx->phases.assign(ph, ph + n_phases);
+    ctx->K_host = Ktab;
     ctx->n_phases = n_phases;
     ctx->n_k = nk;
     ctx->all_linear = all_lin;
@@ -635,7 +638,10 @@ extern "C" int fans_apply_linear(fans_ctx *ctx, int32_t fo, int32_t fd)
         return FANS_ERR_STATE;
     }
     ctx->n_residual_evals++;
-    FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, ctx->field[fd], ctx->field[fo], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    if (stencil_supported(ctx) && !getenv("FANS_LINEAR_SWEEP"))
+        FANS_CHECK(stencil_run(ctx, ctx->field[fd], ctx->field[fo], nullptr, nullptr, nullptr, nullptr));
+    else
+        FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, ctx->field[fd], ctx->field[fo], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     return FANS_OK;
 }

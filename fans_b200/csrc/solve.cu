@@ -6,6 +6,8 @@
 //   Solver::get_homogenized_stress include/solver.h:707-737
 //   MixedBCController::update      include/mixedBCs.h:160-178
 #include "internal.h"
+#include "stencil.h"
+#include <cstdlib>
 #include <cmath>
 
 int ensure_fields(fans_ctx *ctx, std::initializer_list<int> ids);
@@ -140,6 +142,7 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
     const size_t fbytes = sizeof(double) * ctx->h * ctx->nloc;
     const bool linear = ctx->all_linear && !ctx->mixed && !p->force_nonlinear;
     if (linear) FANS_CHECK(ensure_dalt(ctx));
+    const bool use_stencil = stencil_supported(ctx) && !getenv("FANS_LINEAR_SWEEP");
     // s = 0, d = 0 (solverCG.h:70-74), alpha_warm = 0.1, delta = 1 (solverCG.h:68,82)
     CUDA_TRY(ctx, cudaMemsetAsync(s, 0, fbytes, ctx->st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->field[FANS_FIELD_D], 0, fbytes, ctx->st));
@@ -162,7 +165,8 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
             FANS_CHECK(vec_scalars_after_conv(ctx));                             // delta0, delta, beta
             double *d_old = ctx->field[FANS_FIELD_D], *d_new = ctx->d_alt;
             ctx->n_residual_evals++;
-            FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD, nullptr, nullptr));
+            if (use_stencil) FANS_CHECK(stencil_run(ctx, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD));
+            else FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD, nullptr, nullptr));
             ctx->field[FANS_FIELD_D] = d_new;
             ctx->d_alt = d_old;
             FANS_CHECK(vec_cg_update(ctx, r, rnew, u, d_new, s));                // r,u update + norms + deltamid
