@@ -20,6 +20,9 @@
 #define GTILE ((GY + 2) * GPZ)
 #define GETILE ((GY + 1) * (GZ + 1))
 #define G_THREADS 256
+#ifndef STENCIL_MINB
+#define STENCIL_MINB 2
+#endif
 
 __constant__ double c_S[STENCIL_MAXQ * 27 * 9];   // [q][delta][i][j]
 __constant__ double c_KQ[STENCIL_MAXQ * 576];      // [q][row][col]  (8h x 8h, h <= 3)
@@ -126,12 +129,14 @@ __device__ __forceinline__ void node_general(const double *ring, const uint16_t 
 }
 
 template <int H, int NQ>
-__global__ void __launch_bounds__(G_THREADS, 3) k_stencil_linear(const StencilParams p)
+__global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p)
 {
     extern __shared__ __align__(16) double smem[];
     double *ring = smem;                                               // [4][H][GTILE]
     uint16_t *mring = reinterpret_cast<uint16_t *>(smem + 4 * H * GTILE);  // [3][GETILE]
     __shared__ double scratch[32];
+    __shared__ uint16_t qlist[GY * 32];  // queued interface node pairs, per warp row
+    __shared__ int qcnt[GY];
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const int z0 = blockIdx.x * GZ, y0 = blockIdx.y * GY;
@@ -141,33 +146,71 @@ __global__ void __launch_bounds__(G_THREADS, 3) k_stencil_linear(const StencilPa
     const bool valid = (yA < p.ny) && (zA < p.nz);  // nz is even, so A valid <=> B valid
     const double beta = p.s ? *p.beta : 0.0;
 
-    auto load_plane = [&](int xp, bool owned) {
-        const int xg = gwrap(xp, p.n0);
-        double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
-        for (int i = tid; i < GTILE; i += G_THREADS) {
-            const int r = i / GPZ, c = i % GPZ;
-            const int y = gwrap(y0 - 1 + r, p.ny), z = gwrap(z0 - 1 + c, p.nz);
-            const size_t g = ((size_t)xg * p.ny + y) * p.nz + z;
-            const bool mine = owned && r >= 1 && r <= GY && c >= 1 && c <= GZ && (y0 - 1 + r) < p.ny && (z0 - 1 + c) < p.nz;
+    // in-plane offsets of the tile positions this thread loads (fixed over the march): no div/mod in the x loop
+    constexpr int NLD = (GTILE + G_THREADS - 1) / G_THREADS, NLM = (GETILE + G_THREADS - 1) / G_THREADS;
+    int goff[NLD], moff[NLM];
+    unsigned mine_mask = 0;
 #pragma unroll
-            for (int cc = 0; cc < H; ++cc) {
-                double v = p.d_old[cc * p.nloc + g];
-                if (p.s) {
-                    v = p.s[cc * p.nloc + g] + beta * v;
-                    if (mine) p.d_new[cc * p.nloc + g] = v;
-                }
-                pl[cc * GTILE + i] = v;
-            }
+    for (int j = 0; j < NLD; ++j) {
+        const int i = tid + j * G_THREADS;
+        goff[j] = -1;
+        if (i < GTILE) {
+            const int r = i / GPZ, c = i % GPZ;
+            goff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 1 + c, p.nz);
+            if (r >= 1 && r <= GY && c >= 1 && c <= GZ && (y0 - 1 + r) < p.ny && (z0 - 1 + c) < p.nz) mine_mask |= 1u << j;
         }
+    }
+#pragma unroll
+    for (int j = 0; j < NLM; ++j) {
+        const int i = tid + j * G_THREADS;
+        moff[j] = -1;
+        if (i < GETILE) {
+            const int r = i / (GZ + 1), c = i % (GZ + 1);
+            moff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 1 + c, p.nz);
+        }
+    }
+    const size_t plane_sz = (size_t)p.ny * p.nz;
+    auto load_plane = [&](int xp, bool owned) {
+        const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
+        double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
+        double v[NLD][H];
+#pragma unroll
+        for (int j = 0; j < NLD; ++j)
+            if (goff[j] >= 0) {
+#pragma unroll
+                for (int cc = 0; cc < H; ++cc) v[j][cc] = p.d_old[cc * p.nloc + gbase + goff[j]];
+            }
+        if (p.s) {
+            double sv[NLD][H];
+#pragma unroll
+            for (int j = 0; j < NLD; ++j)
+                if (goff[j] >= 0) {
+#pragma unroll
+                    for (int cc = 0; cc < H; ++cc) sv[j][cc] = p.s[cc * p.nloc + gbase + goff[j]];
+                }
+#pragma unroll
+            for (int j = 0; j < NLD; ++j)
+                if (goff[j] >= 0) {
+#pragma unroll
+                    for (int cc = 0; cc < H; ++cc) {
+                        v[j][cc] = sv[j][cc] + beta * v[j][cc];
+                        if (owned && ((mine_mask >> j) & 1u)) p.d_new[cc * p.nloc + gbase + goff[j]] = v[j][cc];
+                    }
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < NLD; ++j)
+            if (goff[j] >= 0) {
+#pragma unroll
+                for (int cc = 0; cc < H; ++cc) pl[cc * GTILE + tid + j * G_THREADS] = v[j][cc];
+            }
     };
     auto load_ms = [&](int xp) {
-        const int xg = gwrap(xp, p.n0);
+        const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
         uint16_t *mp = mring + ((xp + 3) % 3) * GETILE;
-        for (int i = tid; i < GETILE; i += G_THREADS) {
-            const int r = i / (GZ + 1), c = i % (GZ + 1);
-            const int y = gwrap(y0 - 1 + r, p.ny), z = gwrap(z0 - 1 + c, p.nz);
-            mp[i] = p.phidx[((size_t)xg * p.ny + y) * p.nz + z];
-        }
+#pragma unroll
+        for (int j = 0; j < NLM; ++j)
+            if (moff[j] >= 0) mp[tid + j * G_THREADS] = p.phidx[gbase + moff[j]];
     };
 
     load_plane(xs - 1, false);
@@ -178,33 +221,64 @@ __global__ void __launch_bounds__(G_THREADS, 3) k_stencil_linear(const StencilPa
         load_plane(k + 1, (k + 1) < xe);
         load_ms(k);
         __syncthreads();
+        // ---- phase 1: homogeneous node pairs take the 27-point stencil; interface pairs are queued
+        bool homog = true;
+        int ph = 0;
         if (valid) {
             // phases of the 12 elements around the node pair: planes k-1,k ; rows ry-1,ry ; columns rzA-1..rzA+1
             const uint16_t *m0 = mring + ((k - 1 + 3) % 3) * GETILE, *m1 = mring + ((k + 3) % 3) * GETILE;
             const int e00 = (ry - 1) * (GZ + 1) + rzA - 1, e10 = ry * (GZ + 1) + rzA - 1;
-            const int ph = m1[e10 + 1];
-            bool homog = true;
+            ph = m1[e10 + 1];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 homog = homog && (m0[e00 + c] == ph) && (m0[e10 + c] == ph) && (m1[e00 + c] == ph) && (m1[e10 + c] == ph);
+        }
+        const unsigned qmask = __ballot_sync(0xffffffffu, valid && !homog);
+        if (valid && homog) {
             double accA[H], accB[H];
 #pragma unroll
             for (int c = 0; c < H; ++c) accA[c] = 0.0, accB[c] = 0.0;
-            if (homog) {
-                if (NQ > 0 && ph == 0) stencil_pair<H, 0>(ring, k, ry, rzA - 1, accA, accB);
-                else if (NQ > 1 && ph == 1) stencil_pair<H, (NQ > 1 ? 1 : 0)>(ring, k, ry, rzA - 1, accA, accB);
-                else if (NQ > 2 && ph == 2) stencil_pair<H, (NQ > 2 ? 2 : 0)>(ring, k, ry, rzA - 1, accA, accB);
-                else if (NQ > 3 && ph == 3) stencil_pair<H, (NQ > 3 ? 3 : 0)>(ring, k, ry, rzA - 1, accA, accB);
-            } else {
-                node_general<H, NQ>(ring, mring, k, ry, rzA, accA);
-                node_general<H, NQ>(ring, mring, k, ry, rzA + 1, accB);
-            }
+            if (NQ > 0 && ph == 0) stencil_pair<H, 0>(ring, k, ry, rzA - 1, accA, accB);
+            else if (NQ > 1 && ph == 1) stencil_pair<H, (NQ > 1 ? 1 : 0)>(ring, k, ry, rzA - 1, accA, accB);
+            else if (NQ > 2 && ph == 2) stencil_pair<H, (NQ > 2 ? 2 : 0)>(ring, k, ry, rzA - 1, accA, accB);
+            else if (NQ > 3 && ph == 3) stencil_pair<H, (NQ > 3 ? 3 : 0)>(ring, k, ry, rzA - 1, accA, accB);
             const size_t g = ((size_t)k * p.ny + yA) * p.nz + zA;
             const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + ry * GPZ + rzA;
 #pragma unroll
             for (int c = 0; c < H; ++c) {
                 *reinterpret_cast<double2 *>(p.out + c * p.nloc + g) = make_double2(accA[c], accB[c]);
                 racc[0] += accA[c] * ctr[c * GTILE] + accB[c] * ctr[c * GTILE + 1];
+            }
+        }
+        if (qmask) {
+            if (valid && !homog) qlist[wy * 32 + __popc(qmask & ((1u << lane) - 1u))] = (uint16_t)(ry * 128 + rzA);
+        }
+        if (lane == 0) qcnt[wy] = __popc(qmask);
+        __syncthreads();
+        // ---- phase 2: the queued interface nodes of the whole CTA, densely packed onto lanes (exact element form)
+        int pre[GY + 1];
+        pre[0] = 0;
+#pragma unroll
+        for (int w = 0; w < GY; ++w) pre[w + 1] = pre[w] + qcnt[w];
+        const int nitems = 2 * pre[GY];
+        for (int n = tid; n < nitems; n += G_THREADS) {
+            const int pair = n >> 1;
+            int w = 0, base = 0;
+#pragma unroll
+            for (int q = 1; q < GY; ++q)
+                if (pair >= pre[q]) w = q, base = pre[q];
+            const int code = qlist[w * 32 + (pair - base)];
+            const int qry = code >> 7, qrz = (code & 127) + (n & 1);
+            double acc[H];
+#pragma unroll
+            for (int c = 0; c < H; ++c) acc[c] = 0.0;
+            node_general<H, NQ>(ring, mring, k, qry, qrz, acc);
+            const size_t g = ((size_t)k * p.ny + (y0 + qry - 1)) * p.nz + (z0 + qrz - 1);
+            const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + qry * GPZ + qrz;
+#pragma unroll
+            for (int c = 0; c < H; ++c) {
+                p.out[c * p.nloc + g] = acc[c];
+                racc[0] += acc[c] * ctr[c * GTILE];
             }
         }
     }
