@@ -57,7 +57,7 @@ EXPORTS = [
     "fans_set_reference_stiffness", "fans_set_gradient", "fans_get_gradient", "fans_set_mixed_bc", "fans_update_mixed_bc",
     "fans_field_upload", "fans_field_download", "fans_field_zero", "fans_field_copy", "fans_residual", "fans_apply_linear",
     "fans_convolution", "fans_dot", "fans_axpy", "fans_norm", "fans_solve", "fans_homogenized_stress", "fans_commit_history",
-    "fans_extrapolate_displacement", "fans_get_field", "fans_launch_count", "fans_set_profiling", "fans_get_profile",
+    "fans_extrapolate_displacement", "fans_get_field", "fans_strain_stress", "fans_launch_count", "fans_set_profiling", "fans_get_profile",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def load():
     lib.fans_commit_history.argtypes = [P]
     lib.fans_extrapolate_displacement.argtypes = [P]
     lib.fans_get_field.argtypes = [P, C.c_char_p, C.c_void_p, C.c_size_t]
+    lib.fans_strain_stress.argtypes = [P, dp, dp]
     lib.fans_set_profiling.argtypes = [P, C.c_int32]
     lib.fans_get_profile.argtypes = [P, C.c_int32, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_int64)]
     lib.fans_launch_count.argtypes = [P]
@@ -275,6 +276,13 @@ class Context:
 
     def extrapolate_displacement(self):
         self._ck(self.lib.fans_extrapolate_displacement(self.ptr))
+
+    def strain_stress(self):
+        """(strain, stress) element averages from ONE sweep, each [x][y][z][n_str]."""
+        e = np.empty(self.dims + (self.n_str,))
+        s = np.empty(self.dims + (self.n_str,))
+        self._ck(self.lib.fans_strain_stress(self.ptr, _dptr(e), _dptr(s)))
+        return e, s
 
     def get_field(self, name):
         nx, ny, nz = self.dims

@@ -712,6 +712,38 @@ extern "C" int fans_extrapolate_displacement(fans_ctx *ctx)
 // ------------------------------------------------------------------------------------------------
 // postprocess data sources
 // ------------------------------------------------------------------------------------------------
+extern "C" int fans_strain_stress(fans_ctx *ctx, double *strain_host, double *stress_host)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const size_t N = ctx->nloc;
+    const int ns = ctx->nstr;
+    FANS_CHECK(ensure_field(ctx, FANS_FIELD_U));
+    double *de = nullptr, *ds = nullptr;
+    if (strain_host) CUDA_TRY(ctx, cudaMalloc(&de, sizeof(double) * ns * N));
+    if (stress_host && cudaMalloc(&ds, sizeof(double) * ns * N) != cudaSuccess) {
+        cudaFree(de);
+        fans_set_error(ctx, FANS_ERR_CUDA, "fans_strain_stress: out of device memory");
+        return FANS_ERR_CUDA;
+    }
+    int rc = sweep_run(ctx, SWEEP_STRAINSTRESS, ctx->field[FANS_FIELD_U], nullptr, nullptr, nullptr, nullptr, nullptr, de, ds);
+    if (rc == FANS_OK) {
+        std::vector<double> tmp((size_t)ns * N);
+        for (int pass = 0; pass < 2; ++pass) {
+            double *src = pass == 0 ? de : ds, *o = pass == 0 ? strain_host : stress_host;
+            if (!o) continue;
+            cudaMemcpyAsync(tmp.data(), src, sizeof(double) * ns * N, cudaMemcpyDeviceToHost, ctx->st);
+            cudaStreamSynchronize(ctx->st);
+            for (int i = 0; i < ns; ++i)
+                for (size_t v = 0; v < N; ++v) o[v * ns + i] = tmp[i * N + v];
+        }
+        rc = check_fault(ctx);
+    }
+    cudaFree(de);
+    cudaFree(ds);
+    return rc;
+}
+
 extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t bytes)
 {
     if (!ctx || !name || !dst) return FANS_ERR_ARG;
@@ -726,23 +758,8 @@ extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t
         return true;
     };
     if (n == "strain" || n == "stress") {
-        const int ns = ctx->nstr;
-        if (!need(sizeof(double) * ns * N)) return FANS_ERR_ARG;
-        double *de = nullptr, *ds = nullptr;
-        CUDA_TRY(ctx, cudaMalloc(&de, sizeof(double) * ns * N));
-        CUDA_TRY(ctx, cudaMalloc(&ds, sizeof(double) * ns * N));
-        int rc = sweep_run(ctx, SWEEP_STRAINSTRESS, ctx->field[FANS_FIELD_U], nullptr, nullptr, nullptr, nullptr, nullptr, de, ds);
-        std::vector<double> tmp((size_t)ns * N);
-        if (rc == FANS_OK) {
-            cudaMemcpyAsync(tmp.data(), n == "strain" ? de : ds, sizeof(double) * ns * N, cudaMemcpyDeviceToHost, ctx->st);
-            cudaStreamSynchronize(ctx->st);
-            double *o = (double *)dst;
-            for (int i = 0; i < ns; ++i)
-                for (size_t v = 0; v < N; ++v) o[v * ns + i] = tmp[i * N + v];
-        }
-        cudaFree(de);
-        cudaFree(ds);
-        return rc;
+        if (!need(sizeof(double) * ctx->nstr * N)) return FANS_ERR_ARG;
+        return n == "strain" ? fans_strain_stress(ctx, (double *)dst, nullptr) : fans_strain_stress(ctx, nullptr, (double *)dst);
     }
     if (n == "plastic_flag") {
         if (!ctx->pflag) {

@@ -159,6 +159,10 @@ int fans_extrapolate_displacement(fans_ctx *ctx);                           /* e
  *   "plastic_strain","kinematic_hardening_variable"   double [x][y][z][6], "isotropic_hardening_variable" double [x][y][z]
  *   "fundamental_solution"       double [y_local][x][kz][h*(h+1)/2]  natural frequency order (debug / tests) */
 int fans_get_field(fans_ctx *ctx, const char *name, void *host_dst, size_t bytes);
+/* ONE getStrainStress sweep (the loop of Solver::postprocess, solver.h:497-530): element-averaged strain and stress,
+ * each double [x][y][z][n_str]; either pointer may be NULL.  Like the reference's sweep it calls the material law once per
+ * Gauss point, with the same side effects on the history variables (J2Plasticity.h:103-104). */
+int fans_strain_stress(fans_ctx *ctx, double *strain_host, double *stress_host);
 
 /* per-kernel-class device timing (CUDA events on the library's stream). cls = 0.. until *name is "" */
 int fans_set_profiling(fans_ctx *ctx, int32_t on);  /* resets the accumulators */

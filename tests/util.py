@@ -80,3 +80,61 @@ THERMAL = [{"phases": [0, 1], "matmodel": "LinearThermalIsotropic", "material_pr
 ELASTIC = [{"phases": [0, 1], "matmodel": "LinearElasticIsotropic",
             "material_properties": {"bulk_modulus": [62.5, 222.222], "shear_modulus": [28.8462, 166.6667]}}]
 EP = {"measure": "Linfinity", "type": "absolute", "tolerance": 1e-10}
+
+
+def run_gpu_load_cases(ms, cfg, max_steps=None, on_step=None):
+    """Python mirror of runSolver (src/main.cpp:9-46) + MixedBCController::activate (mixedBCs.h:180-226) driving the
+    CUDA library through its C ABI.  Returns (per load case -> per step dict) like fans_oracle.run_load_cases."""
+    problem = cfg["problem_type"]
+    strain_type = cfg.get("strain_type", "small")
+    n_str = 3 if problem == "thermal" else (9 if strain_type == "large" else 6)
+    ep = cfg["error_parameters"]
+    ls = cfg.get("linesearch_parameters", {})
+    results = []
+    for entry in cfg["macroscale_loading"]:
+        # the oracle object is used here ONLY as a parameter parser (phase descriptors, kapparef): n_it=0, never solved
+        par = fo.OracleSolver(ms, cfg["microstructure"]["L"], problem, cfg["materials"], cfg.get("FE_type", "HEX8"), cfg["method"],
+                              strain_type, ep, 0, None, cfg.get("reference_material"))
+        ctx = ctx_from_oracle(par)
+        mbc = None
+        if isinstance(entry, dict):
+            mbc = fo.MixedBC(entry["strain_indices"], entry["stress_indices"], entry.get("strain", []), entry.get("stress", []), n_str)
+            mbc.finalize(par.kapparef)
+            n_steps = mbc.n_steps
+        else:
+            n_steps = len(entry)
+        g0_vec = g0_prev = None
+        steps = []
+        for t in range(n_steps if max_steps is None else min(n_steps, max_steps)):
+            if mbc is not None:
+                if t == 0:
+                    g0_vec = np.zeros(n_str)
+                    if n_str == 9:
+                        g0_vec[[0, 4, 8]] = 1.0
+                    g0_prev = g0_vec.copy()
+                else:
+                    g0_vec = ctx.get_gradient()
+                    delta = g0_vec - g0_prev
+                    g0_prev = g0_vec.copy()
+                    for k in mbc.idx_F:
+                        g0_vec[k] += delta[k]
+                for i, k in enumerate(mbc.idx_E):
+                    g0_vec[k] = mbc.F_E_path[t, i]
+                ctx.set_gradient(g0_vec)
+                ctx.set_mixed_bc(mbc.idx_F, mbc.M, mbc.P_F_path[t] if mbc.idx_F else [])
+                ctx.update_mixed_bc()
+            else:
+                ctx.set_mixed_bc(None)
+                ctx.set_gradient(np.asarray(entry[t], dtype=np.float64))
+            r = ctx.solve(cfg["method"], cfg["n_it"], ep["tolerance"], ep["measure"], ep["type"], ls.get("max_iter", 5), ls.get("tol", 1e-2))
+            res = {"iters": r["iters"], "err_all": r["err_all"], "g0": ctx.get_gradient(), "n_residual_evals": r["n_residual_evals"]}
+            if on_step is not None:
+                on_step(ctx, len(results), t, res)
+            else:
+                res["stress_average"] = ctx.homogenized_stress()
+            steps.append(res)
+            if cfg.get("extrapolate_displacement", True):
+                ctx.extrapolate_displacement()
+        results.append(steps)
+        last = ctx
+    return results, last
