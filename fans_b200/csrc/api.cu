@@ -305,8 +305,9 @@ static int create_rest(fans_ctx *ctx)
 
     ctx->kzc = ctx->nz / 2 + 1;
     ctx->kzp = (ctx->kzc + 7) / 8 * 8;
-    ctx->gT = (ctx->h == 1) ? 8 : 4;
-    while ((size_t)ctx->h * ctx->nx * ctx->gT * sizeof(double2) > 200 * 1024 && ctx->gT > 1) ctx->gT /= 2;
+    ctx->gT = fft_x_tile_width(ctx->nx, ctx->h);
+    ctx->yT = (ctx->ny >= 512) ? 4 : 8;
+    if (const char *e = getenv("FANS_YT")) ctx->yT = (atoi(e) == 4) ? 4 : 8;
     FANS_CHECK(fft_plan_init(ctx, ctx->planx, ctx->nx, ctx->nx));
     FANS_CHECK(fft_plan_init(ctx, ctx->plany, ctx->ny, ctx->ny));
     FANS_CHECK(fft_plan_init(ctx, ctx->planz, ctx->nz / 2, ctx->nz));
@@ -817,6 +818,7 @@ extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
         double *o = (double *)dst;  // natural order [ky][kx][kz][NG]
         const size_t NT = (size_t)ctx->nx * T;
+        const int E = ctx->nx < 8 ? ctx->nx : 8, TPC = ctx->nx / E;
         for (int ky = 0; ky < ctx->ny; ++ky) {
             const int py = ctx->plany.pos_host[ky];
             if (py < ctx->y1 || py >= ctx->y1 + ctx->n1) continue;
@@ -826,7 +828,7 @@ extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t
                     const int tile = kz / T, t = kz % T;
                     for (int k = 0; k < NG; ++k)
                         o[(((size_t)ky * ctx->nx + kx) * ctx->kzc + kz) * NG + k] =
-                            tmp[((((size_t)(py - ctx->y1)) * nTiles + tile) * NG + k) * NT + (size_t)px * T + t];
+                            tmp[((((size_t)(py - ctx->y1)) * nTiles + tile) * NG + k) * NT + ((size_t)(px % E) * TPC + px / E) * T + t];
                 }
             }
         }

@@ -37,12 +37,6 @@ struct FftPlan {
     std::vector<int> pos_host;
 };
 
-// stage descriptor passed by value to the kernels
-struct FftStages {
-    int N, logN, nst, twmul;  // twmul = ntab / N
-    int radix[8];
-};
-
 struct PhaseDev {  // device copy of one fans_phase_desc (params trimmed)
     int    model, local_mat, group_n_mat, k_index;  // k_index: slot of the phase stiffness in the K table (linear) or -1
     const double *tangent;                          // linear phases: device pointer to C (n_str x n_str, row-major)
@@ -69,7 +63,9 @@ struct fans_ctx {
     int kzc = 0, kzp = 0;      // nz/2+1 and padded pitch (complex elements)
     double2 *spec = nullptr;   // [h][n0][ny][kzp]   (P==1)   /   transposed [h][n1][nx][kzp] (P>1)
     double *gamma = nullptr;   // tile-major layout, see gamma.cu
+    double2 *specB = nullptr;  // P > 1: the transposed spectrum (this rank's y rows, all x), blocks [p][h][n0][n1][kzp]
     int gT = 4;                // kz tile width of the fused x pass
+    int yT = 8;                // kz tile width of the y passes
     FftPlan planx, plany, planz;  // planz: half-length complex plan of the r2c/c2r transform (N = nz/2)
     bool gamma_ready = false;
 

@@ -1,0 +1,177 @@
+// fft_z.cu — passes P1 / P5 of the convolution (include/solver.h:387-412): r2c and c2r along z, the contiguous axis.
+//   P1  a real line of nz doubles is read as Nh = nz/2 complex numbers, transformed by the register FFT and untangled:
+//         E = (Z_k + conj Z_{Nh-k})/2, D = (Z_k - conj Z_{Nh-k})/2, w = exp(-2 pi i k/nz):  X_k = E - i w D,  X_{Nh-k} = conj(E + i w D)
+//   P5  the mirror image (unnormalised like FFTW's c2r) with a fused epilogue:  out = scale * x  and  red = <dotw, out>
+//       (s = -Gamma r and delta = <r, s> of SolverCG, include/solverCG.h:88-92, cost no extra pass over HBM).
+// One line is carried by Nh/8 threads (one warp for nz = 512); a CTA holds 256/(Nh/8) lines.  Global loads/stores go
+// straight from/to registers, fully coalesced along z.
+#include "fft_reg.cuh"
+#include "internal.h"
+
+struct LineIdx {  // padded line: +1 slot per 8 rows, +1 per 64 rows -> conflict-free stage exchanges and untangle
+    __device__ __forceinline__ int operator()(int row) const { return row + (row >> 3) + (row >> 6); }
+};
+__host__ __device__ constexpr int zline_pitch(int NH) { return NH + NH / 8 + NH / 64 + 2; }
+__host__ __device__ constexpr int z_tpl(int NH) { return NH / rp_elems(NH); }
+__host__ __device__ constexpr int z_lpb(int NH) { return z_tpl(NH) >= 256 ? 1 : 256 / z_tpl(NH); }
+
+__device__ __forceinline__ size_t spec_line(const SpecGeom &g, int ny, size_t line)
+{
+    const int y = (int)(line % ny);
+    const size_t r = line / ny;
+    const int xl = (int)(r % g.n0), c = (int)(r / g.n0);
+    return (size_t)c * g.cStride + (size_t)(y >> g.l2n1) * g.blkStride + ((size_t)xl * g.n1 + (y & (g.n1 - 1))) * g.kzp;
+}
+
+template <int NH>
+__global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zf(const double *__restrict__ real, double2 *__restrict__ spec,
+                                                                  const double2 *__restrict__ tw, const int *__restrict__ pos,
+                                                                  SpecGeom g, int ny, size_t nlines)
+{
+    extern __shared__ double2 sm[];
+    constexpr int E = rp_elems(NH), TPL = z_tpl(NH), LPB = z_lpb(NH), NST = rp_nstages(NH), PITCH = zline_pitch(NH);
+    const int l = threadIdx.x / TPL, jt = threadIdx.x % TPL;
+    const size_t line = (size_t)blockIdx.x * LPB + l;
+    const bool valid = line < nlines;
+    double2 *sml = sm + l * PITCH;
+    const LineIdx idx;
+    double2 a[1][E];
+    const double2 *in = reinterpret_cast<const double2 *>(real) + line * NH;
+#pragma unroll
+    for (int e = 0; e < E; ++e) a[0][e] = valid ? in[rp_row<NH, 0>(jt, e)] : make_double2(0.0, 0.0);
+    rp_forward<NH, 1>(a, jt, sml, 0, idx, tw, 2);  // table length nz = 2 Nh
+    if (NST > 1) __syncthreads();
+    rp_put<NH, NST - 1>(a[0], jt, sml, idx);
+    __syncthreads();
+    if (!valid) return;
+    double2 *out = spec + spec_line(g, ny, line);
+    for (int k = jt; k <= NH / 2; k += TPL) {
+        const double2 A = sml[idx(__ldg(&pos[k]))];
+        const double2 Bc = sml[idx(__ldg(&pos[(NH - k) & (NH - 1)]))];
+        const double2 B = make_double2(Bc.x, -Bc.y);
+        const double2 Ev = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y + B.y));
+        const double2 D = make_double2(0.5 * (A.x - B.x), 0.5 * (A.y - B.y));
+        const double2 wd = rc_mul(__ldg(&tw[k]), D);  // w D ;  i w D = (-wd.y, wd.x)
+        out[NH - k] = make_double2(Ev.x - wd.y, -(Ev.y + wd.x));  // conj(E + i w D)
+        out[k] = make_double2(Ev.x + wd.y, Ev.y - wd.x);          // E - i w D   (for k = Nh/2 both coincide; this one wins)
+    }
+}
+
+template <int NH>
+__global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zi(const double2 *__restrict__ spec, double *__restrict__ real,
+                                                                  const double2 *__restrict__ tw, const int *__restrict__ pos,
+                                                                  SpecGeom g, int ny, size_t nlines, double scale,
+                                                                  const double *__restrict__ dotw, double *part,
+                                                                  unsigned int *ticket, double *red_out)
+{
+    extern __shared__ double2 sm[];
+    __shared__ double scratch[32];
+    constexpr int E = rp_elems(NH), TPL = z_tpl(NH), LPB = z_lpb(NH), NST = rp_nstages(NH), PITCH = zline_pitch(NH);
+    const int l = threadIdx.x / TPL, jt = threadIdx.x % TPL;
+    const size_t line = (size_t)blockIdx.x * LPB + l;
+    const bool valid = line < nlines;
+    double2 *sml = sm + l * PITCH;
+    const LineIdx idx;
+    if (valid) {
+        const double2 *in = spec + spec_line(g, ny, line);
+        for (int k = jt; k <= NH / 2; k += TPL) {
+            const double2 A = in[k];
+            const double2 Bc = in[NH - k];
+            const double2 B = make_double2(Bc.x, -Bc.y);
+            const double2 Ev = rc_add(A, B), D = rc_sub(A, B);
+            const double2 wd = rc_mulc(D, __ldg(&tw[k]));  // cw D with cw = conj(w_k)
+            if (k > 0) sml[idx(__ldg(&pos[NH - k]))] = make_double2(Ev.x + wd.y, -(Ev.y - wd.x));  // conj(E - i cw D)
+            sml[idx(__ldg(&pos[k]))] = make_double2(Ev.x - wd.y, Ev.y + wd.x);                      // E + i cw D
+        }
+    } else {
+        for (int k = jt; k < NH; k += TPL) sml[idx(k)] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    double2 a[1][E];
+    rp_get<NH, NST - 1>(a[0], jt, sml, idx);
+    rp_inverse<NH, 1>(a, jt, sml, 0, idx, tw, 2);
+    double acc[1] = {0.0};
+    if (valid) {
+        double2 *out = reinterpret_cast<double2 *>(real) + line * NH;
+        const double2 *dw = dotw ? reinterpret_cast<const double2 *>(dotw) + line * NH : nullptr;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int row = rp_row<NH, 0>(jt, e);
+            double2 v = a[0][e];
+            v.x *= scale;
+            v.y *= scale;
+            if (dw) {
+                const double2 r = dw[row];
+                acc[0] += r.x * v.x + r.y * v.y;
+            }
+            out[row] = v;
+        }
+    }
+    if (red_out) grid_reduce<1, 1>(acc, scratch, part, ticket, red_out);
+}
+
+template <int NH>
+static int launch_zf(fans_ctx *ctx, const double *in, const SpecGeom &g, size_t nlines)
+{
+    constexpr int LPB = z_lpb(NH), NTHR = z_tpl(NH) * LPB;
+    const size_t smem = sizeof(double2) * zline_pitch(NH) * LPB;
+    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_zf<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fft_zf<NH><<<(unsigned)((nlines + LPB - 1) / LPB), NTHR, smem, ctx->st>>>(in, ctx->spec, ctx->planz.tw, ctx->planz.pos, g, ctx->ny, nlines);
+    return FANS_OK;
+}
+template <int NH>
+static int launch_zi(fans_ctx *ctx, double *out, const SpecGeom &g, size_t nlines, double scale, const double *dotw, double *red_out)
+{
+    constexpr int LPB = z_lpb(NH), NTHR = z_tpl(NH) * LPB;
+    const size_t smem = sizeof(double2) * zline_pitch(NH) * LPB;
+    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_zi<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fft_zi<NH><<<(unsigned)((nlines + LPB - 1) / LPB), NTHR, smem, ctx->st>>>(ctx->spec, out, ctx->planz.tw, ctx->planz.pos, g, ctx->ny, nlines,
+                                                                              scale, dotw, ctx->d_part, ctx->d_ticket, red_out);
+    return FANS_OK;
+}
+
+#define Z_SWITCH(CALL)                                                                                          \
+    switch (ctx->nz / 2) {                                                                                      \
+    case 2: rc = CALL(2); break;                                                                                \
+    case 4: rc = CALL(4); break;                                                                                \
+    case 8: rc = CALL(8); break;                                                                                \
+    case 16: rc = CALL(16); break;                                                                              \
+    case 32: rc = CALL(32); break;                                                                              \
+    case 64: rc = CALL(64); break;                                                                              \
+    case 128: rc = CALL(128); break;                                                                            \
+    case 256: rc = CALL(256); break;                                                                            \
+    case 512: rc = CALL(512); break;                                                                            \
+    default: fans_set_error(ctx, FANS_ERR_ARG, "unsupported n_z for the z pass");                              \
+    }
+
+int fft_pass_z_fwd(fans_ctx *ctx, const double *in)
+{
+    prof_begin(ctx, PC_FFT_Z_FWD);
+    const SpecGeom g = spec_geom_A(ctx);
+    const size_t nlines = (size_t)ctx->h * ctx->n0 * ctx->ny;
+    int rc = FANS_ERR_ARG;
+#define ZF(N_) launch_zf<N_>(ctx, in, g, nlines)
+    Z_SWITCH(ZF)
+#undef ZF
+    prof_end(ctx);
+    ctx->launches++;
+    if (rc != FANS_OK) return rc;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int fft_pass_z_inv(fans_ctx *ctx, double *out, double scale, const double *dotw, double *red_out)
+{
+    prof_begin(ctx, PC_FFT_Z_INV);
+    const SpecGeom g = spec_geom_A(ctx);
+    const size_t nlines = (size_t)ctx->h * ctx->n0 * ctx->ny;
+    int rc = FANS_ERR_ARG;
+#define ZI(N_) launch_zi<N_>(ctx, out, g, nlines, scale, dotw, red_out)
+    Z_SWITCH(ZI)
+#undef ZI
+    prof_end(ctx);
+    ctx->launches++;
+    if (rc != FANS_OK) return rc;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}

@@ -4,7 +4,7 @@
 //   AA = Re A Re A^T + Im A Im A^T ;  block(i,j) = sum(Ker0[8i:8i+8, 8j:8j+8] o AA)
 //   Gamma_hat = pinv(block) with ABSOLUTE singular-value cut 1e-14 (solver.h:89-96,189-191), xi = 0 left zero (:169),
 //   scaled by 1/(nx ny nz) (:198).
-// Stored in the tile-major order the fused x pass streams (fft.cu, k_fft_x_gamma) and in the
+// Stored in the tile-major, register-ordered layout the fused x pass streams (fft_x.cu, k_fft_xg) and in the
 // digit-reversed frequency order the DIF transforms produce along x and y.
 #include "common.cuh"
 
@@ -57,7 +57,7 @@ __device__ __forceinline__ void jacobi_pinv3(double a[3][3], double tol, double 
 template <int H>
 __global__ void k_build_gamma(double *__restrict__ gamma, const double *__restrict__ Ker0, const int *__restrict__ frqx,
                               const int *__restrict__ frqy, int nx, int ny, int nz, int n1, int y1, int kzc, int T,
-                              int nTiles, double invN)
+                              int nTiles, double invN, int E)
 {
     constexpr int NG = H * (H + 1) / 2;
     const size_t NT = (size_t)nx * T;
@@ -67,7 +67,9 @@ __global__ void k_build_gamma(double *__restrict__ gamma, const double *__restri
         const size_t ot = idx / NT;
         const int tile = (int)(ot % nTiles);
         const int o = (int)(ot / nTiles);
-        const int row = i / T, t = i % T;
+        // register order of the fused x pass (fft_x.cu): i = (e*(nx/E) + jt)*T + t, storage row = jt*E + e
+        const int t = i % T, qq = i / T, TPC = nx / E;
+        const int row = (qq % TPC) * E + qq / TPC;
         const int kz = tile * T + t;
         double g[NG];
 #pragma unroll
@@ -130,10 +132,10 @@ int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const in
     const double invN = 1.0 / ((double)ctx->nx * (double)ctx->ny * (double)ctx->nz);
     if (ctx->h == 1)
         k_build_gamma<1><<<(unsigned)nb, nthr, 0, ctx->st>>>(ctx->gamma, Ker0_dev, frqx, frqy, ctx->nx, ctx->ny, ctx->nz, ctx->n1, ctx->y1,
-                                                           ctx->kzc, T, nTiles, invN);
+                                                           ctx->kzc, T, nTiles, invN, ctx->nx < 8 ? ctx->nx : 8);
     else
         k_build_gamma<3><<<(unsigned)nb, nthr, 0, ctx->st>>>(ctx->gamma, Ker0_dev, frqx, frqy, ctx->nx, ctx->ny, ctx->nz, ctx->n1, ctx->y1,
-                                                           ctx->kzc, T, nTiles, invN);
+                                                           ctx->kzc, T, nTiles, invN, ctx->nx < 8 ? ctx->nx : 8);
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());

@@ -10,6 +10,9 @@ int  fft_pass_z_fwd(fans_ctx *ctx, const double *in);
 int  fft_pass_y(fans_ctx *ctx, bool inverse);
 int  fft_pass_x_gamma(fans_ctx *ctx);
 int  fft_pass_z_inv(fans_ctx *ctx, double *out, double scale, const double *dotw, double *red_out);
+int  fft_x_tile_width(int nx, int h);
+struct SpecGeom;
+SpecGeom spec_geom_A(const fans_ctx *ctx);
 
 // gamma.cu
 int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const int *frqy);
