@@ -51,8 +51,10 @@ int fft_plan_init(fans_ctx *ctx, FftPlan &p, int N, int ntab)
         tw[ntab / 4] = make_double2(0.0, -1.0);
         tw[3 * ntab / 4] = make_double2(0.0, 1.0);
     }
-    CUDA_TRY(ctx, cudaMalloc(&p.tw, sizeof(double2) * ntab));
-    CUDA_TRY(ctx, cudaMemcpy(p.tw, tw.data(), sizeof(double2) * ntab, cudaMemcpyHostToDevice));
+    tw.resize(2 * (size_t)ntab);  // second half: conjugates, read by the inverse transforms (fft_reg.cuh, rp_stage)
+    for (int i = 0; i < ntab; ++i) tw[ntab + i] = make_double2(tw[i].x, -tw[i].y);
+    CUDA_TRY(ctx, cudaMalloc(&p.tw, sizeof(double2) * 2 * ntab));
+    CUDA_TRY(ctx, cudaMemcpy(p.tw, tw.data(), sizeof(double2) * 2 * ntab, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMalloc(&p.pos, sizeof(int) * N));
     CUDA_TRY(ctx, cudaMemcpy(p.pos, p.pos_host.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
     return FANS_OK;

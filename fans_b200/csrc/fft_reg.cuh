@@ -90,12 +90,15 @@ __device__ __forceinline__ int rp_row(int tid, int e)
     return ((q >> logM) << logL) + (q & (M - 1)) + (k << logM);
 }
 
-// butterflies + twiddles of stage S on the registers.  tw: table of exp(-2 pi i n / ntab), twmul = ntab / N.
+// butterflies + twiddles of stage S on the registers.  tw: table of exp(-2 pi i n / ntab) followed by its conjugate, twmul = ntab / N.
 template <int N, int S, bool INV>
 __device__ __forceinline__ void rp_stage(double2 *a, int tid, const double2 *__restrict__ tw, int twmul)
 {
     constexpr int R = rp_radix(N, S), L = rp_L(N, S), M = L / R, NB = rp_elems(N) / R;
     const int tws = twmul * (N / L);
+    // The inverse reads the CONJUGATE half of the table (tw[ntab + n] = conj(tw[n])): were both directions to share the
+    // same loads, the compiler would keep every twiddle of the forward transform alive (spilled) until the inverse needs it.
+    if (INV) tw += twmul * N;
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         double2 *b = a + i * R;
@@ -116,7 +119,7 @@ __device__ __forceinline__ void rp_stage(double2 *a, int tid, const double2 *__r
         }
         if (INV && M > 1) {
 #pragma unroll
-            for (int m = 1; m < R; ++m) b[m] = rc_mulc(b[m], w[m]);
+            for (int m = 1; m < R; ++m) b[m] = rc_mul(b[m], w[m]);
         }
         if (R == 8) rdft8<INV>(b);
         else if (R == 4) rdft4<INV>(b[0], b[1], b[2], b[3]);

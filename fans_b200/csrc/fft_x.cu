@@ -1,7 +1,7 @@
 // fft_x.cu — pass P3 of the convolution (include/solver.h:395-409): forward transform along x, the Fourier-space
 // fundamental-solution multiply  r_hat <- Gamma_hat(xi) r_hat  (solver.h:399-406) and the inverse transform along x, fused:
-// all `howmany` components of a (y, kz-tile) pencil live in the registers of one CTA, so the h x h real-symmetric multiply
-// happens between the last forward butterfly and the first inverse butterfly without touching shared or global memory.
+// all `howmany` components of a (y, kz-tile) pencil are held by one CTA (registers + thread-private shared-memory slots), so the
+// h x h real-symmetric multiply happens between the last forward butterfly and the first inverse butterfly, off HBM.
 // Gamma_hat is streamed once per iteration in exactly the register order of the threads (gamma.cu writes it that way):
 //     gamma[((cta*NG + k) * (N/E) * E + e*(N/E) + jt) * T + t],   storage row = jt*E + e,   NG = H(H+1)/2 upper triangle.
 #include "fft_reg.cuh"
@@ -18,46 +18,61 @@ struct TileIdxX {
     }
 };
 
+// minimum resident CTAs per SM the register budget is tuned for (threads per CTA = H*(N/E)*T)
+__host__ __device__ constexpr int xg_min_blocks(int nthr) { return nthr > 512 ? 1 : (nthr > 256 ? 2 : 3); }
+
 template <int N, int H, int T>
-__global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T <= 256 && H == 3) ? 2 : 1)
+__global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (N / rp_elems(N)) * T))
     k_fft_xg(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles)
 {
+    // One thread group per component: every thread carries E points of ONE component through the stages (32 data registers),
+    // the H groups share the barriers.  At the Fourier-space boundary the groups swap their values through thread-private
+    // slots of the (then idle) exchange tiles and each group forms its own row of  Gamma_hat r_hat.
     extern __shared__ double2 sm[];
-    constexpr int E = rp_elems(N), TPC = N / E, NST = rp_nstages(N), NG = H * (H + 1) / 2;
-    const int t = threadIdx.x % T, jt = threadIdx.x / T;
+    constexpr int E = rp_elems(N), TPC = N / E, NST = rp_nstages(N), NG = H * (H + 1) / 2, NTC = TPC * T;
+    const int c = threadIdx.x / NTC, tc = threadIdx.x % NTC;
+    const int t = tc % T, jt = tc / T;
     const int tile = blockIdx.x % nTiles, yl = blockIdx.x / nTiles;
-    double2 *base = spec + (size_t)yl * g.kzp + (size_t)tile * T + t;
+    double2 *base = spec + (size_t)c * g.cStride + (size_t)yl * g.kzp + (size_t)tile * T + t;
     const double *gam = gamma + (size_t)blockIdx.x * NG * (N * T) + jt * T + t;
     const TileIdxX<T> idx{t};
-    double2 a[H][E];
+    double2 *X = sm + c * (N * T);
+    double2 a[1][E];
 #pragma unroll
-    for (int c = 0; c < H; ++c)
+    for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_x(g, rp_row<N, 0>(jt, e))];
+    rp_forward<N, 1>(a, jt, X, 0, idx, tw, 1);
+    // Green operator; storage row of register e after the last stage = jt*E + e
+    if (H == 1) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) a[c][e] = base[(size_t)c * g.cStride + spec_row_x(g, rp_row<N, 0>(jt, e))];
-    rp_forward<N, H>(a, jt, sm, N * T, idx, tw, 1);
-    // Green operator on the registers (storage row of register e after the last stage = jt*E + e)
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const double *ge = gam + (size_t)e * TPC * T;
-        if (H == 1) {
-            const double g0 = __ldg(ge);
+        for (int e = 0; e < E; ++e) {
+            const double g0 = __ldg(gam + (size_t)e * NTC);
             a[0][e] = make_double2(g0 * a[0][e].x, g0 * a[0][e].y);
-        } else {
-            constexpr size_t NT = (size_t)N * T;
-            const double g00 = __ldg(ge), g01 = __ldg(ge + NT), g02 = __ldg(ge + 2 * NT);
-            const double g11 = __ldg(ge + 3 * NT), g12 = __ldg(ge + 4 * NT), g22 = __ldg(ge + 5 * NT);
-            const double2 r0 = a[0][e], r1 = a[H > 1 ? 1 : 0][e], r2 = a[H > 2 ? 2 : 0][e];
-            a[0][e] = make_double2(g00 * r0.x + g01 * r1.x + g02 * r2.x, g00 * r0.y + g01 * r1.y + g02 * r2.y);
-            a[H > 1 ? 1 : 0][e] = make_double2(g01 * r0.x + g11 * r1.x + g12 * r2.x, g01 * r0.y + g11 * r1.y + g12 * r2.y);
-            a[H > 2 ? 2 : 0][e] = make_double2(g02 * r0.x + g12 * r1.x + g22 * r2.x, g02 * r0.y + g12 * r1.y + g22 * r2.y);
+        }
+    } else {
+        constexpr size_t NT = (size_t)N * T;
+        // packed upper triangle 00,01,02,11,12,22: row c of the symmetric matrix
+        const int k0 = (c == 0) ? 0 : (c == 1 ? 1 : 2), k1 = (c == 0) ? 1 : (c == 1 ? 3 : 4), k2 = (c == 0) ? 2 : (c == 1 ? 4 : 5);
+        if (NST > 1) __syncthreads();  // everybody is done reading the last exchange
+#pragma unroll
+        for (int e = 0; e < E; ++e) X[e * NTC + tc] = a[0][e];
+        double gc[E][3];  // issued after the put (a[] is dead) so the loads fly while the CTA gathers at the barrier
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const double *ge = gam + (size_t)e * NTC;
+            gc[e][0] = __ldg(ge + k0 * NT);
+            gc[e][1] = __ldg(ge + k1 * NT);
+            gc[e][2] = __ldg(ge + k2 * NT);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const double2 r0 = sm[e * NTC + tc], r1 = sm[(H > 1 ? 1 : 0) * (N * T) + e * NTC + tc], r2 = sm[(H > 2 ? 2 : 0) * (N * T) + e * NTC + tc];
+            a[0][e] = make_double2(gc[e][0] * r0.x + gc[e][1] * r1.x + gc[e][2] * r2.x, gc[e][0] * r0.y + gc[e][1] * r1.y + gc[e][2] * r2.y);
         }
     }
-    rp_inverse<N, H>(a, jt, sm, N * T, idx, tw, 1);
+    rp_inverse<N, 1>(a, jt, X, 0, idx, tw, 1);
 #pragma unroll
-    for (int c = 0; c < H; ++c)
-#pragma unroll
-        for (int e = 0; e < E; ++e) base[(size_t)c * g.cStride + spec_row_x(g, rp_row<N, 0>(jt, e))] = a[c][e];
-    (void)NST;
+    for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
 }
 
 template <int N, int H, int T>
@@ -65,14 +80,14 @@ static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g)
 {
     constexpr int E = rp_elems(N);
     const int nTiles = (ctx->kzc + T - 1) / T;
-    const size_t smem = sizeof(double2) * N * T * H;
-    if (smem > 227 * 1024) {
-        fans_set_error(ctx, FANS_ERR_ARG, "x pass tile does not fit shared memory");
+    const size_t smem = sizeof(double2) * N * T * H;  // one exchange tile per component
+    if (smem > 227 * 1024 || H * (N / E) * T > 1024) {
+        fans_set_error(ctx, FANS_ERR_ARG, "x pass tile does not fit one CTA");
         return FANS_ERR_ARG;
     }
     if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg<N, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((size_t)ctx->n1 * nTiles);
-    k_fft_xg<N, H, T><<<grid, (N / E) * T, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles);
+    k_fft_xg<N, H, T><<<grid, H * (N / E) * T, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles);
     return FANS_OK;
 }
 
@@ -80,7 +95,7 @@ static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g)
 int fft_x_tile_width(int nx, int h)
 {
     int T = (h == 1) ? 8 : 4;
-    while ((size_t)h * nx * T * sizeof(double2) > 100 * 1024 && T > 2) T /= 2;
+    while (((size_t)h * nx * T * sizeof(double2) > 100 * 1024 || h * (nx / 8) * T > 1024) && T > 2) T /= 2;
     return T;
 }
 

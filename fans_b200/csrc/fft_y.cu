@@ -16,7 +16,7 @@ struct TileIdx {  // swizzled [row][t] tile: conflict-free butterflies for T = 4
 };
 
 template <int N, int T, bool INV>
-__global__ void __launch_bounds__((N / rp_elems(N)) * T) k_fft_y(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles)
+__global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T >= 512) ? (1024 / ((N / rp_elems(N)) * T)) : 1) k_fft_y(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles)
 {
     extern __shared__ double2 sm[];
     constexpr int E = rp_elems(N), TPC = N / E, NST = rp_nstages(N);
