@@ -57,7 +57,8 @@ EXPORTS = [
     "fans_set_reference_stiffness", "fans_set_gradient", "fans_get_gradient", "fans_set_mixed_bc", "fans_update_mixed_bc",
     "fans_field_upload", "fans_field_download", "fans_field_zero", "fans_field_copy", "fans_residual", "fans_apply_linear",
     "fans_convolution", "fans_dot", "fans_axpy", "fans_norm", "fans_solve", "fans_homogenized_stress", "fans_commit_history",
-    "fans_extrapolate_displacement", "fans_get_field", "fans_strain_stress", "fans_launch_count", "fans_set_profiling", "fans_get_profile",
+    "fans_extrapolate_displacement", "fans_get_field", "fans_strain_stress", "fans_launch_count", "fans_set_profiling", "fans_get_profile", "fans_comm_unique_id", "fans_comm_create",
+    "fans_comm_destroy",
 ]
 
 _lib = None
@@ -108,6 +109,9 @@ def load():
     lib.fans_strain_stress.argtypes = [P, dp, dp]
     lib.fans_set_profiling.argtypes = [P, C.c_int32]
     lib.fans_get_profile.argtypes = [P, C.c_int32, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_int64)]
+    lib.fans_comm_unique_id.argtypes = [C.c_void_p]
+    lib.fans_comm_create.argtypes = [C.POINTER(P), C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    lib.fans_comm_destroy.argtypes = [P]
     lib.fans_launch_count.argtypes = [P]
     lib.fans_launch_count.restype = C.c_int64
     _lib = lib
@@ -121,22 +125,27 @@ def _dptr(a):
 class Context:
     """One fans_ctx (= one Solver instance on one GPU). Thin, argument-checking wrapper over the C ABI."""
 
-    def __init__(self, dims, L, howmany, n_str, fe_type="HEX8", device=-1):
+    def __init__(self, dims, L, howmany, n_str, fe_type="HEX8", device=-1, comm=None):
+        """dims: GLOBAL grid. comm: fans_b200.dist.SlabComm for world_size > 1 (this rank then owns dims[0]/P x-planes;
+        every field / microstructure buffer passed to this object is the rank's slab [n_x/P][n_y][n_z])."""
         self.lib = load()
-        self.dims = tuple(int(d) for d in dims)
+        self.gdims = tuple(int(d) for d in dims)
+        P_, r_ = (comm.world_size, comm.rank) if comm is not None else (1, 0)
+        self.dims = (self.gdims[0] // P_,) + self.gdims[1:]
         self.h, self.n_str = int(howmany), int(n_str)
         cfg = Config()
-        cfg.dims[:] = self.dims
+        cfg.dims[:] = self.gdims
         cfg.L[:] = [float(x) for x in L]
         cfg.howmany, cfg.n_str = self.h, self.n_str
         if fe_type not in FE:
             raise FansError("Unknown FE_type: '%s'. Supported types: HEX8, HEX8R, BBAR" % fe_type)
         cfg.fe_type = FE[fe_type]
-        cfg.world_size, cfg.world_rank = 1, 0
-        cfg.local_n0, cfg.local_0_start = self.dims[0], 0
-        cfg.local_n1, cfg.local_1_start = self.dims[1], 0
+        cfg.world_size, cfg.world_rank = P_, r_
+        cfg.local_n0, cfg.local_0_start = self.gdims[0] // P_, r_ * (self.gdims[0] // P_)
+        cfg.local_n1, cfg.local_1_start = self.gdims[1] // P_, r_ * (self.gdims[1] // P_)
         cfg.device = device
-        cfg.nccl_comm = None
+        cfg.nccl_comm = comm.handle if comm is not None else None
+        self.comm = comm
         cfg.stream = None
         self.n_gp = 1 if fe_type == "HEX8R" else 8
         self.ptr = C.c_void_p()
@@ -294,8 +303,8 @@ class Context:
             out = np.empty((nx, ny, nz, 6))
         elif name == "isotropic_hardening_variable":
             out = np.empty((nx, ny, nz))
-        elif name == "fundamental_solution":
-            out = np.empty((ny, nx, nz // 2 + 1, self.h * (self.h + 1) // 2))
+        elif name == "fundamental_solution":  # global frequency grid; only this rank's y rows are filled when world_size > 1
+            out = np.zeros((ny, self.gdims[0], nz // 2 + 1, self.h * (self.h + 1) // 2))
         else:
             raise FansError("unknown field " + name)
         self._ck(self.lib.fans_get_field(self.ptr, name.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))

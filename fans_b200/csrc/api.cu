@@ -53,7 +53,7 @@ void prof_resolve(fans_ctx *ctx)
 
 static const char *PROF_NAMES[FANS_PROF_CLASSES] = {"fft_z_fwd", "fft_y_fwd", "fft_x_gamma", "fft_y_inv", "fft_z_inv", "sweep_linear",
                                                     "sweep_residual", "sweep_strainstress", "cg_update", "reduce", "axpy", "other",
-                                                    "", "", "", ""};
+                                                    "comm_alltoall", "comm_halo", "comm_scalars", ""};
 
 extern "C" int fans_set_profiling(fans_ctx *ctx, int32_t on)
 {
@@ -262,9 +262,13 @@ extern "C" int fans_create(fans_ctx **out, const fans_config *cfg)
         if (n < 4 || (n & (n - 1)) != 0 || n > 2048)
             return fail(FANS_ERR_ARG, "grid dimensions must be powers of two in [4, 2048] (got " + std::to_string(n) + ")");
     }
-    if (ctx->P != 1) return fail(FANS_ERR_ARG, "world_size > 1: use the slab entry points (multi-GPU build)");
-    if (ctx->n0 != ctx->nx || ctx->x0 != 0 || ctx->n1 != ctx->ny || ctx->y1 != 0)
-        return fail(FANS_ERR_ARG, "single-rank context must own the whole grid");
+    // slab sizes as fftw_mpi_local_size_many_transposed hands them out for these grids (src/reader.cpp:311-331)
+    if ((ctx->P & (ctx->P - 1)) != 0 || ctx->nx % ctx->P != 0 || ctx->ny % ctx->P != 0)
+        return fail(FANS_ERR_ARG, "world_size must be a power of two dividing n_x and n_y");
+    if (ctx->rank < 0 || ctx->rank >= ctx->P) return fail(FANS_ERR_ARG, "world_rank out of range");
+    if (ctx->n0 != ctx->nx / ctx->P || ctx->x0 != ctx->rank * ctx->n0 || ctx->n1 != ctx->ny / ctx->P || ctx->y1 != ctx->rank * ctx->n1)
+        return fail(FANS_ERR_ARG, "slab sizes must be local_n0 = n_x/P at rank*local_n0 and local_n1 = n_y/P at rank*local_n1");
+    if (ctx->P > 1 && ctx->nx / 4 < ctx->P) return fail(FANS_ERR_ARG, "[ FANS3D_Grid ] ERROR: Number of processes too large");  // reader.cpp:306
     ctx->ngp = (ctx->fe == FANS_FE_HEX8R) ? 1 : 8;
     for (int d = 0; d < 3; ++d) {
         ctx->L[d] = cfg->L[d];
@@ -286,7 +290,8 @@ extern "C" int fans_create(fans_ctx **out, const fans_config *cfg)
         if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) return fail(FANS_ERR_CUDA, "cudaStreamCreate failed");
         ctx->own_stream = true;
     }
-    const int rc = create_rest(ctx);
+    int rc = comm_check(ctx);
+    if (rc == FANS_OK) rc = create_rest(ctx);
     if (rc != FANS_OK) {
         g_create_error = ctx->err;
         fans_destroy(ctx);
@@ -318,11 +323,17 @@ static int create_rest(fans_ctx *ctx)
     const size_t spec_elems = (size_t)ctx->h * ctx->n0 * ctx->ny * ctx->kzp;
     CUDA_TRY(ctx, cudaMalloc(&ctx->spec, sizeof(double2) * spec_elems));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec, 0, sizeof(double2) * spec_elems, ctx->st));
+    if (ctx->P > 1) {  // the transposed spectrum: this rank's y rows for all x
+        CUDA_TRY(ctx, cudaMalloc(&ctx->specB, sizeof(double2) * spec_elems));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->specB, 0, sizeof(double2) * spec_elems, ctx->st));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->ms_lo, sizeof(uint16_t) * ctx->ny * ctx->nz));
+    }
 
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * (1 << 20)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_red, sizeof(double) * S_COUNT));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_red, 0, sizeof(double) * S_COUNT, ctx->st));
     CUDA_TRY(ctx, cudaMallocHost(&ctx->h_red, sizeof(double) * S_COUNT));
+    CUDA_TRY(ctx, cudaMallocHost(&ctx->h_stage, sizeof(double) * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), ctx->st));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_flag, sizeof(int)));
@@ -342,11 +353,12 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     if (ctx->st) cudaStreamSynchronize(ctx->st);
     for (int f = 0; f < FANS_N_FIELDS; ++f)
         if (ctx->field[f]) cudaFree(ctx->field[f]);
-    void *ptrs[] = {ctx->d_alt, ctx->stage_io, ctx->ms, ctx->phidx, ctx->spec, ctx->gamma, ctx->d_phase, ctx->d_K, ctx->phase_lut,
+    void *ptrs[] = {ctx->specB, ctx->ms_lo, ctx->halo_send_lo, ctx->halo_send_hi, ctx->halo_lo, ctx->halo_hi, ctx->d_alt, ctx->stage_io, ctx->ms, ctx->phidx, ctx->spec, ctx->gamma, ctx->d_phase, ctx->d_K, ctx->phase_lut,
                     ctx->hist, ctx->hist_t, ctx->pflag, ctx->d_part, ctx->d_red, ctx->d_ticket, ctx->d_flag, ctx->d_C};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     fft_plan_free(ctx->planx);
     fft_plan_free(ctx->plany);
     fft_plan_free(ctx->planz);
@@ -376,6 +388,10 @@ extern "C" int fans_set_microstructure(fans_ctx *ctx, const uint16_t *ms)
     }
     if (!ctx->phidx) CUDA_TRY(ctx, cudaMalloc(&ctx->phidx, sizeof(uint16_t) * ctx->nloc));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->phidx, ms, sizeof(uint16_t) * ctx->nloc, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->P > 1) {  // phases of element plane -1 (the previous rank's last plane) for the gather-form stencil
+        const size_t plane = (size_t)ctx->ny * ctx->nz;
+        FANS_CHECK(comm_halo(ctx, nullptr, nullptr, ctx->phidx + (size_t)(ctx->n0 - 1) * plane, ctx->ms_lo, sizeof(uint16_t) * plane));
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     ctx->ms_ready = true;
     return FANS_OK;
@@ -687,9 +703,9 @@ extern "C" int fans_norm(fans_ctx *ctx, int32_t f, int32_t measure, double *out)
     FANS_CHECK(ensure_field(ctx, f));
     FANS_CHECK(vec_reduce4(ctx, ctx->field[f], nullptr, ctx->d_red + S_GEN));
     FANS_CHECK(read_scalars(ctx));
-    if (measure == FANS_MEASURE_L1) *out = ctx->h_red[S_GEN];
-    else if (measure == FANS_MEASURE_L2) *out = std::sqrt(ctx->h_red[S_GEN + 1]);
-    else if (measure == FANS_MEASURE_LINF) *out = ctx->h_red[S_GEN + 3];
+    if (measure == FANS_MEASURE_L1) *out = ctx->h_red[S_GENMAX];
+    else if (measure == FANS_MEASURE_L2) *out = std::sqrt(ctx->h_red[S_GENMAX + 1]);
+    else if (measure == FANS_MEASURE_LINF) *out = ctx->h_red[S_GENMAX + 3];
     else {
         fans_set_error(ctx, FANS_ERR_ARG, "Unknown measure type");
         return FANS_ERR_ARG;

@@ -59,6 +59,10 @@ struct fans_ctx {
     uint16_t *ms = nullptr;    // [n0][ny][nz]
     uint16_t *phidx = nullptr;  // phase id per voxel on the device (== ms values, validated < n_phases), [n0][ny][nz]
 
+    // slab halos (world_size > 1): one node plane [h][ny][nz] each; ms_lo = phases of element plane -1
+    double *halo_send_lo = nullptr, *halo_send_hi = nullptr, *halo_lo = nullptr, *halo_hi = nullptr;
+    uint16_t *ms_lo = nullptr;
+
     // spectrum + Green operator
     int kzc = 0, kzp = 0;      // nz/2+1 and padded pitch (complex elements)
     double2 *spec = nullptr;   // [h][n0][ny][kzp]   (P==1)   /   transposed [h][n1][nx][kzp] (P>1)
@@ -100,6 +104,7 @@ struct fans_ctx {
     double *d_part = nullptr;   // per-block partial sums
     double *d_red = nullptr;    // reduced scalars (device)
     double *h_red = nullptr;    // pinned host mirror
+    double *h_stage = nullptr;  // pinned host->device staging scalar
     unsigned int *d_ticket = nullptr;
     int neg_jac_flag_host = 0;
     int *d_flag = nullptr;      // sticky device fault flag (J <= 0)
@@ -121,7 +126,7 @@ void fans_set_error(fans_ctx *ctx, int code, const std::string &msg);
 
 // kernel classes for profiling (index into prof_ms / prof_n); names in api.cu
 enum { PC_FFT_Z_FWD = 0, PC_FFT_Y_FWD, PC_FFT_X_GAMMA, PC_FFT_Y_INV, PC_FFT_Z_INV, PC_SWEEP_LINEAR, PC_SWEEP_RESIDUAL,
-       PC_SWEEP_STRAINSTRESS, PC_CG_UPDATE, PC_REDUCE, PC_AXPY, PC_OTHER };
+       PC_SWEEP_STRAINSTRESS, PC_CG_UPDATE, PC_REDUCE, PC_AXPY, PC_OTHER, PC_COMM_A2A, PC_COMM_HALO, PC_COMM_SCALAR };
 void prof_begin(fans_ctx *ctx, int cls);
 void prof_end(fans_ctx *ctx);
 void prof_resolve(fans_ctx *ctx);  // call after a stream synchronisation

@@ -32,6 +32,15 @@ int vec_extrapolate(fans_ctx *ctx, double *u, double *up);
 int vec_aos_to_soa(fans_ctx *ctx, const double *aos, double *soa);
 int vec_soa_to_aos(fans_ctx *ctx, const double *soa, double *aos);
 int vec_scalars_after_conv(fans_ctx *ctx);
+int halo_exchange_both(fans_ctx *ctx, const double *in, const double *s, const double *beta_dev);
+int halo_exchange_up(fans_ctx *ctx, const double *in, const double *s, const double *beta_dev);
+int halo_add_down(fans_ctx *ctx, double *r);
+
+// comm.cu (slab exchanges over NCCL)
+int comm_check(fans_ctx *ctx);
+int comm_allreduce(fans_ctx *ctx, const double *in, double *out, int n, bool is_max);
+int comm_halo(fans_ctx *ctx, const void *to_prev, void *from_next, const void *to_next, void *from_prev, size_t bytes);
+int comm_alltoall(fans_ctx *ctx, const double2 *src, double2 *dst);
 
 // solve.cu
 int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out);

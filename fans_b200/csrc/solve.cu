@@ -24,8 +24,9 @@ int read_scalars(fans_ctx *ctx)
 
 static int write_scalar(fans_ctx *ctx, int slot, double v)
 {
-    ctx->h_red[S_COUNT - 1] = v;  // pinned staging slot (never read back from the device)
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_red + slot, &ctx->h_red[S_COUNT - 1], sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->h_stage[0] = v;  // pinned staging slot
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_red + slot, ctx->h_stage, sizeof(double), cudaMemcpyHostToDevice, ctx->st));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     return FANS_OK;
 }
@@ -39,9 +40,12 @@ int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const d
     }
     FANS_CHECK(fft_pass_z_fwd(ctx, in));
     FANS_CHECK(fft_pass_y(ctx, false));
+    if (ctx->P > 1) FANS_CHECK(comm_alltoall(ctx, ctx->spec, ctx->specB));  // x-slabs -> y-slabs (FFTW_MPI_TRANSPOSED_OUT)
     FANS_CHECK(fft_pass_x_gamma(ctx));
+    if (ctx->P > 1) FANS_CHECK(comm_alltoall(ctx, ctx->specB, ctx->spec));  // back (FFTW_MPI_TRANSPOSED_IN)
     FANS_CHECK(fft_pass_y(ctx, true));
     FANS_CHECK(fft_pass_z_inv(ctx, out, scale, dotw, red_out));
+    if (red_out && ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, red_out, red_out, 1, false));
     return FANS_OK;
 }
 
@@ -69,7 +73,7 @@ static int compute_error(fans_ctx *ctx, const double *r, ErrState &es, double *e
 {
     FANS_CHECK(vec_reduce4(ctx, r, nullptr, ctx->d_red + S_GEN));
     FANS_CHECK(read_scalars(ctx));
-    *err_out = error_from_scalars(ctx, es, S_GEN);
+    *err_out = error_from_scalars(ctx, es, S_GENMAX);
     return FANS_OK;
 }
 
@@ -79,6 +83,7 @@ static int homogenized_stress(fans_ctx *ctx, double *out)
     FANS_CHECK(ensure_fields(ctx, {FANS_FIELD_U}));
     FANS_CHECK(sweep_run(ctx, SWEEP_STRAINSTRESS, ctx->field[FANS_FIELD_U], nullptr, nullptr, nullptr, nullptr, ctx->d_red + S_STRESS,
                          nullptr, nullptr));
+    if (ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, ctx->d_red + S_STRESS, ctx->d_red + S_STRESS, ctx->nstr, false));  // solver.h:733
     FANS_CHECK(read_scalars(ctx));
     const double N = (double)ctx->nx * ctx->ny * ctx->nz;
     for (int i = 0; i < ctx->nstr; ++i) out[i] = ctx->h_red[S_STRESS + i] / N;
@@ -172,7 +177,7 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
             FANS_CHECK(vec_cg_update(ctx, r, rnew, u, d_new, s));                // r,u update + norms + deltamid
             FANS_CHECK(read_scalars(ctx));
             es.iter++;
-            err_rel = error_from_scalars(ctx, es, S_L1);
+            err_rel = error_from_scalars(ctx, es, S_ERRMAX);
         } else {
             double *d = ctx->field[FANS_FIELD_D];
             // deltamid = <r,s> (solverCG.h:86)

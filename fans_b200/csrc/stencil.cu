@@ -10,7 +10,7 @@
 // Data movement: a CTA owns an (8 x 64) node column and marches along x with a 4-slot shared-memory ring of node
 // planes (one-node halo in y,z), so every d value is read from HBM once per CTA column (halo re-reads hit L2) and the
 // fused update d = s + beta*d is formed on the fly while loading.  One __syncthreads per plane.
-#include "common.cuh"
+#include "internal.h"
 #include "materials.cuh"
 #include "stencil.h"
 
@@ -41,6 +41,9 @@ struct StencilParams {
     double *part;
     unsigned int *ticket;
     double *red_out;       // <d_new, K d_new>
+    // slab decomposition (world_size > 1): node planes -1 and n0 and element plane -1 come from the neighbour ranks
+    const double *halo_lo, *halo_hi;   // [H][ny*nz], already the UPDATED direction (no s/beta combination)
+    const uint16_t *ms_lo;             // [ny*nz] phases of element plane -1
 };
 
 __device__ __forceinline__ int gwrap(int v, int n)
@@ -174,13 +177,23 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
         const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
         double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
         double v[NLD][H];
+        const double *hal = (p.halo_lo && xp < 0) ? p.halo_lo : ((p.halo_hi && xp >= p.n0) ? p.halo_hi : nullptr);
+        if (hal) {
 #pragma unroll
-        for (int j = 0; j < NLD; ++j)
-            if (goff[j] >= 0) {
+            for (int j = 0; j < NLD; ++j)
+                if (goff[j] >= 0) {
 #pragma unroll
-                for (int cc = 0; cc < H; ++cc) v[j][cc] = p.d_old[cc * p.nloc + gbase + goff[j]];
-            }
-        if (p.s) {
+                    for (int cc = 0; cc < H; ++cc) v[j][cc] = hal[cc * plane_sz + goff[j]];
+                }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NLD; ++j)
+                if (goff[j] >= 0) {
+#pragma unroll
+                    for (int cc = 0; cc < H; ++cc) v[j][cc] = p.d_old[cc * p.nloc + gbase + goff[j]];
+                }
+        }
+        if (p.s && !hal) {
             double sv[NLD][H];
 #pragma unroll
             for (int j = 0; j < NLD; ++j)
@@ -206,11 +219,11 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
             }
     };
     auto load_ms = [&](int xp) {
-        const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
+        const uint16_t *src = (p.ms_lo && xp < 0) ? p.ms_lo : p.phidx + (size_t)gwrap(xp, p.n0) * plane_sz;
         uint16_t *mp = mring + ((xp + 3) % 3) * GETILE;
 #pragma unroll
         for (int j = 0; j < NLM; ++j)
-            if (moff[j] >= 0) mp[tid + j * G_THREADS] = p.phidx[gbase + moff[j]];
+            if (moff[j] >= 0) mp[tid + j * G_THREADS] = src[moff[j]];
     };
 
     load_plane(xs - 1, false);
@@ -333,6 +346,11 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     p.phidx = ctx->phidx;
     p.nq = ctx->n_k;
     p.part = ctx->d_part, p.ticket = ctx->d_ticket, p.red_out = red_out;
+    if (ctx->P > 1) {
+        // halo planes of the UPDATED direction: pack planes 0 / n0-1 (forming s + beta d on the fly), ring exchange
+        FANS_CHECK(halo_exchange_both(ctx, d_old, s_in, beta_dev));
+        p.halo_lo = ctx->halo_lo, p.halo_hi = ctx->halo_hi, p.ms_lo = ctx->ms_lo;
+    }
     const int gy = (ctx->ny + GY - 1) / GY, gz = (ctx->nz + GZ - 1) / GZ;
     int xchunk = ctx->n0;
     while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < 48L * FANS_SMS) xchunk = (xchunk + 1) / 2;
@@ -352,5 +370,6 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
         return rc;
     }
     CUDA_TRY(ctx, cudaGetLastError());
+    if (red_out && ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, red_out, red_out, 1, false));
     return FANS_OK;
 }

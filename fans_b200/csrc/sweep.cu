@@ -11,7 +11,7 @@
 //   (c) each node thread gathers its 4 contributions of this element plane, adds the 4 carried in registers from the
 //       previous plane, writes the node force (coalesced along z) and keeps the next carry.
 // The assembly order is fixed => bitwise reproducible results.  Halo voxels are re-read from shared memory only.
-#include "common.cuh"
+#include "internal.h"
 #include "materials.cuh"
 
 #define TY 8
@@ -50,6 +50,9 @@ struct SweepParams {
     double *red_out;         // SW_LINEAR: <in_new, out>;  SW_STRAINSTRESS: sum of element stress (n_str values)
     // strain/stress output (optional)
     double *eps_out, *sig_out;   // [n_str][nloc] element averages
+    // slab decomposition (world_size > 1), scatter form across the slab boundary like the reference (solver.h:244-269):
+    const double *in_hi;         // node plane n0 of the input (= plane 0 of the next rank), [H][ny*nz], final values
+    double *out_hi;              // contributions of this rank's last element plane to node plane n0 (sent to the next rank)
 };
 
 __device__ __forceinline__ int wrapi(int v, int n)
@@ -109,14 +112,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
     // ---- plane loader: node plane xp (periodic in x) into ring slot `slot`
     auto load_plane = [&](int xp, int slot, bool owned_plane) {
         const int xg = wrapi(xp, p.n0);
+        const bool hal = p.in_hi && xp >= p.n0;
         for (int i = tid; i < NTILE; i += SWEEP_THREADS) {
             const int ry = i / (TZ + 2), rz = i % (TZ + 2);
             const int y = wrapi(y0 - 1 + ry, p.ny), z = wrapi(z0 - 1 + rz, p.nz);
             const size_t g = ((size_t)xg * p.ny + y) * p.nz + z;
 #pragma unroll
             for (int c = 0; c < H; ++c) {
-                double v = p.in[c * p.nloc + g];
-                if (MODE == SW_LINEAR && p.in2) {
+                double v = hal ? p.in_hi[(size_t)c * p.ny * p.nz + (size_t)y * p.nz + z] : p.in[c * p.nloc + g];
+                if (MODE == SW_LINEAR && p.in2 && !hal) {
                     v = p.in2[c * p.nloc + g] + beta * v;
                     if (owned_plane && ry >= 1 && ry <= TY && rz >= 1 && rz <= TZ && (y0 - 1 + ry) < p.ny && (z0 - 1 + rz) < p.nz)
                         p.in_out[c * p.nloc + g] = v;
@@ -135,7 +139,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
 #pragma unroll
         for (int c = 0; c < H; ++c) u0[c] = 0.0;
         // strain/stress sweeps only evaluate owned elements (no assembly => no halo elements, no plane xs-1)
-        const bool do_el = has_el && (MODE != SW_STRAINSTRESS || (own_valid && x >= xs));
+        // world_size > 1: element plane -1 belongs to the previous rank, which sends its contributions instead
+        const bool skip_lo = p.in_hi && x < 0;
+        const bool do_el = has_el && !skip_lo && (MODE != SW_STRAINSTRESS || (own_valid && x >= xs));
+        if (skip_lo && has_el && MODE != SW_STRAINSTRESS) {
+#pragma unroll
+            for (int i = 0; i < ND; ++i) stg[i * NELT + eidx] = 0.0;
+        }
         if (do_el) {
             // gather the 8 nodes: local node i = bx + 2 by + 4 bz  (include/solver.h:333-340)
             double ue[ND];
@@ -330,6 +340,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
         }
         lo ^= 1;
     }
+    if (MODE != SW_STRAINSTRESS && p.out_hi && xe == p.n0 && own_valid) {
+#pragma unroll
+        for (int c = 0; c < H; ++c) p.out_hi[(size_t)c * p.ny * p.nz + (size_t)ey * p.nz + ez] = carry[c];
+    }
     if (p.red_out) {
         if constexpr (MODE == SW_STRAINSTRESS) grid_reduce<NSTR, NSTR>(racc, scratch, p.part, p.ticket, p.red_out);
         else if constexpr (MODE == SW_LINEAR) grid_reduce<1, 1>(racc, scratch, p.part, p.ticket, p.red_out);
@@ -383,6 +397,14 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     FANS_CHECK(upload_constants(ctx));
     SweepParams p;
     memset(&p, 0, sizeof(p));
+    double *red_final = nullptr;
+    if (ctx->P > 1) {
+        // upper halo of the (updated) input; the K.d dot product is formed after the boundary contributions have been added
+        FANS_CHECK(halo_exchange_up(ctx, in, mode == SW_LINEAR ? s_in : nullptr, beta_dev));
+        p.in_hi = ctx->halo_hi;
+        p.out_hi = ctx->halo_send_hi;
+        if (mode == SW_LINEAR) red_final = red_out, red_out = nullptr;
+    }
     p.n0 = ctx->n0;
     p.ny = ctx->ny;
     p.nz = ctx->nz;
@@ -417,16 +439,25 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
     const size_t smem = sizeof(double) * (2 * ctx->h * NTILE + 8 * ctx->h * NELT);
-#define SW_DISPATCH(H_, N_)                                                                  \
-    do {                                                                                     \
-        if (mode == SW_LINEAR) return launch_sweep<H_, N_, SW_LINEAR>(ctx, p, grid, smem);   \
-        if (mode == SW_RESIDUAL) return launch_sweep<H_, N_, SW_RESIDUAL>(ctx, p, grid, smem); \
-        return launch_sweep<H_, N_, SW_STRAINSTRESS>(ctx, p, grid, smem);                    \
+    int rc = FANS_ERR_ARG;
+#define SW_DISPATCH(H_, N_)                                                                       \
+    do {                                                                                          \
+        if (mode == SW_LINEAR) rc = launch_sweep<H_, N_, SW_LINEAR>(ctx, p, grid, smem);          \
+        else if (mode == SW_RESIDUAL) rc = launch_sweep<H_, N_, SW_RESIDUAL>(ctx, p, grid, smem); \
+        else rc = launch_sweep<H_, N_, SW_STRAINSTRESS>(ctx, p, grid, smem);                      \
     } while (0)
     if (ctx->h == 1 && ctx->nstr == 3) SW_DISPATCH(1, 3);
-    if (ctx->h == 3 && ctx->nstr == 6) SW_DISPATCH(3, 6);
-    if (ctx->h == 3 && ctx->nstr == 9) SW_DISPATCH(3, 9);
+    else if (ctx->h == 3 && ctx->nstr == 6) SW_DISPATCH(3, 6);
+    else if (ctx->h == 3 && ctx->nstr == 9) SW_DISPATCH(3, 9);
+    else fans_set_error(ctx, FANS_ERR_ARG, "unsupported (howmany, n_str) combination");
 #undef SW_DISPATCH
-    fans_set_error(ctx, FANS_ERR_ARG, "unsupported (howmany, n_str) combination");
-    return FANS_ERR_ARG;
+    if (rc != FANS_OK) return rc;
+    if (ctx->P > 1 && mode != SW_STRAINSTRESS) {
+        FANS_CHECK(halo_add_down(ctx, out));
+        if (red_final) {  // <d_new, K d_new> over the completed field, summed over the slabs
+            FANS_CHECK(vec_reduce4(ctx, d_new ? d_new : in, out, ctx->d_red + S_GEN));
+            CUDA_TRY(ctx, cudaMemcpyAsync(red_final, ctx->d_red + S_GEN + 2, sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
+        }
+    }
+    return FANS_OK;
 }

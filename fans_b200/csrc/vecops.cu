@@ -2,8 +2,7 @@
 // Replaces the Eigen array expressions of SolverCG::internalSolve / LineSearchSecant (include/solverCG.h:86-107,
 // 119-160), SolverFP::internalSolve (include/solverFP.h:46), Solver::compute_error (include/solver.h:414-431) and
 // Solver::extrapolateDisplacement (include/solver.h:302-311).  All fields are flat SoA arrays of h*nloc doubles.
-#include "common.cuh"
-#include "scalars.h"
+#include "internal.h"
 
 #define VEC_THREADS 256
 
@@ -125,7 +124,74 @@ __global__ void k_scalars_after_conv(double *S)
     S[S_BETA] = fmax(0.0, (delta - S[S_DELTAMID]) / delta0);
 }
 
+// slab halos: planes 0 and n0-1 of every component of  v = s ? s + beta*in : in  into contiguous send buffers [h][plane]
+__global__ void k_pack_planes(const double *__restrict__ in, const double *__restrict__ s, const double *__restrict__ beta_dev,
+                              size_t nloc, size_t plane, int n0, int h, double *__restrict__ out_lo, double *__restrict__ out_hi)
+{
+    const double beta = s ? *beta_dev : 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < plane * h; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / plane, o = i % plane;
+        const size_t g0 = c * nloc + o, g1 = c * nloc + (size_t)(n0 - 1) * plane + o;
+        if (out_lo) out_lo[i] = s ? s[g0] + beta * in[g0] : in[g0];
+        if (out_hi) out_hi[i] = s ? s[g1] + beta * in[g1] : in[g1];
+    }
+}
+// r(plane 0) += contribution of the previous rank's last element plane (solver.h:267-269)
+__global__ void k_add_plane0(double *__restrict__ r, const double *__restrict__ add, size_t nloc, size_t plane, int h)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < plane * h; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / plane, o = i % plane;
+        r[c * nloc + o] += add[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
+static int ensure_halo_buffers(fans_ctx *ctx)
+{
+    if (ctx->halo_send_lo) return FANS_OK;
+    const size_t bytes = sizeof(double) * ctx->h * ctx->ny * ctx->nz;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->halo_send_lo, bytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->halo_send_hi, bytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->halo_lo, bytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->halo_hi, bytes));
+    return FANS_OK;
+}
+
+// both neighbours get a plane of v = s ? s + beta*in : in  (gather-form stencil): fills ctx->halo_lo / halo_hi
+int halo_exchange_both(fans_ctx *ctx, const double *in, const double *s, const double *beta_dev)
+{
+    FANS_CHECK(ensure_halo_buffers(ctx));
+    const size_t plane = (size_t)ctx->ny * ctx->nz;
+    k_pack_planes<<<vec_grid(plane * ctx->h), VEC_THREADS, 0, ctx->st>>>(in, s, beta_dev, ctx->nloc, plane, ctx->n0, ctx->h, ctx->halo_send_lo,
+                                                                         ctx->halo_send_hi);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return comm_halo(ctx, ctx->halo_send_lo, ctx->halo_hi, ctx->halo_send_hi, ctx->halo_lo, sizeof(double) * ctx->h * plane);
+}
+
+// only the upper halo (node plane n0 = the next rank's plane 0), like the reference's u exchange (solver.h:244-245)
+int halo_exchange_up(fans_ctx *ctx, const double *in, const double *s, const double *beta_dev)
+{
+    FANS_CHECK(ensure_halo_buffers(ctx));
+    const size_t plane = (size_t)ctx->ny * ctx->nz;
+    k_pack_planes<<<vec_grid(plane * ctx->h), VEC_THREADS, 0, ctx->st>>>(in, s, beta_dev, ctx->nloc, plane, ctx->n0, ctx->h, ctx->halo_send_lo, nullptr);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return comm_halo(ctx, ctx->halo_send_lo, ctx->halo_hi, nullptr, nullptr, sizeof(double) * ctx->h * plane);
+}
+
+// scatter-form assembly across the slab boundary: send the contributions to node plane n0 (ctx->halo_send_hi, written by the
+// sweep) to the next rank and add what the previous rank sent into plane 0 (solver.h:264-269)
+int halo_add_down(fans_ctx *ctx, double *r)
+{
+    const size_t plane = (size_t)ctx->ny * ctx->nz;
+    FANS_CHECK(comm_halo(ctx, nullptr, nullptr, ctx->halo_send_hi, ctx->halo_lo, sizeof(double) * ctx->h * plane));
+    k_add_plane0<<<vec_grid(plane * ctx->h), VEC_THREADS, 0, ctx->st>>>(r, ctx->halo_lo, ctx->nloc, plane, ctx->h);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
 int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const double *d, const double *s)
 {
     prof_begin(ctx, PC_CG_UPDATE);
@@ -135,6 +201,9 @@ int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const d
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    // error norms: MAX over the slabs for every measure (solver.h:430);  deltamid = <r,s>: SUM (solverCG.h:57)
+    FANS_CHECK(comm_allreduce(ctx, ctx->d_red + S_L1, ctx->d_red + S_ERRMAX, 4, true));
+    if (ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, ctx->d_red + S_DELTAMID, ctx->d_red + S_DELTAMID, 1, false));
     return FANS_OK;
 }
 
@@ -146,6 +215,10 @@ int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    if (out_dev == ctx->d_red + S_GEN) {  // norms: MAX over the slabs (solver.h:430); dot product: SUM (solverCG.h:57)
+        FANS_CHECK(comm_allreduce(ctx, out_dev, ctx->d_red + S_GENMAX, 4, true));
+        if (ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, out_dev + 2, out_dev + 2, 1, false));
+    }
     return FANS_OK;
 }
 

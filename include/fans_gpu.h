@@ -77,7 +77,7 @@ typedef struct {
     int32_t fe_type;       /* FANS_FE_* */
     int32_t world_size;    /* number of x-slabs (ranks) */
     int32_t world_rank;
-    int32_t local_n0;      /* x-planes owned, starting at local_0_start   */
+    int32_t local_n0;      /* x-planes owned, starting at local_0_start: n_x/world_size at world_rank*local_n0 */
     int32_t local_0_start;
     int32_t local_n1;      /* Fourier-space y-planes owned (transposed layout), starting at local_1_start */
     int32_t local_1_start;
@@ -121,6 +121,14 @@ int  fans_create(fans_ctx **ctx, const fans_config *cfg);
 void fans_destroy(fans_ctx *ctx);
 const char *fans_last_error(const fans_ctx *ctx); /* ctx may be NULL: error of the last failed fans_create */
 int  fans_version(void);
+
+/* ---- slab communicator: replaces MPI_COMM_WORLD of the reference (src/main.cpp:60-61).  One rank per GPU; rank order = slab
+ * order.  fans_comm_unique_id on rank 0, ship the 128 bytes to every rank (MPI_Bcast / torch.distributed / a file), then every
+ * rank calls fans_comm_create and passes the handle in fans_config.nccl_comm.  (An ncclComm_t the host created itself with the
+ * same libnccl is accepted as well.) ---- */
+int fans_comm_unique_id(void *id128 /* out: 128 bytes */);
+int fans_comm_create(void **comm, int32_t n_ranks, int32_t rank, const void *id128, int32_t device /* -1: current */);
+int fans_comm_destroy(void *comm);
 
 /* ---- problem data ---- */
 int fans_set_microstructure(fans_ctx *ctx, const uint16_t *ms);                               /* Solver::ms solver.h:34,121 */
