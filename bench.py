@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the FANS per-iteration solve loop on B200.
 
-Metric (BASELINE.json): CG iterations/s and voxel-DOF updates/s of a 512^3 two-phase linear-elastic CG solve
-(HEX8, sphere inclusion), with the fraction of the measured HBM roofline.  A "step" is ONE CG iteration
-(convolution: 5 FFT passes with the fused Green operator; fused direction update + K.d sweep; fused r/u update + norms).
+Metric (BASELINE.json): voxel-DOF updates/s (and CG iterations/s) of a two-phase linear-elastic CG solve (HEX8, spherical
+inclusion) on 512^3 voxels PER GPU, with the fraction of the measured HBM roofline.  A "step" is ONE CG iteration
+(convolution: 5 FFT passes with the fused Green operator; fused direction update + K.d stencil; fused r/u update + norms).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--size n] [--impl ours|reference]
 
-One JSON line on stdout (rank 0).  `--impl reference` times the CPU restatement of the reference algorithm
-(oracle/) on a bounded sample on the host cores.
+N > 1 (launched by torchrun, one rank per GPU): the grid grows with N (weak scaling, 512^3 voxels per GPU):
+N=2: 1024x512x512, N=4: 1024x1024x512, N=8: 1024^3 (BASELINE config 4's grid), decomposed into x-slabs like the reference.
+One JSON line on stdout (rank 0).  `--impl reference` times the CPU restatement of the reference algorithm (oracle/) on a
+bounded sample on the host cores (the reference itself needs MPI/FFTW/HDF5/Eigen and cannot be built in this image).
 """
 import argparse
 import json
@@ -54,7 +56,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def __enter__(self):
         self.t.start()
@@ -75,7 +77,7 @@ class ClockSampler:
 
 
 def cpu_port_rate(n, iters):
-    """CPU restatement (oracle, NumPy, all host threads NumPy/BLAS uses) timed on an n^3 sample of the same workload."""
+    """CPU restatement (oracle: NumPy/BLAS + scipy.fft on every host thread) timed on an n^3 sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import fans_oracle as fo
     ms = fo.sphere_microstructure(n)
@@ -89,23 +91,38 @@ def cpu_port_rate(n, iters):
     return 3.0 * n ** 3 * sol.iter / dt, sol.iter, dt
 
 
-def run_reference(args):
+def workload_name(dims):
+    return "linear-elastic two-phase ellipsoidal inclusion (semi-axes 0.4 n), CG, HEX8, %dx%dx%d, 1 load case" % tuple(dims)
+
+
+def run_reference(args, dims):
     n = args.ref_size
-    vals = []
     for _ in range(max(1, args.warmup // 3)):
         cpu_port_rate(n, 1)
-    rate, it, dt = cpu_port_rate(n, args.steps)
+    rate, it, dt = cpu_port_rate(n, max(args.steps, 1))
     cores = os.cpu_count()
     line = {"impl": "reference", "metric": "voxel_dof_updates_per_s", "value": rate, "unit": "voxel-DOF/s", "n_gpus": args.gpus,
             "steps": it, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(it, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "linear-elastic two-phase sphere, CG, HEX8, 512^3 (timed on a %d^3 sample of it)" % n},
+            "config": {"workload": workload_name(dims), "sample": "%d^3 sample of it" % n},
             "cg_iterations_per_s": it / dt,
             "cpu_baseline": {"value": rate, "unit": "voxel-DOF/s", "cores": cores, "kind": "port",
-                             "sample": "%d CG iterations on a %d^3 sample, NumPy restatement of the reference (oracle/), not the FANS binary" % (it, n)},
+                             "sample": "%d CG iterations on a %d^3 sample, NumPy/scipy.fft restatement of the reference (oracle/), "
+                                       "not the FANS binary (it needs MPI/FFTW/HDF5/Eigen: unbuildable here)" % (it, n)},
             "e2e": {"value": rate, "unit": "voxel-DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def grid_for(n, gpus):
+    """weak scaling: n^3 voxels per GPU; the grid doubles along x, then y, then z"""
+    dims = [n, n, n]
+    g, ax = gpus, 0
+    while g > 1:
+        dims[ax] *= 2
+        ax = (ax + 1) % 3
+        g //= 2
+    return dims
 
 
 def main():
@@ -120,87 +137,122 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dims = grid_for(args.size, max(world, args.gpus) if args.impl == "reference" else world)
     if args.impl == "reference":
         if rank == 0:
-            run_reference(args)
-        return
-    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
-        if rank == 0:
-            print(json.dumps({"metric": "voxel_dof_updates_per_s", "n_gpus": args.gpus, "error": "multi-GPU slab path not built in this round"}))
+            run_reference(args, dims)
         return
 
     import numpy as np
-    from fans_b200 import simple
+    import torch
+    from fans_b200 import simple, dist as fdist
 
+    comm = fdist.init()
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
     n, K, W = args.size, args.steps, max(args.warmup, 3)
-    ms = simple.sphere_microstructure(n)
-    ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", 0)
+    x0, n0 = fdist.slab(dims[0], world, rank)
+    ms = simple.ellipsoid_microstructure(dims, x0, n0)
+    ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", dev, gdims=dims, comm=comm if world > 1 else None)
     ctx.set_gradient(G0)
-    launches0 = ctx.launch_count()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
     # warm-up: W iterations of a fresh solve (tol = 0 forces exactly n_it iterations)
     ctx.zero("u")
     ctx.solve("cg", W, 0.0, "Linfinity", "absolute")
     ctx.zero("u")
+    barrier()
     l0 = ctx.launch_count()
-    with ClockSampler(0) as cs:
+    with ClockSampler(dev) as cs:
         res = ctx.solve("cg", K, 0.0, "Linfinity", "absolute")
+        barrier()
     l1 = ctx.launch_count()
     assert res["iters"] == K, res
-    t_loop = res["loop_ms"] * 1e-3
-    dof = 3.0 * n ** 3
+    t_loop = max_over_ranks(res["loop_ms"]) * 1e-3   # CUDA events on the library stream around exactly K iterations
+    nvox = float(dims[0]) * dims[1] * dims[2]
+    dof = 3.0 * nvox
     value = dof * K / t_loop
+
     # per-kernel device times (separate, untimed run so the event pairs do not perturb the number above)
     ctx.zero("u")
     ctx.set_profiling(True)
     ctx.solve("cg", max(3, min(K, 5)), 0.0, "Linfinity", "absolute")
     prof = ctx.profile()
     ctx.set_profiling(False)
-    F = 8.0 * 3 * n ** 3
+    nloc = float(n0) * dims[1] * dims[2]
+    F = 8.0 * 3 * nloc
     alg = {"fft_z_fwd": 2 * F, "fft_y_fwd": 2 * F, "fft_x_gamma": 3 * F, "fft_y_inv": 2 * F, "fft_z_inv": 3 * F,
-           "sweep_linear": 4 * F + 2.0 * n ** 3, "cg_update": 7 * F}
+           "sweep_linear": 4 * F + 2.0 * nloc, "cg_update": 7 * F}
     iter_classes = {k: v for k, v in prof.items() if k in alg}
     dom = max(iter_classes, key=lambda k: iter_classes[k][0] / iter_classes[k][1])
     dom_ms = iter_classes[dom][0] / iter_classes[dom][1]
     peaks, which = measured_peaks()
     peak = float(peaks["hbm_gbs"])
     achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
-    iter_gbs = BYTES_PER_VOXEL_ITER_H3 * n ** 3 * K / t_loop / 1e9
+    iter_gbs = BYTES_PER_VOXEL_ITER_H3 * nloc * K / t_loop / 1e9   # per GPU
 
-    # e2e: host buffers in, host buffers out, copies inside the timed region
-    u_host = None
-    ctx.zero("u")
+    # e2e: the reference-facing call sequence with HOST buffers (pinned): microstructure + start field in, K iterations,
+    # homogenized stress + displacement field out; all copies inside the timed region, wall clock, max over ranks
+    u_host = torch.zeros((n0, dims[1], dims[2], 3), dtype=torch.float64, pin_memory=True).numpy()
+    ctx.upload("u", u_host)
+    ctx.solve("cg", 1, 0.0, "Linfinity", "absolute")   # untimed: first-touch of the staging buffer
+    u_host[...] = 0.0
+    barrier()
     t0 = time.perf_counter()
     ctx.set_microstructure(ms)               # H2D: phase image
     ctx.set_gradient(G0)
+    ctx.upload("u", u_host)                  # H2D: start field (Solver::v_u)
     r2 = ctx.solve("cg", K, 0.0, "Linfinity", "absolute")
-    sig = ctx.homogenized_stress()
-    u_host = ctx.download("u")               # D2H: fluctuation field
-    t_e2e = time.perf_counter() - t0
+    sig = ctx.homogenized_stress()           # D2H: n_str doubles
+    ctx.download_into("u", u_host)           # D2H: fluctuation field
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e = dof * r2["iters"] / t_e2e
 
-    line = {"metric": "voxel_dof_updates_per_s", "value": value, "unit": "voxel-DOF/s", "n_gpus": 1, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * t_loop / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "linear-elastic two-phase sphere (r=0.4n), CG, HEX8, %d^3, 1 load case" % n, "grid": [n, n, n],
-                       "l2": "fields (3.2 GB each at 512^3) are far larger than the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the library stream around exactly K iterations (one host poll of the error per iteration included)"},
-            "cg_iterations_per_s": K / t_loop,
-            "hbm_roofline_iteration": {"bytes_per_voxel_iter": BYTES_PER_VOXEL_ITER_H3, "achieved_gbs": iter_gbs, "peak_gbs": peak,
-                                        "frac": iter_gbs / peak, "peak_source": which},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which, "ms_per_launch": dom_ms},
-            "kernel_ms": {k: v[0] / v[1] for k, v in prof.items()},
-            "clocks": cs.summary(),
-            "e2e": {"value": e2e, "unit": "voxel-DOF/s", "h2d_bytes_per_step": ms.nbytes / K, "d2h_bytes_per_step": (u_host.nbytes + sig.nbytes) / K,
-                    "what": "set_microstructure + K CG iterations + homogenized stress + download of u, wall clock"},
-            "gpu_launches": l1 - l0,
-            "homogenized_stress": [float(x) for x in sig]}
-    if not args.no_cpu:
-        rate, it, dt = cpu_port_rate(args.cpu_size, 8)
-        line["cpu_baseline"] = {"value": rate, "unit": "voxel-DOF/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "%d CG iterations on a %d^3 sample of the workload, NumPy restatement (oracle/), %.1f s" % (it, args.cpu_size, dt)}
-    print(json.dumps(line))
+    if rank == 0:
+        line = {"metric": "voxel_dof_updates_per_s", "value": value, "unit": "voxel-DOF/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * t_loop / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(dims), "grid": dims, "voxels_per_gpu": nloc,
+                           "decomposition": "x-slabs, %d plane(s) of %dx%d per GPU" % (n0, dims[1], dims[2]),
+                           "l2": "fields (3.2 GB each per GPU) are far larger than the 126 MB L2; no flush needed",
+                           "timing": "CUDA events on the library stream around exactly K iterations (one host poll of the error per "
+                                     "iteration included), max over ranks, barrier + synchronize on both sides"},
+                "cg_iterations_per_s": K / t_loop,
+                "hbm_roofline_iteration": {"bytes_per_voxel_iter": BYTES_PER_VOXEL_ITER_H3, "achieved_gbs_per_gpu": iter_gbs, "peak_gbs": peak,
+                                            "frac": iter_gbs / peak, "peak_source": which},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": which, "ms_per_launch": dom_ms},
+                "kernel_ms": {k: v[0] / v[1] for k, v in prof.items()},
+                "clocks": cs.summary(),
+                "e2e": {"value": e2e, "unit": "voxel-DOF/s", "h2d_bytes_per_step": world * (ms.nbytes + u_host.nbytes) / K,
+                        "d2h_bytes_per_step": world * (u_host.nbytes + sig.nbytes) / K,
+                        "what": "set_microstructure + upload u + K CG iterations + homogenized stress + download u, pinned host buffers, wall clock"},
+                "gpu_launches": l1 - l0,
+                "homogenized_stress": [float(x) for x in sig]}
+        if not args.no_cpu and world == 1:
+            rate, it, dt = cpu_port_rate(args.cpu_size, 8)
+            line["cpu_baseline"] = {"value": rate, "unit": "voxel-DOF/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "%d CG iterations on a %d^3 sample of the workload, NumPy/scipy.fft restatement (oracle/), %.1f s"
+                                              % (it, args.cpu_size, dt)}
+        print(json.dumps(line))
     ctx.close()
+    comm.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -227,6 +227,12 @@ class Context:
         self._ck(self.lib.fans_field_download(self.ptr, FIELD[field], _dptr(a)))
         return a
 
+    def download_into(self, field, a):
+        """download into a caller-owned (e.g. pinned) C-contiguous float64 array of field_shape"""
+        assert a.shape == self.field_shape and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.fans_field_download(self.ptr, FIELD[field], _dptr(a)))
+        return a
+
     def zero(self, field):
         self._ck(self.lib.fans_field_zero(self.ptr, FIELD[field]))
 

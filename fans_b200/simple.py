@@ -18,6 +18,20 @@ def sphere_microstructure(n, radius_frac=0.4):
     return ms
 
 
+def ellipsoid_microstructure(dims, x0=0, n0=None):
+    """Slab [x0, x0+n0) of the bench image on a dims[0] x dims[1] x dims[2] grid: phase 1 inside the centred ellipsoid with
+    semi-axes 0.4 n_x, 0.4 n_y, 0.4 n_z (the sphere of sphere_microstructure when the grid is a cube)."""
+    nx, ny, nz = dims
+    n0 = nx if n0 is None else n0
+    fx = ((np.arange(nx) - (nx - 1) / 2.0) / (0.4 * nx)) ** 2
+    fy = ((np.arange(ny) - (ny - 1) / 2.0) / (0.4 * ny)) ** 2
+    fz = ((np.arange(nz) - (nz - 1) / 2.0) / (0.4 * nz)) ** 2
+    ms = np.empty((n0, ny, nz), dtype=np.uint16)
+    for i in range(n0):
+        ms[i] = (fx[x0 + i] + fy[:, None] + fz[None, :]) <= 1.0
+    return ms
+
+
 def elastic_tangent(lam, mu):
     k = np.zeros((6, 6))
     k[:3, :3] = lam
@@ -25,12 +39,13 @@ def elastic_tangent(lam, mu):
     return k
 
 
-def linear_elastic_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1):
-    """LinearElasticIsotropic on phases 0..len(bulk)-1; reference stiffness = (max+min)/2 of lambda and mu."""
+def linear_elastic_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1, gdims=None, comm=None):
+    """LinearElasticIsotropic on phases 0..len(bulk)-1; reference stiffness = (max+min)/2 of lambda and mu.
+    ms is this rank's slab; gdims the global grid (defaults to ms.shape)."""
     bulk = np.asarray(bulk, dtype=np.float64)
     mu = np.asarray(shear, dtype=np.float64)
     lam = bulk - (2.0 / 3.0) * mu
-    ctx = L.Context(ms.shape, Lbox, 3, 6, fe_type, device)
+    ctx = L.Context(gdims if gdims is not None else ms.shape, Lbox, 3, 6, fe_type, device, comm)
     descs = []
     for i in range(len(bulk)):
         d = L.PhaseDesc()

@@ -23,6 +23,12 @@ from __future__ import annotations
 import math
 import numpy as np
 
+try:  # same DFT, all host threads (the CPU-baseline leg of bench.py times this path)
+    import scipy.fft as _fft
+    _FFT_KW = {"workers": -1}
+except Exception:  # pragma: no cover
+    _fft, _FFT_KW = np.fft, {}
+
 SQRT_HALF = 7.071067811865476e-01  # include/matmodel.h:288
 
 
@@ -851,13 +857,13 @@ class OracleSolver:
 
     def convolution(self, r):
         """solver.h:387-412 : unnormalised r2c, per-frequency Gamma_hat multiply, unnormalised c2r."""
-        rhat = np.fft.rfftn(r, axes=(0, 1, 2))
+        rhat = _fft.rfftn(r, axes=(0, 1, 2), **_FFT_KW)
         count = self.ny * self.nx * (self.nz // 2 + 1)
         shat = np.einsum("xyzij,xyzj->xyzi", self.gamma_hat, rhat)
         if count % 2 == 1:
             # solver.h:400 integer division drops the last frequency (layout [ky][kx][kz]) -> left as r_hat
             shat[-1, -1, -1] = rhat[-1, -1, -1]
-        return np.fft.irfftn(shat, s=(self.nx, self.ny, self.nz), axes=(0, 1, 2)) * float(self.N)
+        return _fft.irfftn(shat, s=(self.nx, self.ny, self.nz), axes=(0, 1, 2), **_FFT_KW) * float(self.N)
 
     # ---------------- compute_error (solver.h:414-452) -------------------------------------
     def compute_error(self, r):
