@@ -328,6 +328,8 @@ static int create_rest(fans_ctx *ctx)
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->specB, 0, sizeof(double2) * spec_elems, ctx->st));
         CUDA_TRY(ctx, cudaMalloc(&ctx->ms_lo, sizeof(uint16_t) * ctx->ny * ctx->nz));
     }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    FANS_CHECK(comm_map_peers(ctx));
 
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * (1 << 20)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_red, sizeof(double) * S_COUNT));
@@ -351,6 +353,11 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
+    if (ctx->P > 1 && ctx->p2p) {
+        comm_barrier(ctx);  // nobody may still be storing into this rank's spectrum when it is freed
+        cudaStreamSynchronize(ctx->st);
+        comm_unmap_peers(ctx);
+    }
     for (int f = 0; f < FANS_N_FIELDS; ++f)
         if (ctx->field[f]) cudaFree(ctx->field[f]);
     void *ptrs[] = {ctx->specB, ctx->ms_lo, ctx->halo_send_lo, ctx->halo_send_hi, ctx->halo_lo, ctx->halo_hi, ctx->d_alt, ctx->stage_io, ctx->ms, ctx->phidx, ctx->spec, ctx->gamma, ctx->d_phase, ctx->d_K, ctx->phase_lut,

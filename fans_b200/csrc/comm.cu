@@ -17,6 +17,7 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -39,7 +40,7 @@ bool nccl_load()
         g_nccl.err = "libnccl.so.2 lacks nccl" #name;                           \
         return false;                                                           \
     }
-    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(AllReduce) NCCL_SYM(Send) NCCL_SYM(Recv)
+    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(AllReduce) NCCL_SYM(Send) NCCL_SYM(Recv) NCCL_SYM(AllGather)
     NCCL_SYM(GroupStart) NCCL_SYM(GroupEnd) NCCL_SYM(GetErrorString)
 #undef NCCL_SYM
     g_nccl.h = h;
@@ -159,6 +160,80 @@ int comm_alltoall(fans_ctx *ctx, const double2 *src, double2 *dst)
         NCCL_TRY(ctx, g_nccl.Recv(dst + (size_t)from * blk, 2 * blk, ncclDouble, from, c, ctx->st));
     }
     NCCL_TRY(ctx, g_nccl.GroupEnd());
+    prof_end(ctx);
+    return FANS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer-mapped spectrum buffers (fused transpose): every rank maps the A (x-slab) and B (y-slab) spectrum buffers of all
+// other ranks through CUDA IPC, so the last FFT pass before a transpose can store its rows straight into the owner's
+// memory over NVLink / NVSwitch instead of packing + ncclSend/ncclRecv.  The 64-byte handles travel with one ncclAllGather.
+// ------------------------------------------------------------------------------------------------
+int comm_map_peers(fans_ctx *ctx)
+{
+    const int P = ctx->P;
+    for (int q = 0; q < 8; ++q) ctx->peerA[q] = ctx->peerB[q] = nullptr;
+    ctx->peerA[ctx->rank] = ctx->spec;
+    ctx->peerB[ctx->rank] = ctx->specB;
+    ctx->p2p = false;
+    if (P == 1 || P > 8) return FANS_OK;
+    if (const char *e = getenv("FANS_P2P"))
+        if (atoi(e) == 0) return FANS_OK;
+    struct Pair { cudaIpcMemHandle_t a, b; };
+    Pair mine;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&mine.a, ctx->spec));
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&mine.b, ctx->specB));
+    Pair *d_all = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_all, sizeof(Pair) * (P + 1)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_all + P, &mine, sizeof(Pair), cudaMemcpyHostToDevice, ctx->st));
+    NCCL_TRY(ctx, g_nccl.AllGather(d_all + P, d_all, sizeof(Pair), ncclChar, (ncclComm_t)ctx->cfg.nccl_comm, ctx->st));
+    std::vector<Pair> all(P);
+    CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), d_all, sizeof(Pair) * P, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    cudaFree(d_all);
+    bool ok = true;
+    for (int q = 0; q < P && ok; ++q) {
+        if (q == ctx->rank) continue;
+        void *pa = nullptr, *pb = nullptr;
+        if (cudaIpcOpenMemHandle(&pa, all[q].a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pb, all[q].b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            break;
+        }
+        ctx->peerA[q] = (double2 *)pa;
+        ctx->peerB[q] = (double2 *)pb;
+    }
+    // all ranks must agree (a rank that cannot map its peers would deadlock the others at the first barrier)
+    double flag = ok ? 0.0 : 1.0, *d_flag = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_flag, sizeof(double)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    NCCL_TRY(ctx, g_nccl.AllReduce(d_flag, d_flag, 1, ncclDouble, ncclMax, (ncclComm_t)ctx->cfg.nccl_comm, ctx->st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    cudaFree(d_flag);
+    ctx->p2p = (flag == 0.0);
+    if (!ctx->p2p) comm_unmap_peers(ctx);
+    return FANS_OK;
+}
+
+void comm_unmap_peers(fans_ctx *ctx)
+{
+    for (int q = 0; q < 8; ++q) {
+        if (q == ctx->rank) continue;
+        if (ctx->peerA[q]) cudaIpcCloseMemHandle(ctx->peerA[q]);
+        if (ctx->peerB[q]) cudaIpcCloseMemHandle(ctx->peerB[q]);
+        ctx->peerA[q] = ctx->peerB[q] = nullptr;
+    }
+}
+
+// stream-ordered barrier over the slabs: when it completes on this rank's stream, every rank's stream has reached it, i.e.
+// the kernels (and their peer stores) enqueued before it have finished everywhere
+int comm_barrier(fans_ctx *ctx)
+{
+    if (ctx->P == 1) return FANS_OK;
+    prof_begin(ctx, PC_COMM_A2A);
+    NCCL_TRY(ctx, g_nccl.AllReduce(ctx->d_red + S_BARRIER, ctx->d_red + S_BARRIER, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->cfg.nccl_comm, ctx->st));
     prof_end(ctx);
     return FANS_OK;
 }

@@ -68,6 +68,8 @@ struct fans_ctx {
     double2 *spec = nullptr;   // [h][n0][ny][kzp]   (P==1)   /   transposed [h][n1][nx][kzp] (P>1)
     double *gamma = nullptr;   // tile-major layout, see gamma.cu
     double2 *specB = nullptr;  // P > 1: the transposed spectrum (this rank's y rows, all x), blocks [p][h][n0][n1][kzp]
+    double2 *peerA[8], *peerB[8];  // peer-mapped spectrum buffers of every rank (own entry = spec / specB), see comm.cu
+    bool p2p = false;          // fused transposes: FFT passes store straight into the owner's buffer over NVLink
     int gT = 4;                // kz tile width of the fused x pass
     int yT = 8;                // kz tile width of the y passes
     FftPlan planx, plany, planz;  // planz: half-length complex plan of the r2c/c2r transform (N = nz/2)

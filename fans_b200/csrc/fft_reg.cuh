@@ -198,3 +198,19 @@ __device__ __forceinline__ size_t spec_row_x(const SpecGeom &g, int x)
 {
     return (size_t)(x >> g.l2n0) * g.blkStride + (size_t)(x & (g.n0 - 1)) * ((size_t)g.n1 * g.kzp);
 }
+
+// Fused transpose: where the last pass before a transpose stores its rows.  on == 0: locally (blocks of this rank's buffer,
+// exchanged afterwards with ncclSend/ncclRecv); on == 1: straight into the owning rank's buffer (peer-mapped through CUDA
+// IPC, comm.cu), block `me` there -- the data crosses NVLink once, tile by tile, while the other CTAs keep computing.
+struct PeerTable {
+    double2 *p[8];
+    int me, on;
+};
+__device__ __forceinline__ double2 *peer_select(const PeerTable &pt, int q)
+{
+    double2 *sel = pt.p[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+        if (q == i) sel = pt.p[i];
+    return sel;
+}

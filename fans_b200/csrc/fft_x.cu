@@ -23,7 +23,8 @@ __host__ __device__ constexpr int xg_min_blocks(int nthr) { return nthr > 512 ? 
 
 template <int N, int H, int T>
 __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (N / rp_elems(N)) * T))
-    k_fft_xg(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles)
+    k_fft_xg(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,
+             PeerTable peers)
 {
     // One thread group per component: every thread carries E points of ONE component through the stages (32 data registers),
     // the H groups share the barriers.  At the Fourier-space boundary the groups swap their values through thread-private
@@ -71,12 +72,21 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
         }
     }
     rp_inverse<N, 1>(a, jt, X, 0, idx, tw, 1);
+    if (peers.on) {  // plane x belongs to rank x / n0: store it into that rank's x-slab spectrum, block `me`
+        const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)yl * g.kzp + (size_t)tile * T + t;
 #pragma unroll
-    for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
+        for (int e = 0; e < E; ++e) {
+            const int row = rp_row<N, 0>(jt, e);
+            peer_select(peers, row >> g.l2n0)[off + (size_t)(row & (g.n0 - 1)) * ((size_t)g.n1 * g.kzp)] = a[0][e];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
+    }
 }
 
 template <int N, int H, int T>
-static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g)
+static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const PeerTable &peers)
 {
     constexpr int E = rp_elems(N);
     const int nTiles = (ctx->kzc + T - 1) / T;
@@ -87,7 +97,7 @@ static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g)
     }
     if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg<N, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((size_t)ctx->n1 * nTiles);
-    k_fft_xg<N, H, T><<<grid, H * (N / E) * T, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles);
+    k_fft_xg<N, H, T><<<grid, H * (N / E) * T, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, peers);
     return FANS_OK;
 }
 
@@ -106,10 +116,14 @@ int fft_pass_x_gamma(fans_ctx *ctx)
     double2 *specB = ctx->P > 1 ? ctx->specB : ctx->spec;
     int rc = FANS_ERR_ARG;
     const int T = ctx->gT;
+    PeerTable peers;
+    for (int q = 0; q < 8; ++q) peers.p[q] = ctx->peerA[q];
+    peers.me = ctx->rank;
+    peers.on = 0;  // the x pass stays local (in place on the transposed spectrum); the y passes carry both transposes
 #define X_CASE(N_)                                                                                     \
     case N_:                                                                                           \
-        if (ctx->h == 1) rc = (T == 8) ? launch_xg<N_, 1, 8>(ctx, specB, g) : (T == 4 ? launch_xg<N_, 1, 4>(ctx, specB, g) : launch_xg<N_, 1, 2>(ctx, specB, g)); \
-        else rc = (T == 4) ? launch_xg<N_, 3, 4>(ctx, specB, g) : launch_xg<N_, 3, 2>(ctx, specB, g);  \
+        if (ctx->h == 1) rc = (T == 8) ? launch_xg<N_, 1, 8>(ctx, specB, g, peers) : (T == 4 ? launch_xg<N_, 1, 4>(ctx, specB, g, peers) : launch_xg<N_, 1, 2>(ctx, specB, g, peers)); \
+        else rc = (T == 4) ? launch_xg<N_, 3, 4>(ctx, specB, g, peers) : launch_xg<N_, 3, 2>(ctx, specB, g, peers);  \
         break;
     switch (ctx->nx) {
         X_CASE(4) X_CASE(8) X_CASE(16) X_CASE(32) X_CASE(64) X_CASE(128) X_CASE(256) X_CASE(512) X_CASE(1024)

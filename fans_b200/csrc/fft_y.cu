@@ -1,4 +1,6 @@
-// fft_y.cu — passes P2 / P4 of the convolution (include/solver.h:387-412): in-place transform along y of one component,
+// fft_y.cu — passes P2 / P4 of the convolution (include/solver.h:387-412): transform along y of one component (in place on one
+// GPU; with slabs the forward pass PUSHES its rows into the owners' transposed spectrum and the inverse pass PULLS them back over
+// NVLink, which is the x<->y transpose FFTW-MPI performs with MPI all-to-alls),
 // one (component, x plane, kz tile of T columns) per CTA.  Rows are T*16-byte segments of the spectrum, loaded straight
 // into registers (8 independent 16-byte loads per thread in flight), transformed with the register FFT of fft_reg.cuh and
 // stored straight from registers; shared memory is only the inter-stage exchange tile.
@@ -16,7 +18,7 @@ struct TileIdx {  // swizzled [row][t] tile: conflict-free butterflies for T = 4
 };
 
 template <int N, int T, bool INV>
-__global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T >= 512) ? (1024 / ((N / rp_elems(N)) * T)) : 1) k_fft_y(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles)
+__global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T >= 512) ? (1024 / ((N / rp_elems(N)) * T)) : 1) k_fft_y(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles, PeerTable peers)
 {
     extern __shared__ double2 sm[];
     constexpr int E = rp_elems(N), TPC = N / E, NST = rp_nstages(N);
@@ -33,11 +35,29 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T 
 #pragma unroll
         for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_y(g, rp_row<N, 0>(jt, e))];
         rp_forward<N, 1>(a, jt, sm, N * T, idx, tw, 1);
+        if (peers.on) {  // row y belongs to rank y / n1: store it into that rank's transposed spectrum, block `me`
+            const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)xl * g.n1 * g.kzp + (size_t)tile * T + t;
 #pragma unroll
-        for (int e = 0; e < E; ++e) base[spec_row_y(g, rp_row<N, NST - 1>(jt, e))] = a[0][e];
+            for (int e = 0; e < E; ++e) {
+                const int row = rp_row<N, NST - 1>(jt, e);
+                peer_select(peers, row >> g.l2n1)[off + (size_t)(row & (g.n1 - 1)) * g.kzp] = a[0][e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) base[spec_row_y(g, rp_row<N, NST - 1>(jt, e))] = a[0][e];
+        }
     } else {
+        if (peers.on) {  // row y lives in rank (y / n1)'s transposed spectrum, block `me`: pull it over NVLink
+            const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)xl * g.n1 * g.kzp + (size_t)tile * T + t;
 #pragma unroll
-        for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_y(g, rp_row<N, NST - 1>(jt, e))];
+            for (int e = 0; e < E; ++e) {
+                const int row = rp_row<N, NST - 1>(jt, e);
+                a[0][e] = peer_select(peers, row >> g.l2n1)[off + (size_t)(row & (g.n1 - 1)) * g.kzp];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_y(g, rp_row<N, NST - 1>(jt, e))];
+        }
         rp_inverse<N, 1>(a, jt, sm, N * T, idx, tw, 1);
 #pragma unroll
         for (int e = 0; e < E; ++e) base[spec_row_y(g, rp_row<N, 0>(jt, e))] = a[0][e];
@@ -45,7 +65,7 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T 
 }
 
 template <int N, int T>
-static int launch_y(fans_ctx *ctx, bool inverse, const SpecGeom &g)
+static int launch_y(fans_ctx *ctx, bool inverse, const SpecGeom &g, const PeerTable &peers)
 {
     constexpr int E = rp_elems(N);
     const int nTiles = (ctx->kzc + T - 1) / T;
@@ -54,10 +74,10 @@ static int launch_y(fans_ctx *ctx, bool inverse, const SpecGeom &g)
     const int nthr = (N / E) * T;
     if (!inverse) {
         if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fft_y<N, T, false><<<grid, nthr, smem, ctx->st>>>(ctx->spec, ctx->plany.tw, g, nTiles);
+        k_fft_y<N, T, false><<<grid, nthr, smem, ctx->st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers);
     } else {
         if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y<N, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fft_y<N, T, true><<<grid, nthr, smem, ctx->st>>>(ctx->spec, ctx->plany.tw, g, nTiles);
+        k_fft_y<N, T, true><<<grid, nthr, smem, ctx->st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers);
     }
     return FANS_OK;
 }
@@ -83,9 +103,13 @@ int fft_pass_y(fans_ctx *ctx, bool inverse)
     const SpecGeom g = spec_geom_A(ctx);
     int rc = FANS_ERR_ARG;
     const int T = ctx->yT;
+    PeerTable peers;
+    for (int q = 0; q < 8; ++q) peers.p[q] = ctx->peerB[q];
+    peers.me = ctx->rank;
+    peers.on = (ctx->P > 1 && ctx->p2p) ? 1 : 0;  // forward: push rows to their owners; inverse: pull them back
 #define Y_CASE(N_)                                                         \
     case N_:                                                               \
-        rc = (T == 8) ? launch_y<N_, 8>(ctx, inverse, g) : launch_y<N_, 4>(ctx, inverse, g); \
+        rc = (T == 8) ? launch_y<N_, 8>(ctx, inverse, g, peers) : launch_y<N_, 4>(ctx, inverse, g, peers); \
         break;
     switch (ctx->ny) {
         Y_CASE(4) Y_CASE(8) Y_CASE(16) Y_CASE(32) Y_CASE(64) Y_CASE(128) Y_CASE(256) Y_CASE(512) Y_CASE(1024)

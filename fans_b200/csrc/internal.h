@@ -41,6 +41,9 @@ int comm_check(fans_ctx *ctx);
 int comm_allreduce(fans_ctx *ctx, const double *in, double *out, int n, bool is_max);
 int comm_halo(fans_ctx *ctx, const void *to_prev, void *from_next, const void *to_next, void *from_prev, size_t bytes);
 int comm_alltoall(fans_ctx *ctx, const double2 *src, double2 *dst);
+int comm_map_peers(fans_ctx *ctx);
+void comm_unmap_peers(fans_ctx *ctx);
+int comm_barrier(fans_ctx *ctx);
 
 // solve.cu
 int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out);

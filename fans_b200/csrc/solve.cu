@@ -40,12 +40,16 @@ int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const d
     }
     FANS_CHECK(fft_pass_z_fwd(ctx, in));
     FANS_CHECK(fft_pass_y(ctx, false));
-    if (ctx->P > 1) FANS_CHECK(comm_alltoall(ctx, ctx->spec, ctx->specB));  // x-slabs -> y-slabs (FFTW_MPI_TRANSPOSED_OUT)
+    // x-slabs -> y-slabs (FFTW_MPI_TRANSPOSED_OUT) and back (FFTW_MPI_TRANSPOSED_IN).  Fused form: the y / x pass has already
+    // stored its rows into the owners' buffers over NVLink, only a stream-ordered barrier is left; otherwise block all-to-all.
+    if (ctx->P > 1) FANS_CHECK(ctx->p2p ? comm_barrier(ctx) : comm_alltoall(ctx, ctx->spec, ctx->specB));
     FANS_CHECK(fft_pass_x_gamma(ctx));
-    if (ctx->P > 1) FANS_CHECK(comm_alltoall(ctx, ctx->specB, ctx->spec));  // back (FFTW_MPI_TRANSPOSED_IN)
+    if (ctx->P > 1) FANS_CHECK(ctx->p2p ? comm_barrier(ctx) : comm_alltoall(ctx, ctx->specB, ctx->spec));
     FANS_CHECK(fft_pass_y(ctx, true));
     FANS_CHECK(fft_pass_z_inv(ctx, out, scale, dotw, red_out));
     if (red_out && ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, red_out, red_out, 1, false));
+    // fused form: nobody may push the next spectrum into a buffer a peer is still pulling from (the all-reduce above is a barrier)
+    else if (ctx->P > 1 && ctx->p2p) FANS_CHECK(comm_barrier(ctx));
     return FANS_OK;
 }
 

@@ -25,15 +25,17 @@ def _ngpu():
         return 0
 
 
-@pytest.fixture(scope="module", params=[2, 4, 8])
+# (ranks, fused transposes): 1 = the y passes push / pull their rows through peer-mapped memory over NVLink (the product path),
+# 0 = plain ncclSend/ncclRecv block all-to-all (FANS_P2P=0)
+@pytest.fixture(scope="module", params=[(2, 1), (2, 0), (4, 1), (8, 1)], ids=lambda p: "P%d-%s" % (p[0], "fused" if p[1] else "nccl"))
 def run(request, tmp_path_factory):
-    P = request.param
+    P, fused = request.param
     if _ngpu() < P:
         pytest.skip("needs %d GPUs" % P)
-    out = tmp_path_factory.mktemp("mgpu%d" % P)
+    out = tmp_path_factory.mktemp("mgpu%d_%d" % (P, fused))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(P), "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + P), os.path.join(HERE, "mgpu_worker.py"), str(out)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+           "--master-port", str(29500 + 2 * P + fused), os.path.join(HERE, "mgpu_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, FANS_P2P=str(fused)))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return P, str(out)
 
