@@ -1,0 +1,143 @@
+// main.cpp — command-line front end of the GPU build, mirror of the reference's src/main.cpp:9-80:
+//     FANS_gpu input.json results_dir          (reference: mpiexec -n P FANS input.json results.h5)
+// Same JSON input, same load-case x time-step loop (runSolver), same console summary.  Results go through a ResultsSink;
+// libhdf5 is not available in this image, so the sink writes one raw little-endian file per dataset under
+//     results_dir/<dataset>_results/<prefix>/load<L>/time_step<T>/<name>.bin   + results_dir/index.jsonl (name, dtype, dims; "xyz" order)
+// following the reference's HDF5 group layout (include/reader.h:331-351).
+//     FANS_gpu --describe input.json [ms.u16 nx ny nz]   prints what the host derives from the input (no GPU needed).
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "solver.hpp"
+
+using namespace fans;
+
+struct DirSink : ResultsSink {
+    std::string root, dataset;
+    std::ofstream index;
+    DirSink(const std::string &r, const std::string &ds) : root(r), dataset(ds)
+    {
+        mkdirs(root);
+        index.open(root + "/index.jsonl", std::ios::app);
+    }
+    static void mkdirs(const std::string &p)
+    {
+        for (size_t i = 1; i <= p.size(); ++i)
+            if (i == p.size() || p[i] == '/') mkdir(p.substr(0, i).c_str(), 0777);
+    }
+    void write(const std::string &name, int load_idx, int time_idx, const std::string &dtype, const std::vector<size_t> &dims, const void *data,
+               bool is_field) override
+    {
+        const std::string dir = root + dataset + "/load" + std::to_string(load_idx) + "/time_step" + std::to_string(time_idx);
+        mkdirs(dir);
+        size_t n = 1;
+        for (size_t d : dims) n *= d;
+        const size_t esz = dtype == "f64" ? 8 : (dtype == "u16" ? 2 : 4);
+        std::ofstream f(dir + "/" + name + ".bin", std::ios::binary);
+        f.write((const char *)data, (std::streamsize)(n * esz));
+        index << "{\"name\": \"" << name << "\", \"load\": " << load_idx << ", \"time_step\": " << time_idx << ", \"dtype\": \"" << dtype
+              << "\", \"dims\": [";
+        for (size_t i = 0; i < dims.size(); ++i) index << (i ? ", " : "") << dims[i];
+        index << "], \"field\": " << (is_field ? "true" : "false") << ", \"order\": \"xyz\", \"path\": \"" << dir.substr(root.size()) << "/" << name
+              << ".bin\"}\n";
+        index.flush();
+    }
+};
+
+static void load_raw_ms(Reader &reader, const char *file, int nx, int ny, int nz)
+{
+    std::ifstream in(file, std::ios::binary);
+    if (!in) throw std::runtime_error(std::string("cannot open ") + file);
+    std::vector<uint16_t> ms((size_t)nx * ny * nz);
+    in.read((char *)ms.data(), (std::streamsize)(ms.size() * 2));
+    const int d[3] = {nx, ny, nz};
+    reader.SetMicrostructure(d, ms.data());
+}
+
+static int describe(Reader &reader)
+{
+    MaterialManager mm(reader);
+    printf("{\"howmany\": %d, \"n_str\": %d, \"n_phases\": %d, \"all_linear\": %s, \"dims\": [%d, %d, %d], \"n_load_cases\": %zu,\n \"kapparef\": [",
+           reader.howmany(), reader.n_str(), mm.n_phases, mm.all_linear ? "true" : "false", reader.dims[0], reader.dims[1], reader.dims[2],
+           reader.load_cases.size());
+    for (size_t i = 0; i < mm.kapparef_mat.a.size(); ++i) printf("%s%.17g", i ? ", " : "", mm.kapparef_mat.a[i]);
+    printf("],\n \"phases\": [");
+    const auto descs = mm.phase_descs();
+    for (size_t p = 0; p < descs.size(); ++p) {
+        printf("%s{\"model\": %d, \"local_mat\": %d, \"group_n_mat\": %d, \"params\": [", p ? ", " : "", descs[p].model, descs[p].local_mat,
+               descs[p].group_n_mat);
+        for (int k = 0; k < FANS_MAX_PARAMS; ++k) printf("%s%.17g", k ? ", " : "", descs[p].params[k]);
+        printf("]}");
+    }
+    printf("],\n \"volume_fractions\": [");
+    for (size_t i = 0; i < reader.volume_fractions.size(); ++i) printf("%s%.17g", i ? ", " : "", reader.volume_fractions[i]);
+    printf("],\n \"mixed_M\": [");
+    bool first = true;
+    for (auto &lc : reader.load_cases)
+        if (lc.mixed) {
+            MixedBC b = lc.mbc;
+            b.finalize(mm.kapparef_mat);
+            printf("%s[", first ? "" : ", ");
+            for (size_t i = 0; i < b.M.a.size(); ++i) printf("%s%.17g", i ? ", " : "", b.M.a[i]);
+            printf("]");
+            first = false;
+        }
+    printf("]}\n");
+    return 0;
+}
+
+// runSolver, src/main.cpp:9-46
+static void runSolver(Reader &reader, DirSink &sink)
+{
+    for (size_t load_path_idx = 0; load_path_idx < reader.load_cases.size(); ++load_path_idx) {
+        MaterialManager *matmanager = createMaterialManager(reader);
+        Solver *solver = createSolver(reader, matmanager);  // a fresh Solver (u = 0) per load case, like the reference
+        for (size_t time_step_idx = 0; time_step_idx < reader.load_cases[load_path_idx].n_steps; ++time_step_idx) {
+            printf("\n║ ▶ Load case %zu/%zu: Time step %zu/%zu\n", load_path_idx + 1, reader.load_cases.size(), time_step_idx + 1,
+                   reader.load_cases[load_path_idx].n_steps);
+            if (reader.load_cases[load_path_idx].mixed) {
+                solver->enableMixedBC(reader.load_cases[load_path_idx].mbc, time_step_idx);
+            } else {
+                solver->disableMixedBC();
+                matmanager->set_gradient(reader.load_cases[load_path_idx].g0_path[time_step_idx]);
+            }
+            solver->solve();
+            solver->postprocess(sink, (int)load_path_idx, (int)time_step_idx);
+            printf("# iterations %zu\n", solver->iter);
+            if (reader.extrapolate_displacement) solver->extrapolateDisplacement();
+        }
+        delete solver;
+        delete matmanager;
+    }
+}
+
+int main(int argc, char **argv)
+{
+    try {
+        if (argc >= 3 && std::strcmp(argv[1], "--describe") == 0) {
+            Reader reader;
+            reader.ReadInputFile(argv[2]);
+            if (argc >= 7) load_raw_ms(reader, argv[3], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]));
+            else reader.ReadMS(reader.howmany());
+            return describe(reader);
+        }
+        if (argc != 3 && argc != 7) {
+            fprintf(stderr, "Usage: %s <input_file.json> <results_dir> [ms.u16 nx ny nz]\n", argv[0]);
+            return 10;
+        }
+        Reader reader;
+        reader.ReadInputFile(argv[1]);
+        if (argc == 7) load_raw_ms(reader, argv[3], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]));
+        else reader.ReadMS(reader.howmany());
+        DirSink sink(argv[2], reader.dataset_name);
+        runSolver(reader, sink);
+        return 0;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ERROR: %s\n", e.what());
+        return 10;
+    }
+}

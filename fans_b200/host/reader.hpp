@@ -11,13 +11,12 @@
 #include <string>
 #include <vector>
 
+#include "h5mini.hpp"
 #include "json.hpp"
 #include "mixedbc.hpp"
 
 namespace fans {
 
-bool h5mini_read_dataset(const std::string &file, const std::string &dataset, std::vector<int> &dims, std::vector<uint16_t> &data,
-                         std::string &permute_order, std::string &err);
 
 class Reader {
   public:

@@ -1,0 +1,80 @@
+"""CPU tests of the C++ host layer (fans_b200/host/*.hpp): the mirror of Reader / Matmodel / MaterialManager / MixedBC that sits
+above the C ABI.  `FANS_gpu --describe` prints what the host derives from a reference input file (phase descriptors, reference
+stiffness, mixed-BC matrices) without touching the GPU; it is compared with the oracle's parse of the same input."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fans_oracle as fo
+import golden_util as gu
+import cpp_host
+import util
+
+SCENARIOS = ["LinearThermal", "LinearElastic", "PseudoPlastic", "J2Plasticity", "CompressibleNeoHookean", "MixedBCs", "MixedBCs_LargeStrain"]
+
+
+@pytest.fixture(scope="module")
+def exe():
+    return cpp_host.build()
+
+
+@pytest.fixture(scope="module")
+def ms_file(tmp_path_factory):
+    p = tmp_path_factory.mktemp("ms") / "sphere32.u16"
+    gu.sphere32().tofile(p)
+    return str(p)
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_describe_matches_oracle(exe, ms_file, name, tmp_path):
+    cfg = gu.reference_input(name)
+    inp = tmp_path / "in.json"
+    inp.write_text(json.dumps(cfg))
+    out = subprocess.run([exe, "--describe", str(inp), ms_file, "32", "32", "32"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout)
+    strain_type = cfg.get("strain_type", "small")
+    par = fo.OracleSolver(gu.sphere32(), cfg["microstructure"]["L"], cfg["problem_type"], cfg["materials"], cfg.get("FE_type", "HEX8"),
+                          cfg["method"], strain_type, cfg["error_parameters"], 0)
+    assert (d["howmany"], d["n_str"], d["n_phases"], d["all_linear"]) == (par.h, par.n_str, par.n_phases, par.all_linear)
+    assert np.allclose(np.array(d["kapparef"]).reshape(par.n_str, par.n_str), par.kapparef, rtol=1e-13, atol=1e-13)
+    assert np.allclose(d["volume_fractions"], [1 - 8744 / 32768, 8744 / 32768])
+    for got, want in zip(d["phases"], util.phase_descs_from_oracle(par)):
+        assert (got["model"], got["local_mat"], got["group_n_mat"]) == (want.model, want.local_mat, want.group_n_mat)
+        assert np.allclose(got["params"], list(want.params), rtol=1e-13, atol=1e-15)
+    mixed = [lc for lc in cfg["macroscale_loading"] if isinstance(lc, dict)]
+    assert len(d["mixed_M"]) == len(mixed)
+    for got, lc in zip(d["mixed_M"], mixed):
+        mbc = fo.MixedBC(lc["strain_indices"], lc["stress_indices"], lc.get("strain", []), lc.get("stress", []), par.n_str)
+        mbc.finalize(par.kapparef)
+        assert np.allclose(np.array(got).reshape(mbc.M.shape), mbc.M, rtol=1e-10, atol=1e-14)
+
+
+def test_bad_inputs_raise_reference_errors(exe, ms_file, tmp_path):
+    cfg = gu.reference_input("LinearElastic")
+    for mutate, msg in [(lambda c: c.update(FE_type="HEX27"), "FE_type must be one of"),
+                        (lambda c: c.update(problem_type="acoustic"), "not a valid problem type"),
+                        (lambda c: c["materials"][0].update(matmodel="Nope"), "Nope"),
+                        (lambda c: c["materials"][0].update(phases=[0, 2]), "not assigned")]:
+        c = json.loads(json.dumps(cfg))
+        mutate(c)
+        inp = tmp_path / "bad.json"
+        inp.write_text(json.dumps(c))
+        out = subprocess.run([exe, "--describe", str(inp), ms_file, "32", "32", "32"], capture_output=True, text=True)
+        assert out.returncode == 10 and msg in out.stderr, (out.returncode, out.stderr)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test/microstructures/sphere32.h5"), reason="reference checkout not present")
+def test_h5mini_reads_the_reference_microstructure(exe, tmp_path):
+    """The built-in HDF5 reader on the reference's own file (deflate chunk, zyx order) == the committed fixture."""
+    cfg = gu.reference_input("LinearThermal")
+    inp = tmp_path / "in.json"
+    inp.write_text(json.dumps(cfg))
+    out = subprocess.run([exe, "--describe", str(inp)], capture_output=True, text=True, cwd="/root/reference/test")
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout)
+    assert d["dims"] == [32, 32, 32]
+    assert np.allclose(d["volume_fractions"], [1 - 8744 / 32768, 8744 / 32768])

@@ -1,0 +1,62 @@
+"""The C++ host front end end to end on the GPU: FANS_gpu <input.json> <results_dir> on reference scenarios, results read back
+from the sink and compared with the committed oracle fixture (the same numbers the reference's pytest suite looks at)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import cpp_host
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cli(tmp_path, cfg):
+    exe = cpp_host.build()
+    ms = tmp_path / "ms.u16"
+    gu.sphere32().tofile(ms)
+    inp = tmp_path / "in.json"
+    inp.write_text(json.dumps(cfg))
+    out = tmp_path / "results"
+    r = subprocess.run([exe, str(inp), str(out), str(ms), "32", "32", "32"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    index = [json.loads(l) for l in open(out / "index.jsonl")]
+    def load(name, lc, t):
+        e = [i for i in index if i["name"] == name and i["load"] == lc and i["time_step"] == t][0]
+        dt = {"f64": np.float64, "f32": np.float32, "u16": np.uint16}[e["dtype"]]
+        return np.fromfile(str(out) + e["path"], dtype=dt).reshape(e["dims"])
+    return load, r.stdout
+
+
+@pytest.mark.parametrize("name,steps", [("LinearElastic", 1), ("LinearThermal", 1), ("MixedBCs", 2)])
+def test_cli_scenario(tmp_path, name, steps):
+    cfg = gu.reference_input(name)
+    for i, lc in enumerate(cfg["macroscale_loading"]):   # bound the run like the fixture
+        if isinstance(lc, dict):
+            for k in ("strain", "stress"):
+                lc[k] = lc[k][:steps]
+        else:
+            cfg["macroscale_loading"][i] = lc[:steps]
+    load, stdout = run_cli(tmp_path, cfg)
+    for g in gu.oracle_scenario(name):
+        if g["step"] >= steps:
+            continue
+        sa = load("stress_average", g["load_case"], g["step"])
+        assert rel_err(sa, g["stress_average"]) < 1e-9 or np.abs(np.array(g["stress_average"])).max() < 1e-12
+        ea = load("strain_average", g["load_case"], g["step"])
+        assert rel_err(ea, g["g0"]) < 1e-9
+        err = load("absolute_error", g["load_case"], g["step"])
+        assert abs(len(err) - 1 - g["iters"]) <= 1
+        # reference pytest invariants on the written fields (test_strain_stress_averaging.py, test_displacement_averaging.py)
+        stress = load("stress", g["load_case"], g["step"])
+        assert np.allclose(stress.reshape(-1, stress.shape[-1]).mean(0), sa, rtol=1e-5, atol=1e-8)
+        uf = load("displacement_fluctuation", g["load_case"], g["step"])
+        assert np.allclose(uf.reshape(-1, uf.shape[-1]).mean(0), 0.0, atol=1e-8)
+    if name in ("LinearElastic", "LinearThermal"):   # results: homogenized_tangent requested (test_homogenization_consistency.py)
+        C = load("homogenized_tangent", 0, 0)
+        sa, ea = load("stress_average", 0, 0), load("strain_average", 0, 0)
+        assert np.allclose(C @ ea, sa, rtol=1e-4, atol=1e-1) and np.allclose(C, C.T, rtol=1e-5, atol=1e-8)
+        assert np.linalg.eigvalsh(C).min() > 0
