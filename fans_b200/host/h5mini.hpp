@@ -1,7 +1,8 @@
 // h5mini.hpp — minimal, dependency-free (zlib only) reader for the HDF5 microstructure files FANS consumes
 // (src/reader.cpp:227-411 reads them with the parallel HDF5 library, which this image does not have).
 // Supported subset — what h5py / MSUtils write for an image dataset:
-//   superblock v0/v1, old-style groups (symbol table: v1 B-tree + local heap), v1 object headers incl. continuation blocks,
+//   superblock v0/v1, old-style groups (symbol table: v1 B-tree + local heap) and new-style compact groups (link messages),
+//   v1 object headers incl. continuation blocks,
 //   dataspace v1/v2, fixed-point datatypes of 1/2/4/8 bytes (little endian), data layout v3 contiguous or chunked
 //   (v1 chunk B-tree, any number of chunks), optional deflate filter, string attribute `permute_order`.
 // Anything else is reported as an error string, never guessed.
@@ -104,7 +105,34 @@ static inline bool group_lookup(const File &f, uint64_t addr, const std::string 
         err = "'" + name + "' not found";
         return false;
     }
-    err = "object is not an old-style group (no symbol table message)";
+    // new-style "compact" group (libver >= 1.8 writes these for small groups): hard links stored as Link messages (0x06)
+    bool any_link = false;
+    for (const Msg &m : msgs) {
+        if (m.type != 0x06) continue;
+        any_link = true;
+        size_t p = m.pos;
+        if (f.b.at(p) != 1) continue;
+        const int flags = f.b.at(p + 1);
+        p += 2;
+        int ltype = 0;
+        if (flags & 0x08) ltype = f.b.at(p++);
+        if (flags & 0x04) p += 8;  // creation order
+        if (flags & 0x10) p += 1;  // character set
+        const int lsz = 1 << (flags & 3);
+        const size_t nlen = (size_t)f.rd(p, lsz);
+        p += lsz;
+        const std::string nm((const char *)&f.b.at(p), nlen);
+        p += nlen;
+        if (nm == name) {
+            if (ltype != 0) {
+                err = "'" + name + "' is not a hard link";
+                return false;
+            }
+            child = f.rd(p, f.so);
+            return true;
+        }
+    }
+    err = any_link ? "'" + name + "' not found" : "group uses neither a symbol table nor compact link messages (dense link storage is not supported)";
     return false;
 }
 
