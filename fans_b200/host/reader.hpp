@@ -133,8 +133,10 @@ class Reader {
         std::vector<int> fdims;
         std::vector<uint16_t> raw;
         std::string order = "zyx", err;
-        if (!h5mini_read_dataset(ms_filename, ms_datasetname, fdims, raw, order, err))
+        const bool is_npy = ms_filename.size() > 4 && ms_filename.compare(ms_filename.size() - 4, 4, ".npy") == 0;
+        if (!(is_npy ? npy_read(ms_filename, fdims, raw, err) : h5mini_read_dataset(ms_filename, ms_datasetname, fdims, raw, order, err)))
             throw std::runtime_error("cannot read microstructure '" + ms_filename + "':'" + ms_datasetname + "': " + err);
+        if (is_npy && microstructure.contains("permute_order")) order = microstructure["permute_order"].as_string();
         if (fdims.size() != 3) throw std::runtime_error("microstructure dataset must be 3-dimensional");
         if (order == "xyz") {
             dims = fdims;
@@ -151,6 +153,49 @@ class Reader {
     }
 
     std::vector<double> volume_fractions;
+
+    // NumPy .npy (format 1.0-3.0), C-ordered 3-D array of uint8 / uint16: the same image an HDF5 dataset would hold, for hosts
+    // without libhdf5.  Axis order on disk follows the HDF5 convention ("zyx" unless microstructure.permute_order says "xyz").
+    static bool npy_read(const std::string &fn, std::vector<int> &dims, std::vector<uint16_t> &data, std::string &err)
+    {
+        std::ifstream in(fn, std::ios::binary);
+        if (!in) return err = "cannot open file", false;
+        char magic[8];
+        in.read(magic, 8);
+        if (!in || std::string(magic, 6) != "\x93NUMPY") return err = "not a .npy file", false;
+        size_t hlen = 0;
+        unsigned char lb[4] = {0, 0, 0, 0};
+        in.read((char *)lb, magic[6] >= 2 ? 4 : 2);
+        hlen = lb[0] | (lb[1] << 8) | ((size_t)lb[2] << 16) | ((size_t)lb[3] << 24);
+        std::string hdr(hlen, ' ');
+        in.read(&hdr[0], (std::streamsize)hlen);
+        int esz = 0;
+        if (hdr.find("'|u1'") != std::string::npos) esz = 1;
+        else if (hdr.find("'<u2'") != std::string::npos) esz = 2;
+        else return err = "dtype must be uint8 or little-endian uint16", false;
+        if (hdr.find("'fortran_order': False") == std::string::npos) return err = "array must be C-ordered", false;
+        const size_t sp = hdr.find("'shape': (");
+        if (sp == std::string::npos) return err = "no shape in header", false;
+        dims.clear();
+        for (size_t i = sp + 10; i < hdr.size() && hdr[i] != ')';) {
+            if (isdigit((unsigned char)hdr[i])) {
+                size_t j = i;
+                while (j < hdr.size() && isdigit((unsigned char)hdr[j])) ++j;
+                dims.push_back(std::stoi(hdr.substr(i, j - i)));
+                i = j;
+            } else {
+                ++i;
+            }
+        }
+        if (dims.size() != 3) return err = "array must be 3-dimensional", false;
+        const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+        std::vector<unsigned char> raw(n * esz);
+        in.read((char *)raw.data(), (std::streamsize)raw.size());
+        if (!in) return err = "file is shorter than its header says", false;
+        data.resize(n);
+        for (size_t i = 0; i < n; ++i) data[i] = esz == 1 ? raw[i] : (uint16_t)(raw[2 * i] | (raw[2 * i + 1] << 8));
+        return true;
+    }
 
   private:
     void finish_ms()
