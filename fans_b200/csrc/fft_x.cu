@@ -21,83 +21,114 @@ struct TileIdxX {
 // minimum resident CTAs per SM the register budget is tuned for (threads per CTA = H*(N/E)*T)
 __host__ __device__ constexpr int xg_min_blocks(int nthr) { return nthr > 512 ? 1 : (nthr > 256 ? 2 : 3); }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 template <int N, int H, int T>
 __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (N / rp_elems(N)) * T))
     k_fft_xg(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,
-             PeerTable peers)
+             int nWork, PeerTable peers)
 {
     // One thread group per component: every thread carries E points of ONE component through the stages (32 data registers),
     // the H groups share the barriers.  At the Fourier-space boundary the groups swap their values through thread-private
     // slots of the (then idle) exchange tiles and each group forms its own row of  Gamma_hat r_hat.
+    // Persistent CTAs, two tile buffers: while tile w is transformed in buffer `cur` (which doubles as its exchange tile), the
+    // rows of tile w + gridDim.x travel global -> shared with cp.async into the other buffer, so the strided loads of the
+    // spectrum never sit on the critical path.
     extern __shared__ double2 sm[];
-    constexpr int E = rp_elems(N), TPC = N / E, NST = rp_nstages(N), NG = H * (H + 1) / 2, NTC = TPC * T;
+    constexpr int E = rp_elems(N), TPC = N / E, NST = rp_nstages(N), NG = H * (H + 1) / 2, NTC = TPC * T, BUF = H * N * T;
     const int c = threadIdx.x / NTC, tc = threadIdx.x % NTC;
     const int t = tc % T, jt = tc / T;
-    const int tile = blockIdx.x % nTiles, yl = blockIdx.x / nTiles;
-    double2 *base = spec + (size_t)c * g.cStride + (size_t)yl * g.kzp + (size_t)tile * T + t;
-    const double *gam = gamma + (size_t)blockIdx.x * NG * (N * T) + jt * T + t;
     const TileIdxX<T> idx{t};
-    double2 *X = sm + c * (N * T);
-    double2 a[1][E];
+    auto tile_ptr = [&](int w) { return spec + (size_t)c * g.cStride + (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t; };
+    auto issue = [&](int w, int buf) {
+        const double2 *src = tile_ptr(w);
+        double2 *dst = sm + buf * BUF + c * (N * T) + tc;
 #pragma unroll
-    for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_x(g, rp_row<N, 0>(jt, e))];
-    rp_forward<N, 1>(a, jt, X, 0, idx, tw, 1);
-    // Green operator; storage row of register e after the last stage = jt*E + e
-    if (H == 1) {
+        for (int e = 0; e < E; ++e) cp_async16(dst + e * NTC, src + spec_row_x(g, rp_row<N, 0>(jt, e)));
+    };
+    int cur = 0;
+    if ((int)blockIdx.x < nWork) issue(blockIdx.x, 0);
+    for (int w = blockIdx.x; w < nWork; w += gridDim.x, cur ^= 1) {
+        double2 *S = sm + cur * BUF;      // all components of this tile
+        double2 *X = S + c * (N * T);     // this group's exchange tile
+        double2 *base = tile_ptr(w);
+        const double *gam = gamma + (size_t)w * NG * (N * T) + jt * T + t;
+        double2 a[1][E];
+        cp_async_wait_all();
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const double g0 = __ldg(gam + (size_t)e * NTC);
-            a[0][e] = make_double2(g0 * a[0][e].x, g0 * a[0][e].y);
+        for (int e = 0; e < E; ++e) a[0][e] = X[e * NTC + tc];
+        __syncthreads();  // everybody holds its rows (and is done with the previous tile): both buffers may be overwritten
+        if (w + (int)gridDim.x < nWork) issue(w + gridDim.x, cur ^ 1);
+        rp_forward<N, 1>(a, jt, X, 0, idx, tw, 1);
+        // Green operator; storage row of register e after the last stage = jt*E + e
+        if (H == 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const double g0 = __ldg(gam + (size_t)e * NTC);
+                a[0][e] = make_double2(g0 * a[0][e].x, g0 * a[0][e].y);
+            }
+        } else {
+            constexpr size_t NT = (size_t)N * T;
+            // packed upper triangle 00,01,02,11,12,22: row c of the symmetric matrix
+            const int k0 = (c == 0) ? 0 : (c == 1 ? 1 : 2), k1 = (c == 0) ? 1 : (c == 1 ? 3 : 4), k2 = (c == 0) ? 2 : (c == 1 ? 4 : 5);
+            if (NST > 1) __syncthreads();  // everybody is done reading the last exchange
+#pragma unroll
+            for (int e = 0; e < E; ++e) X[e * NTC + tc] = a[0][e];
+            double gc[E][3];  // issued after the put (a[] is dead) so the loads fly while the CTA gathers at the barrier
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const double *ge = gam + (size_t)e * NTC;
+                gc[e][0] = __ldg(ge + k0 * NT);
+                gc[e][1] = __ldg(ge + k1 * NT);
+                gc[e][2] = __ldg(ge + k2 * NT);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const double2 r0 = S[e * NTC + tc], r1 = S[(H > 1 ? 1 : 0) * (N * T) + e * NTC + tc], r2 = S[(H > 2 ? 2 : 0) * (N * T) + e * NTC + tc];
+                a[0][e] = make_double2(gc[e][0] * r0.x + gc[e][1] * r1.x + gc[e][2] * r2.x, gc[e][0] * r0.y + gc[e][1] * r1.y + gc[e][2] * r2.y);
+            }
         }
-    } else {
-        constexpr size_t NT = (size_t)N * T;
-        // packed upper triangle 00,01,02,11,12,22: row c of the symmetric matrix
-        const int k0 = (c == 0) ? 0 : (c == 1 ? 1 : 2), k1 = (c == 0) ? 1 : (c == 1 ? 3 : 4), k2 = (c == 0) ? 2 : (c == 1 ? 4 : 5);
-        if (NST > 1) __syncthreads();  // everybody is done reading the last exchange
+        rp_inverse<N, 1>(a, jt, X, 0, idx, tw, 1);
+        if (peers.on) {  // plane x belongs to rank x / n0: store it into that rank's x-slab spectrum, block `me`
+            const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t;
 #pragma unroll
-        for (int e = 0; e < E; ++e) X[e * NTC + tc] = a[0][e];
-        double gc[E][3];  // issued after the put (a[] is dead) so the loads fly while the CTA gathers at the barrier
+            for (int e = 0; e < E; ++e) {
+                const int row = rp_row<N, 0>(jt, e);
+                peer_select(peers, row >> g.l2n0)[off + (size_t)(row & (g.n0 - 1)) * ((size_t)g.n1 * g.kzp)] = a[0][e];
+            }
+        } else {
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const double *ge = gam + (size_t)e * NTC;
-            gc[e][0] = __ldg(ge + k0 * NT);
-            gc[e][1] = __ldg(ge + k1 * NT);
-            gc[e][2] = __ldg(ge + k2 * NT);
+            for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
         }
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const double2 r0 = sm[e * NTC + tc], r1 = sm[(H > 1 ? 1 : 0) * (N * T) + e * NTC + tc], r2 = sm[(H > 2 ? 2 : 0) * (N * T) + e * NTC + tc];
-            a[0][e] = make_double2(gc[e][0] * r0.x + gc[e][1] * r1.x + gc[e][2] * r2.x, gc[e][0] * r0.y + gc[e][1] * r1.y + gc[e][2] * r2.y);
-        }
-    }
-    rp_inverse<N, 1>(a, jt, X, 0, idx, tw, 1);
-    if (peers.on) {  // plane x belongs to rank x / n0: store it into that rank's x-slab spectrum, block `me`
-        const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)yl * g.kzp + (size_t)tile * T + t;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int row = rp_row<N, 0>(jt, e);
-            peer_select(peers, row >> g.l2n0)[off + (size_t)(row & (g.n0 - 1)) * ((size_t)g.n1 * g.kzp)] = a[0][e];
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
     }
 }
 
 template <int N, int H, int T>
 static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const PeerTable &peers)
 {
-    constexpr int E = rp_elems(N);
+    constexpr int E = rp_elems(N), NTHR = H * (N / E) * T;
     const int nTiles = (ctx->kzc + T - 1) / T;
-    const size_t smem = sizeof(double2) * N * T * H;  // one exchange tile per component
-    if (smem > 227 * 1024 || H * (N / E) * T > 1024) {
+    const size_t smem = 2 * sizeof(double2) * N * T * H;  // two tile buffers (transform in one, next tile lands in the other)
+    if (smem > 227 * 1024 || NTHR > 1024) {
         fans_set_error(ctx, FANS_ERR_ARG, "x pass tile does not fit one CTA");
         return FANS_ERR_ARG;
     }
-    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg<N, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((size_t)ctx->n1 * nTiles);
-    k_fft_xg<N, H, T><<<grid, H * (N / E) * T, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, peers);
+    static int resident = 0;  // per instantiation
+    if (!resident) {
+        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg<N, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fft_xg<N, H, T>, NTHR, smem));
+        if (resident < 1) resident = 1;
+    }
+    const int nWork = ctx->n1 * nTiles;
+    int grid = FANS_SMS * resident;
+    if (const char *env = getenv("FANS_XG_GRID")) grid = atoi(env);
+    if (grid > nWork) grid = nWork;
+    k_fft_xg<N, H, T><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
     return FANS_OK;
 }
 
@@ -105,7 +136,8 @@ static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const Pee
 int fft_x_tile_width(int nx, int h)
 {
     int T = (h == 1) ? 8 : 4;
-    while (((size_t)h * nx * T * sizeof(double2) > 100 * 1024 || h * (nx / 8) * T > 1024) && T > 2) T /= 2;
+    if (const char *env = getenv("FANS_XG_T")) T = atoi(env);
+    while ((2 * (size_t)h * nx * T * sizeof(double2) > 200 * 1024 || h * (nx / 8) * T > 1024) && T > 2) T /= 2;
     return T;
 }
 

@@ -9,7 +9,11 @@
 //   * interface nodes: the exact element form, element by element, K_phase rows again as constant operands.
 // Data movement: a CTA owns an (8 x 64) node column and marches along x with a 4-slot shared-memory ring of node
 // planes (one-node halo in y,z), so every d value is read from HBM once per CTA column (halo re-reads hit L2) and the
-// fused update d = s + beta*d is formed on the fly while loading.  One __syncthreads per plane.
+// fused update d = s + beta*d is formed on the fly while loading.
+// Latency: the raw s / d values of plane k+2 travel global -> shared with cp.async (thread-private staging slots, no
+// registers held) while the CTA computes plane k; they are combined into the ring one step later, so no global-load
+// latency sits on the critical path of the march.  Isotropic phases (every S[delta][i][j], i != j, vanishes unless
+// delta_i != 0 and delta_j != 0 — checked numerically on the host) take a 153-DFMA variant of the 27-point stencil.
 #include "internal.h"
 #include "materials.cuh"
 #include "stencil.h"
@@ -52,35 +56,35 @@ __device__ __forceinline__ int gwrap(int v, int n)
     return v < 0 ? v + n : v;
 }
 
-// homogeneous path: both nodes of the pair, phase Q (compile time => constant-bank operands)
-template <int H, int Q>
-__device__ __forceinline__ void stencil_pair(const double *ring, int k, int ry, int rz0, double (&accA)[H], double (&accB)[H])
+// homogeneous path, x-scatter form: the contribution of ONE row (plane P, tile row ry+dy-1; v = its values at rz0..rz0+3 for
+// every component) to the node pair of output plane o = P - (DXI-1), phase Q (compile time => constant-bank operands).
+// Each plane row is read from shared memory once and feeds the accumulators of the three output planes it touches.
+template <int H, int Q, bool ISO, int DXI, int DY>
+__device__ __forceinline__ void stencil_row(const double (&v)[H][4], double (&accA)[H], double (&accB)[H])
 {
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-        const double *pl = ring + (size_t)((k + dx - 1 + 4) & 3) * H * GTILE;
+    for (int dz = 0; dz < 3; ++dz) {
+        const double *S = c_S + ((Q * 27 + (DXI * 9 + DY * 3 + dz)) * H * H);
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            double v[H][4];
+        for (int i = 0; i < H; ++i)
 #pragma unroll
-            for (int c = 0; c < H; ++c) {
-                const double2 *p2 = reinterpret_cast<const double2 *>(pl + c * GTILE + (ry + dy - 1) * GPZ + rz0);
-                const double2 a = p2[0], b = p2[1];
-                v[c][0] = a.x, v[c][1] = a.y, v[c][2] = b.x, v[c][3] = b.y;
+            for (int j = 0; j < H; ++j) {
+                if (ISO && H == 3 && i != j) {  // odd in delta_i and delta_j: zero on the centre lines
+                    const int dd[3] = {DXI, DY, dz};
+                    if (dd[i] == 1 || dd[j] == 1) continue;
+                }
+                accA[i] = fma(S[i * H + j], v[j][dz], accA[i]);
+                accB[i] = fma(S[i * H + j], v[j][dz + 1], accB[i]);
             }
-#pragma unroll
-            for (int dz = 0; dz < 3; ++dz) {
-                const double *S = c_S + ((Q * 27 + (dx * 9 + dy * 3 + dz)) * H * H);
-#pragma unroll
-                for (int i = 0; i < H; ++i)
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        accA[i] = fma(S[i * H + j], v[j][dz], accA[i]);
-                        accB[i] = fma(S[i * H + j], v[j][dz + 1], accB[i]);
-                    }
-            }
-        }
     }
+}
+template <int H, int NQ, bool ISO, int DXI, int DY>
+__device__ __forceinline__ void stencil_row_dispatch(int ph, const double (&v)[H][4], double (&accA)[H], double (&accB)[H])
+{
+    if (NQ > 0 && ph == 0) stencil_row<H, 0, ISO, DXI, DY>(v, accA, accB);
+    else if (NQ > 1 && ph == 1) stencil_row<H, (NQ > 1 ? 1 : 0), ISO, DXI, DY>(v, accA, accB);
+    else if (NQ > 2 && ph == 2) stencil_row<H, (NQ > 2 ? 2 : 0), ISO, DXI, DY>(v, accA, accB);
+    else if (NQ > 3 && ph == 3) stencil_row<H, (NQ > 3 ? 3 : 0), ISO, DXI, DY>(v, accA, accB);
 }
 
 // exact element form for ONE node at tile position (ry, rz) of plane k; element E = (ox,oy,oz) below the node
@@ -115,11 +119,11 @@ __device__ __forceinline__ void element_dispatch(const double *ring, int k, int 
     else if (NQ > 3 && ph == 3) element_rows<H, (NQ > 3 ? 3 : 0), A>(ring, k, ry, rz, acc);
 }
 
-// ms ring: element plane p in slot (p+3)%3, tile [(GY+1)][(GZ+1)], element (ry,rz) = low corner at node tile (ry,rz)
+// ms ring: element plane p in slot (p+8)&7, tile [(GY+1)][(GZ+1)], element (ry,rz) = low corner at node tile (ry,rz)
 template <int H, int NQ>
 __device__ __forceinline__ void node_general(const double *ring, const uint16_t *mring, int k, int ry, int rz, double (&acc)[H])
 {
-#define EL_PH(ox, oy, oz) ((int)mring[((k - (ox) + 3) % 3) * GETILE + (ry - (oy)) * (GZ + 1) + (rz - (oz))])
+#define EL_PH(ox, oy, oz) ((int)mring[((k - (ox) + 8) & 7) * GETILE + (ry - (oy)) * (GZ + 1) + (rz - (oz))])
     element_dispatch<H, NQ, 0>(ring, k, ry, rz, EL_PH(0, 0, 0), acc);
     element_dispatch<H, NQ, 1>(ring, k, ry, rz, EL_PH(1, 0, 0), acc);
     element_dispatch<H, NQ, 2>(ring, k, ry, rz, EL_PH(0, 1, 0), acc);
@@ -131,12 +135,23 @@ __device__ __forceinline__ void node_general(const double *ring, const uint16_t 
 #undef EL_PH
 }
 
-template <int H, int NQ>
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+#define G_NLD ((GTILE + G_THREADS - 1) / G_THREADS)
+#define G_NLM ((GETILE + G_THREADS - 1) / G_THREADS)
+#define G_STAGE (G_NLD * G_THREADS)   // thread-private staging slots per component
+
+template <int H, int NQ, bool ISO>
 __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p)
 {
     extern __shared__ __align__(16) double smem[];
-    double *ring = smem;                                               // [4][H][GTILE]
-    uint16_t *mring = reinterpret_cast<uint16_t *>(smem + 4 * H * GTILE);  // [3][GETILE]
+    double *ring = smem;                                   // [4][H][GTILE]   combined direction planes
+    double *stg = smem + 4 * H * GTILE;                    // [2][H][G_STAGE] raw d_old / s of the plane in flight
+    uint16_t *mring = reinterpret_cast<uint16_t *>(stg + 2 * H * G_STAGE);  // [8][GETILE]
     __shared__ double scratch[32];
     __shared__ uint16_t qlist[GY * 32];  // queued interface node pairs, per warp row
     __shared__ int qcnt[GY];
@@ -150,7 +165,7 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
     const double beta = p.s ? *p.beta : 0.0;
 
     // in-plane offsets of the tile positions this thread loads (fixed over the march): no div/mod in the x loop
-    constexpr int NLD = (GTILE + G_THREADS - 1) / G_THREADS, NLM = (GETILE + G_THREADS - 1) / G_THREADS;
+    constexpr int NLD = G_NLD, NLM = G_NLM;
     int goff[NLD], moff[NLM];
     unsigned mine_mask = 0;
 #pragma unroll
@@ -173,102 +188,143 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
         }
     }
     const size_t plane_sz = (size_t)p.ny * p.nz;
-    auto load_plane = [&](int xp, bool owned) {
+    // issue: raw values of node plane xp -> this thread's staging slots (asynchronous, nothing held in registers)
+    auto issue = [&](int xp) {
         const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
-        double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
-        double v[NLD][H];
         const double *hal = (p.halo_lo && xp < 0) ? p.halo_lo : ((p.halo_hi && xp >= p.n0) ? p.halo_hi : nullptr);
-        if (hal) {
-#pragma unroll
-            for (int j = 0; j < NLD; ++j)
-                if (goff[j] >= 0) {
-#pragma unroll
-                    for (int cc = 0; cc < H; ++cc) v[j][cc] = hal[cc * plane_sz + goff[j]];
-                }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NLD; ++j)
-                if (goff[j] >= 0) {
-#pragma unroll
-                    for (int cc = 0; cc < H; ++cc) v[j][cc] = p.d_old[cc * p.nloc + gbase + goff[j]];
-                }
-        }
-        if (p.s && !hal) {
-            double sv[NLD][H];
-#pragma unroll
-            for (int j = 0; j < NLD; ++j)
-                if (goff[j] >= 0) {
-#pragma unroll
-                    for (int cc = 0; cc < H; ++cc) sv[j][cc] = p.s[cc * p.nloc + gbase + goff[j]];
-                }
-#pragma unroll
-            for (int j = 0; j < NLD; ++j)
-                if (goff[j] >= 0) {
-#pragma unroll
-                    for (int cc = 0; cc < H; ++cc) {
-                        v[j][cc] = sv[j][cc] + beta * v[j][cc];
-                        if (owned && ((mine_mask >> j) & 1u)) p.d_new[cc * p.nloc + gbase + goff[j]] = v[j][cc];
-                    }
-                }
-        }
+        const double *srcd = hal ? hal : p.d_old + gbase;
+        const size_t cs = hal ? plane_sz : p.nloc;
 #pragma unroll
         for (int j = 0; j < NLD; ++j)
             if (goff[j] >= 0) {
 #pragma unroll
-                for (int cc = 0; cc < H; ++cc) pl[cc * GTILE + tid + j * G_THREADS] = v[j][cc];
+                for (int cc = 0; cc < H; ++cc) cp_async8(stg + cc * G_STAGE + tid + j * G_THREADS, srcd + cc * cs + goff[j]);
+            }
+        if (p.s && !hal) {
+#pragma unroll
+            for (int j = 0; j < NLD; ++j)
+                if (goff[j] >= 0) {
+#pragma unroll
+                    for (int cc = 0; cc < H; ++cc)
+                        cp_async8(stg + (H + cc) * G_STAGE + tid + j * G_THREADS, p.s + cc * p.nloc + gbase + goff[j]);
+                }
+        }
+    };
+    // combine: staging -> ring slot of plane xp as d = s + beta d_old (halo planes and the plain operator: d as is)
+    auto combine = [&](int xp, bool owned) {
+        const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
+        const bool hal = (p.halo_lo && xp < 0) || (p.halo_hi && xp >= p.n0);
+        const bool upd = p.s && !hal;
+        double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
+        cp_async_wait_all();
+#pragma unroll
+        for (int j = 0; j < NLD; ++j)
+            if (goff[j] >= 0) {
+#pragma unroll
+                for (int cc = 0; cc < H; ++cc) {
+                    double v = stg[cc * G_STAGE + tid + j * G_THREADS];
+                    if (upd) {
+                        v = stg[(H + cc) * G_STAGE + tid + j * G_THREADS] + beta * v;
+                        if (owned && ((mine_mask >> j) & 1u)) p.d_new[cc * p.nloc + gbase + goff[j]] = v;
+                    }
+                    pl[cc * GTILE + tid + j * G_THREADS] = v;
+                }
             }
     };
-    auto load_ms = [&](int xp) {
-        const uint16_t *src = (p.ms_lo && xp < 0) ? p.ms_lo : p.phidx + (size_t)gwrap(xp, p.n0) * plane_sz;
-        uint16_t *mp = mring + ((xp + 3) % 3) * GETILE;
+    auto ms_src = [&](int xp) { return (p.ms_lo && xp < 0) ? p.ms_lo : p.phidx + (size_t)gwrap(xp, p.n0) * plane_sz; };
+    uint16_t msr[NLM];
+    auto ms_fetch = [&](int xp) {
+        const uint16_t *src = ms_src(xp);
+#pragma unroll
+        for (int j = 0; j < NLM; ++j) msr[j] = (moff[j] >= 0) ? __ldg(src + moff[j]) : (uint16_t)0;
+    };
+    auto ms_put = [&](int xp) {
+        uint16_t *mp = mring + ((xp + 8) & 7) * GETILE;
 #pragma unroll
         for (int j = 0; j < NLM; ++j)
-            if (moff[j] >= 0) mp[tid + j * G_THREADS] = src[moff[j]];
+            if (moff[j] >= 0) mp[tid + j * G_THREADS] = msr[j];
     };
 
-    load_plane(xs - 1, false);
-    load_plane(xs, true);
-    load_ms(xs - 1);
+    // prologue: plane xs-1 combined, plane xs in flight; element planes xs-1, xs in the ms ring, xs+1 in registers
+    issue(xs - 1);
+    ms_fetch(xs - 1);
+    ms_put(xs - 1);
+    ms_fetch(xs);
+    ms_put(xs);
+    combine(xs - 1, false);
+    issue(xs);
+    ms_fetch(xs + 1);
     double racc[1] = {0.0};
-    for (int k = xs; k < xe; ++k) {
-        load_plane(k + 1, (k + 1) < xe);
-        load_ms(k);
-        __syncthreads();
-        // ---- phase 1: homogeneous node pairs take the 27-point stencil; interface pairs are queued
-        bool homog = true;
-        int ph = 0;
-        if (valid) {
-            // phases of the 12 elements around the node pair: planes k-1,k ; rows ry-1,ry ; columns rzA-1..rzA+1
-            const uint16_t *m0 = mring + ((k - 1 + 3) % 3) * GETILE, *m1 = mring + ((k + 3) % 3) * GETILE;
+    // accumulators of the output planes P-1, P, P+1 (slots 0,1,2) of this thread's node pair, with their homogeneity flags
+    double acc[3][2][H];
+    int hph[3] = {-1, -1, -1};  // phase of a homogeneous neighbourhood, -1: interface pair / outside the chunk / invalid thread
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < H; ++c) acc[j][0][c] = 0.0, acc[j][1][c] = 0.0;
+    // step P: plane P (combined, in the ring) is read once and scattered to the outputs P-1 (dx=+1), P (dx=0), P+1 (dx=-1);
+    // output plane P-1 is then complete.
+    for (int P = xs - 1; P <= xe; ++P) {
+        __syncthreads();  // (A) plane P and element plane P+1 are visible; phase 2 of the previous step is over
+        // ---- phase 1
+        const int o2 = P + 1;  // newest output plane: classify its node pair from the 12 elements around it (planes o2-1, o2)
+        hph[2] = -1;
+        if (valid && o2 >= xs && o2 < xe) {
+            const uint16_t *m0 = mring + ((o2 - 1 + 8) & 7) * GETILE, *m1 = mring + ((o2 + 8) & 7) * GETILE;
             const int e00 = (ry - 1) * (GZ + 1) + rzA - 1, e10 = ry * (GZ + 1) + rzA - 1;
-            ph = m1[e10 + 1];
+            const int ph = m1[e10 + 1];
+            bool homog = true;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 homog = homog && (m0[e00 + c] == ph) && (m0[e10 + c] == ph) && (m1[e00 + c] == ph) && (m1[e10 + c] == ph);
+            hph[2] = homog ? ph : -1;
         }
-        const unsigned qmask = __ballot_sync(0xffffffffu, valid && !homog);
-        if (valid && homog) {
-            double accA[H], accB[H];
-#pragma unroll
-            for (int c = 0; c < H; ++c) accA[c] = 0.0, accB[c] = 0.0;
-            if (NQ > 0 && ph == 0) stencil_pair<H, 0>(ring, k, ry, rzA - 1, accA, accB);
-            else if (NQ > 1 && ph == 1) stencil_pair<H, (NQ > 1 ? 1 : 0)>(ring, k, ry, rzA - 1, accA, accB);
-            else if (NQ > 2 && ph == 2) stencil_pair<H, (NQ > 2 ? 2 : 0)>(ring, k, ry, rzA - 1, accA, accB);
-            else if (NQ > 3 && ph == 3) stencil_pair<H, (NQ > 3 ? 3 : 0)>(ring, k, ry, rzA - 1, accA, accB);
+        const double *pl = ring + (size_t)((P + 4) & 3) * H * GTILE;
+        if (hph[0] >= 0 || hph[1] >= 0 || hph[2] >= 0) {
+            double v[H][4];
+#define ST_ROW(DY)                                                                                              \
+    {                                                                                                           \
+        _Pragma("unroll") for (int c = 0; c < H; ++c)                                                           \
+        {                                                                                                       \
+            const double2 *p2 = reinterpret_cast<const double2 *>(pl + c * GTILE + (ry + DY - 1) * GPZ + rzA - 1); \
+            const double2 a = p2[0], b = p2[1];                                                                 \
+            v[c][0] = a.x, v[c][1] = a.y, v[c][2] = b.x, v[c][3] = b.y;                                         \
+        }                                                                                                       \
+        if (hph[0] >= 0) stencil_row_dispatch<H, NQ, ISO, 2, DY>(hph[0], v, acc[0][0], acc[0][1]);               \
+        if (hph[1] >= 0) stencil_row_dispatch<H, NQ, ISO, 1, DY>(hph[1], v, acc[1][0], acc[1][1]);               \
+        if (hph[2] >= 0) stencil_row_dispatch<H, NQ, ISO, 0, DY>(hph[2], v, acc[2][0], acc[2][1]);               \
+    }
+            ST_ROW(0)
+            ST_ROW(1)
+            ST_ROW(2)
+#undef ST_ROW
+        }
+        const int k = P - 1;  // the output plane completed by this step
+        const bool kin = (k >= xs);
+        const unsigned qmask = __ballot_sync(0xffffffffu, valid && kin && hph[0] < 0);
+        if (valid && kin && hph[0] >= 0) {
             const size_t g = ((size_t)k * p.ny + yA) * p.nz + zA;
             const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + ry * GPZ + rzA;
 #pragma unroll
             for (int c = 0; c < H; ++c) {
-                *reinterpret_cast<double2 *>(p.out + c * p.nloc + g) = make_double2(accA[c], accB[c]);
-                racc[0] += accA[c] * ctr[c * GTILE] + accB[c] * ctr[c * GTILE + 1];
+                *reinterpret_cast<double2 *>(p.out + c * p.nloc + g) = make_double2(acc[0][0][c], acc[0][1][c]);
+                racc[0] += acc[0][0][c] * ctr[c * GTILE] + acc[0][1][c] * ctr[c * GTILE + 1];
             }
         }
         if (qmask) {
-            if (valid && !homog) qlist[wy * 32 + __popc(qmask & ((1u << lane) - 1u))] = (uint16_t)(ry * 128 + rzA);
+            if (valid && kin && hph[0] < 0) qlist[wy * 32 + __popc(qmask & ((1u << lane) - 1u))] = (uint16_t)(ry * 128 + rzA);
         }
         if (lane == 0) qcnt[wy] = __popc(qmask);
-        __syncthreads();
-        // ---- phase 2: the queued interface nodes of the whole CTA, densely packed onto lanes (exact element form)
+        // rotate the output window
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+            acc[0][0][c] = acc[1][0][c], acc[0][1][c] = acc[1][1][c];
+            acc[1][0][c] = acc[2][0][c], acc[1][1][c] = acc[2][1][c];
+            acc[2][0][c] = 0.0, acc[2][1][c] = 0.0;
+        }
+        hph[0] = hph[1], hph[1] = hph[2];
+        __syncthreads();  // (B)
+        // ---- phase 2: the queued interface nodes of plane k, densely packed onto lanes (exact element form, planes k-1..k+1)
         int pre[GY + 1];
         pre[0] = 0;
 #pragma unroll
@@ -282,24 +338,35 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
                 if (pair >= pre[q]) w = q, base = pre[q];
             const int code = qlist[w * 32 + (pair - base)];
             const int qry = code >> 7, qrz = (code & 127) + (n & 1);
-            double acc[H];
+            double a1[H];
 #pragma unroll
-            for (int c = 0; c < H; ++c) acc[c] = 0.0;
-            node_general<H, NQ>(ring, mring, k, qry, qrz, acc);
+            for (int c = 0; c < H; ++c) a1[c] = 0.0;
+            node_general<H, NQ>(ring, mring, k, qry, qrz, a1);
             const size_t g = ((size_t)k * p.ny + (y0 + qry - 1)) * p.nz + (z0 + qrz - 1);
             const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + qry * GPZ + qrz;
 #pragma unroll
             for (int c = 0; c < H; ++c) {
-                p.out[c * p.nloc + g] = acc[c];
-                racc[0] += acc[c] * ctr[c * GTILE];
+                p.out[c * p.nloc + g] = a1[c];
+                racc[0] += a1[c] * ctr[c * GTILE];
+            }
+        }
+        // ---- refill: plane P+1 -> ring slot of plane P-3 (nobody reads it any more), element plane P+2 -> ms ring slot of P-6
+        if (P + 1 <= xe) {
+            combine(P + 1, (P + 1) < xe);
+            ms_put(P + 2);
+            if (P + 2 <= xe) {
+                issue(P + 2);  // lands during the whole next step
+                ms_fetch(P + 3);
             }
         }
     }
+    cp_async_wait_all();
     if (p.red_out) grid_reduce<1, 1>(racc, scratch, p.part, p.ticket, p.red_out);
 }
 
 // ------------------------------------------------------------------------------------------------
 static uint64_t g_stencil_stamp = 0;
+static bool g_stencil_iso = false;
 
 // 27-point block stencil of a homogeneous neighbourhood from the element matrix K (8h x 8h, node-major):
 //   S[delta][i][j] = sum over local nodes a with b = a + delta inside the element of K[h a + i][h b + j]
@@ -319,11 +386,35 @@ void stencil_from_element_matrix(int h, const double *K, double *S /* [27][h][h]
 bool stencil_supported(const fans_ctx *ctx) { return ctx->all_linear && ctx->n_k >= 1 && ctx->n_k <= STENCIL_MAXQ && ctx->n_k == ctx->n_phases; }
 
 template <int H, int NQ>
-static int launch_stencil(fans_ctx *ctx, const StencilParams &p, dim3 grid, size_t smem)
+static int launch_stencil(fans_ctx *ctx, const StencilParams &p, dim3 grid, size_t smem, bool iso)
 {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stencil_linear<H, NQ><<<grid, G_THREADS, smem, ctx->st>>>(p);
+    if (iso && H == 3) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ, (H == 3)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stencil_linear<H, NQ, (H == 3)><<<grid, G_THREADS, smem, ctx->st>>>(p);
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stencil_linear<H, NQ, false><<<grid, G_THREADS, smem, ctx->st>>>(p);
+    }
     return FANS_OK;
+}
+
+// true when every off-diagonal coefficient S[delta][i][j] (i != j) with delta_i == 0 or delta_j == 0 vanishes (to rounding) for all
+// phases: holds for isotropic / cubic / orthotropic-aligned stiffness with any of the element types; the kernel then skips them.
+static bool stencil_iso_pattern(int h, int nq, const double *S)
+{
+    if (h != 3) return false;
+    double mx = 0.0, off = 0.0;
+    for (int q = 0; q < nq; ++q)
+        for (int di = 0; di < 27; ++di) {
+            const int dd[3] = {di / 9, (di / 3) % 3, di % 3};
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    const double v = fabs(S[((q * 27 + di) * 3 + i) * 3 + j]);
+                    mx = fmax(mx, v);
+                    if (i != j && (dd[i] == 1 || dd[j] == 1)) off = fmax(off, v);
+                }
+        }
+    return off <= 1e-13 * mx;
 }
 
 int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s_in, double *d_new, const double *beta_dev,
@@ -338,6 +429,8 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
         CUDA_TRY(ctx, cudaMemcpyToSymbol(c_S, S.data(), sizeof(double) * S.size()));
         CUDA_TRY(ctx, cudaMemcpyToSymbol(c_KQ, ctx->K_host.data(), sizeof(double) * (size_t)ctx->n_k * nd * nd));
         g_stencil_stamp = ctx->const_stamp;
+        const char *env = getenv("FANS_STENCIL_ISO");
+        g_stencil_iso = stencil_iso_pattern(h, ctx->n_k, S.data()) && !(env && env[0] == '0');
     }
     StencilParams p;
     memset(&p, 0, sizeof(p));
@@ -353,14 +446,16 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     }
     const int gy = (ctx->ny + GY - 1) / GY, gz = (ctx->nz + GZ - 1) / GZ;
     int xchunk = ctx->n0;
-    while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < 48L * FANS_SMS) xchunk = (xchunk + 1) / 2;
+    long want = 48L * FANS_SMS;
+    if (const char *env = getenv("FANS_STENCIL_CTAS")) want = atol(env);
+    while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < want) xchunk = (xchunk + 1) / 2;
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
-    const size_t smem = sizeof(double) * 4 * h * GTILE + sizeof(uint16_t) * 3 * GETILE + 16;
+    const size_t smem = sizeof(double) * (4 * h * GTILE + 2 * h * G_STAGE) + sizeof(uint16_t) * 8 * GETILE + 16;
     prof_begin(ctx, PC_SWEEP_LINEAR);
     int rc = FANS_ERR_ARG;
 #define ST_CASE(H_, Q_) \
-    if (h == H_ && ctx->n_k == Q_) rc = launch_stencil<H_, Q_>(ctx, p, grid, smem);
+    if (h == H_ && ctx->n_k == Q_) rc = launch_stencil<H_, Q_>(ctx, p, grid, smem, g_stencil_iso);
     ST_CASE(1, 1) ST_CASE(1, 2) ST_CASE(1, 3) ST_CASE(1, 4) ST_CASE(3, 1) ST_CASE(3, 2) ST_CASE(3, 3) ST_CASE(3, 4)
 #undef ST_CASE
     prof_end(ctx);
