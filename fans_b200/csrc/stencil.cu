@@ -20,10 +20,13 @@
 
 #define GY 8
 #define GZ 64
-#define GPZ (GZ + 2)
+#define GPZ (GZ + 4)                 // node tile columns z0-2 .. z0+GZ+1: every 16-byte pair of the field stays a pair in the tile
 #define GTILE ((GY + 2) * GPZ)
+#define GPAIRS (GTILE / 2)           // 16-byte pairs per component plane tile
 #define GETILE ((GY + 1) * (GZ + 1))
-#define G_THREADS 256
+#define G_CONS 256                   // consumer threads: one node pair each
+#define G_PROD 128                   // producer threads (one warpgroup, runs on a reduced register budget)
+#define G_THREADS (G_CONS + G_PROD)
 #ifndef STENCIL_MINB
 #define STENCIL_MINB 2
 #endif
@@ -123,7 +126,7 @@ __device__ __forceinline__ void element_dispatch(const double *ring, int k, int 
 template <int H, int NQ>
 __device__ __forceinline__ void node_general(const double *ring, const uint16_t *mring, int k, int ry, int rz, double (&acc)[H])
 {
-#define EL_PH(ox, oy, oz) ((int)mring[((k - (ox) + 8) & 7) * GETILE + (ry - (oy)) * (GZ + 1) + (rz - (oz))])
+#define EL_PH(ox, oy, oz) ((int)mring[((k - (ox) + 8) & 7) * GETILE + (ry - (oy)) * (GZ + 1) + (rz - 1 - (oz))])
     element_dispatch<H, NQ, 0>(ring, k, ry, rz, EL_PH(0, 0, 0), acc);
     element_dispatch<H, NQ, 1>(ring, k, ry, rz, EL_PH(1, 0, 0), acc);
     element_dispatch<H, NQ, 2>(ring, k, ry, rz, EL_PH(0, 1, 0), acc);
@@ -135,232 +138,241 @@ __device__ __forceinline__ void node_general(const double *ring, const uint16_t 
 #undef EL_PH
 }
 
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// named barriers (ids 1..15; 0 is __syncthreads): producer/consumer hand-over of ring slots without stalling the whole CTA
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+#define BAR_FULL 1    // +slot: plane (and the element plane after it) is in the ring
+#define BAR_EMPTY 5   // +slot: the consumers are done with the plane that lived in the slot
+#define BAR_CONS 9    // consumer-only barrier (interface queue)
 
-#define G_NLD ((GTILE + G_THREADS - 1) / G_THREADS)
-#define G_NLM ((GETILE + G_THREADS - 1) / G_THREADS)
-#define G_STAGE (G_NLD * G_THREADS)   // thread-private staging slots per component
+#define G_NLP ((GPAIRS + G_PROD - 1) / G_PROD)   // pair items per producer thread and component
+#define G_NLM ((GETILE + G_PROD - 1) / G_PROD)   // phase-image items per producer thread
+#define G_STG (G_NLP * G_PROD)                   // staging pairs per component
 
+// Warp-specialised march along x.  Producer warpgroup (warps 8..11): raw s / d_old pairs of plane Q+1 travel global -> staging with
+// cp.async while it combines plane Q (d = s + beta d_old) into ring slot Q&3, stores d_new and refills the phase-image ring.
+// Consumer warps (0..7): step P reads plane P ONCE from the ring and scatters it into the accumulators of the output planes
+// P-1, P, P+1 (x-scatter form of the 27-point block stencil); plane P-1 is then complete.  Interface nodes (mixed-phase
+// neighbourhood) are queued and evaluated in the exact element form.  Hand-over through named barriers per ring slot, so
+// neither side ever waits for the other unless it is genuinely ahead.
 template <int H, int NQ, bool ISO>
 __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p)
 {
     extern __shared__ __align__(16) double smem[];
     double *ring = smem;                                   // [4][H][GTILE]   combined direction planes
-    double *stg = smem + 4 * H * GTILE;                    // [2][H][G_STAGE] raw d_old / s of the plane in flight
-    uint16_t *mring = reinterpret_cast<uint16_t *>(stg + 2 * H * G_STAGE);  // [8][GETILE]
+    double2 *stg = reinterpret_cast<double2 *>(smem + 4 * H * GTILE);  // [2][H][G_STG] raw d_old / s pairs in flight
+    uint16_t *mring = reinterpret_cast<uint16_t *>(stg + 2 * H * G_STG);  // [8][GETILE]
     __shared__ double scratch[32];
-    __shared__ uint16_t qlist[GY * 32];  // queued interface node pairs, per warp row
-    __shared__ int qcnt[GY];
+    __shared__ uint16_t qlist[2][GY * 32];  // queued interface node pairs, per warp row, double-buffered by step parity
+    __shared__ int qcnt[2][GY];
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const int z0 = blockIdx.x * GZ, y0 = blockIdx.y * GY;
     const int xs = blockIdx.z * p.xchunk, xe = min(xs + p.xchunk, p.n0);
-    const int ry = wy + 1, rzA = 2 * lane + 1;  // tile coordinates of node A; node B = rzA + 1
-    const int yA = y0 + wy, zA = z0 + 2 * lane;
-    const bool valid = (yA < p.ny) && (zA < p.nz);  // nz is even, so A valid <=> B valid
-    const double beta = p.s ? *p.beta : 0.0;
-
-    // in-plane offsets of the tile positions this thread loads (fixed over the march): no div/mod in the x loop
-    constexpr int NLD = G_NLD, NLM = G_NLM;
-    int goff[NLD], moff[NLM];
-    unsigned mine_mask = 0;
-#pragma unroll
-    for (int j = 0; j < NLD; ++j) {
-        const int i = tid + j * G_THREADS;
-        goff[j] = -1;
-        if (i < GTILE) {
-            const int r = i / GPZ, c = i % GPZ;
-            goff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 1 + c, p.nz);
-            if (r >= 1 && r <= GY && c >= 1 && c <= GZ && (y0 - 1 + r) < p.ny && (z0 - 1 + c) < p.nz) mine_mask |= 1u << j;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < NLM; ++j) {
-        const int i = tid + j * G_THREADS;
-        moff[j] = -1;
-        if (i < GETILE) {
-            const int r = i / (GZ + 1), c = i % (GZ + 1);
-            moff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 1 + c, p.nz);
-        }
-    }
     const size_t plane_sz = (size_t)p.ny * p.nz;
-    // issue: raw values of node plane xp -> this thread's staging slots (asynchronous, nothing held in registers)
-    auto issue = [&](int xp) {
-        const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
-        const double *hal = (p.halo_lo && xp < 0) ? p.halo_lo : ((p.halo_hi && xp >= p.n0) ? p.halo_hi : nullptr);
-        const double *srcd = hal ? hal : p.d_old + gbase;
-        const size_t cs = hal ? plane_sz : p.nloc;
-#pragma unroll
-        for (int j = 0; j < NLD; ++j)
-            if (goff[j] >= 0) {
-#pragma unroll
-                for (int cc = 0; cc < H; ++cc) cp_async8(stg + cc * G_STAGE + tid + j * G_THREADS, srcd + cc * cs + goff[j]);
-            }
-        if (p.s && !hal) {
-#pragma unroll
-            for (int j = 0; j < NLD; ++j)
-                if (goff[j] >= 0) {
-#pragma unroll
-                    for (int cc = 0; cc < H; ++cc)
-                        cp_async8(stg + (H + cc) * G_STAGE + tid + j * G_THREADS, p.s + cc * p.nloc + gbase + goff[j]);
-                }
-        }
-    };
-    // combine: staging -> ring slot of plane xp as d = s + beta d_old (halo planes and the plain operator: d as is)
-    auto combine = [&](int xp, bool owned) {
-        const size_t gbase = (size_t)gwrap(xp, p.n0) * plane_sz;
-        const bool hal = (p.halo_lo && xp < 0) || (p.halo_hi && xp >= p.n0);
-        const bool upd = p.s && !hal;
-        double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
-        cp_async_wait_all();
-#pragma unroll
-        for (int j = 0; j < NLD; ++j)
-            if (goff[j] >= 0) {
-#pragma unroll
-                for (int cc = 0; cc < H; ++cc) {
-                    double v = stg[cc * G_STAGE + tid + j * G_THREADS];
-                    if (upd) {
-                        v = stg[(H + cc) * G_STAGE + tid + j * G_THREADS] + beta * v;
-                        if (owned && ((mine_mask >> j) & 1u)) p.d_new[cc * p.nloc + gbase + goff[j]] = v;
-                    }
-                    pl[cc * GTILE + tid + j * G_THREADS] = v;
-                }
-            }
-    };
-    auto ms_src = [&](int xp) { return (p.ms_lo && xp < 0) ? p.ms_lo : p.phidx + (size_t)gwrap(xp, p.n0) * plane_sz; };
-    uint16_t msr[NLM];
-    auto ms_fetch = [&](int xp) {
-        const uint16_t *src = ms_src(xp);
-#pragma unroll
-        for (int j = 0; j < NLM; ++j) msr[j] = (moff[j] >= 0) ? __ldg(src + moff[j]) : (uint16_t)0;
-    };
-    auto ms_put = [&](int xp) {
-        uint16_t *mp = mring + ((xp + 8) & 7) * GETILE;
-#pragma unroll
-        for (int j = 0; j < NLM; ++j)
-            if (moff[j] >= 0) mp[tid + j * G_THREADS] = msr[j];
-    };
-
-    // prologue: plane xs-1 combined, plane xs in flight; element planes xs-1, xs in the ms ring, xs+1 in registers
-    issue(xs - 1);
-    ms_fetch(xs - 1);
-    ms_put(xs - 1);
-    ms_fetch(xs);
-    ms_put(xs);
-    combine(xs - 1, false);
-    issue(xs);
-    ms_fetch(xs + 1);
     double racc[1] = {0.0};
-    // accumulators of the output planes P-1, P, P+1 (slots 0,1,2) of this thread's node pair, with their homogeneity flags
-    double acc[3][2][H];
-    int hph[3] = {-1, -1, -1};  // phase of a homogeneous neighbourhood, -1: interface pair / outside the chunk / invalid thread
+
+    if (wy >= GY) {
+        // =================================== producer warpgroup ===================================
+        const int lane = tid - G_CONS;  // producer thread index 0..G_PROD-1
+        const double beta = p.s ? *p.beta : 0.0;
+        int goff[G_NLP], roff[G_NLP], moff[G_NLM];
+        unsigned mine_mask = 0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int c = 0; c < H; ++c) acc[j][0][c] = 0.0, acc[j][1][c] = 0.0;
-    // step P: plane P (combined, in the ring) is read once and scattered to the outputs P-1 (dx=+1), P (dx=0), P+1 (dx=-1);
-    // output plane P-1 is then complete.
-    for (int P = xs - 1; P <= xe; ++P) {
-        __syncthreads();  // (A) plane P and element plane P+1 are visible; phase 2 of the previous step is over
-        // ---- phase 1
-        const int o2 = P + 1;  // newest output plane: classify its node pair from the 12 elements around it (planes o2-1, o2)
-        hph[2] = -1;
-        if (valid && o2 >= xs && o2 < xe) {
-            const uint16_t *m0 = mring + ((o2 - 1 + 8) & 7) * GETILE, *m1 = mring + ((o2 + 8) & 7) * GETILE;
-            const int e00 = (ry - 1) * (GZ + 1) + rzA - 1, e10 = ry * (GZ + 1) + rzA - 1;
-            const int ph = m1[e10 + 1];
-            bool homog = true;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                homog = homog && (m0[e00 + c] == ph) && (m0[e10 + c] == ph) && (m1[e00 + c] == ph) && (m1[e10 + c] == ph);
-            hph[2] = homog ? ph : -1;
+        for (int j = 0; j < G_NLP; ++j) {
+            const int i = lane + j * G_PROD;
+            goff[j] = -1, roff[j] = 0;
+            if (i < GPAIRS) {
+                const int r = i / (GPZ / 2), q = i % (GPZ / 2);
+                goff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 2 + 2 * q, p.nz);
+                roff[j] = r * GPZ + 2 * q;
+                if (r >= 1 && r <= GY && q >= 1 && q <= GZ / 2 && (y0 - 1 + r) < p.ny && (z0 - 2 + 2 * q) < p.nz) mine_mask |= 1u << j;
+            }
         }
-        const double *pl = ring + (size_t)((P + 4) & 3) * H * GTILE;
-        if (hph[0] >= 0 || hph[1] >= 0 || hph[2] >= 0) {
-            double v[H][4];
+#pragma unroll
+        for (int j = 0; j < G_NLM; ++j) {
+            const int i = lane + j * G_PROD;
+            moff[j] = -1;
+            if (i < GETILE) {
+                const int r = i / (GZ + 1), c = i % (GZ + 1);
+                moff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 1 + c, p.nz);
+            }
+        }
+        auto issue = [&](int xp) {
+            const bool lo = (p.halo_lo && xp < 0), hi = (p.halo_hi && xp >= p.n0);
+            const double *hal = lo ? p.halo_lo : (hi ? p.halo_hi : nullptr);
+            const size_t gbase = (xp < 0 ? (size_t)(xp + p.n0) : (xp >= p.n0 ? (size_t)(xp - p.n0) : (size_t)xp)) * plane_sz;
+            const double *srcd = hal ? hal : p.d_old + gbase;
+            const size_t cs = hal ? plane_sz : p.nloc;
+#pragma unroll
+            for (int cc = 0; cc < H; ++cc)
+#pragma unroll
+                for (int j = 0; j < G_NLP; ++j)
+                    if (goff[j] >= 0) cp_async16(stg + cc * G_STG + lane + j * G_PROD, srcd + cc * cs + goff[j]);
+            if (p.s && !hal) {
+#pragma unroll
+                for (int cc = 0; cc < H; ++cc)
+#pragma unroll
+                    for (int j = 0; j < G_NLP; ++j)
+                        if (goff[j] >= 0) cp_async16(stg + (H + cc) * G_STG + lane + j * G_PROD, p.s + cc * p.nloc + gbase + goff[j]);
+            }
+        };
+        auto combine = [&](int xp, bool owned) {
+            const bool hal = (p.halo_lo && xp < 0) || (p.halo_hi && xp >= p.n0);
+            const bool upd = p.s && !hal;
+            const size_t gbase = (xp < 0 ? (size_t)(xp + p.n0) : (xp >= p.n0 ? (size_t)(xp - p.n0) : (size_t)xp)) * plane_sz;
+            double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
+#pragma unroll
+            for (int cc = 0; cc < H; ++cc)
+#pragma unroll
+                for (int j = 0; j < G_NLP; ++j)
+                    if (goff[j] >= 0) {
+                        double2 v = stg[cc * G_STG + lane + j * G_PROD];
+                        if (upd) {
+                            const double2 sv = stg[(H + cc) * G_STG + lane + j * G_PROD];
+                            v.x = sv.x + beta * v.x, v.y = sv.y + beta * v.y;
+                            if (owned && ((mine_mask >> j) & 1u)) *reinterpret_cast<double2 *>(p.d_new + cc * p.nloc + gbase + goff[j]) = v;
+                        }
+                        *reinterpret_cast<double2 *>(pl + cc * GTILE + roff[j]) = v;
+                    }
+        };
+        uint16_t msr[G_NLM];
+        auto ms_fetch = [&](int xp) {
+            const uint16_t *src = (p.ms_lo && xp < 0) ? p.ms_lo : p.phidx + (size_t)gwrap(xp, p.n0) * plane_sz;
+#pragma unroll
+            for (int j = 0; j < G_NLM; ++j) msr[j] = (moff[j] >= 0) ? __ldg(src + moff[j]) : (uint16_t)0;
+        };
+        auto ms_put = [&](int xp) {
+            uint16_t *mp = mring + ((xp + 8) & 7) * GETILE;
+#pragma unroll
+            for (int j = 0; j < G_NLM; ++j)
+                if (moff[j] >= 0) mp[lane + j * G_PROD] = msr[j];
+        };
+        issue(xs - 1);
+        ms_fetch(xs - 1);
+        ms_put(xs - 1);
+        ms_fetch(xs);
+        for (int Q = xs - 1; Q <= xe; ++Q) {
+            cp_async_wait_all();
+            if (Q >= xs + 3) bar_sync(BAR_EMPTY + (Q & 3), G_THREADS);  // consumers have left plane Q-4
+            combine(Q, Q >= xs && Q < xe);
+            ms_put(Q + 1);
+            bar_arrive(BAR_FULL + (Q & 3), G_THREADS);
+            if (Q + 1 <= xe) {
+                issue(Q + 1);   // lands while the consumers work on plane Q
+                ms_fetch(Q + 2);
+            }
+        }
+    } else {
+        // =================================== consumer warps ===================================
+        const int ry = wy + 1, rzA = 2 * lane + 2;  // tile coordinates of node A (column = z - z0 + 2); node B = rzA + 1
+        const int rzM = 2 * lane + 1;               // column of node A in the phase-image tile (z - z0 + 1)
+        const int yA = y0 + wy, zA = z0 + 2 * lane;
+        const bool valid = (yA < p.ny) && (zA < p.nz);  // nz is even, so A valid <=> B valid
+        // accumulators of the output planes P-1, P, P+1 (slots 0,1,2) of this thread's node pair, with their homogeneity flags
+        double acc[3][2][H];
+        int hph[3] = {-1, -1, -1};  // phase of a homogeneous neighbourhood, -1: interface pair / outside the chunk / invalid thread
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int c = 0; c < H; ++c) acc[j][0][c] = 0.0, acc[j][1][c] = 0.0;
+        for (int P = xs - 1; P <= xe; ++P) {
+            bar_sync(BAR_FULL + (P & 3), G_THREADS);  // plane P and element plane P+1 are in the rings
+            // ---- phase 1
+            const int o2 = P + 1;  // newest output plane: classify its node pair from the 12 elements around it (planes o2-1, o2)
+            hph[2] = -1;
+            if (valid && o2 >= xs && o2 < xe) {
+                const uint16_t *m0 = mring + ((o2 - 1 + 8) & 7) * GETILE, *m1 = mring + ((o2 + 8) & 7) * GETILE;
+                const int e00 = (ry - 1) * (GZ + 1) + rzM - 1, e10 = ry * (GZ + 1) + rzM - 1;
+                const int ph = m1[e10 + 1];
+                bool homog = true;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    homog = homog && (m0[e00 + c] == ph) && (m0[e10 + c] == ph) && (m1[e00 + c] == ph) && (m1[e10 + c] == ph);
+                hph[2] = homog ? ph : -1;
+            }
+            const double *pl = ring + (size_t)((P + 4) & 3) * H * GTILE;
+            if (hph[0] >= 0 || hph[1] >= 0 || hph[2] >= 0) {
+                double v[H][4];
 #define ST_ROW(DY)                                                                                              \
     {                                                                                                           \
         _Pragma("unroll") for (int c = 0; c < H; ++c)                                                           \
         {                                                                                                       \
-            const double2 *p2 = reinterpret_cast<const double2 *>(pl + c * GTILE + (ry + DY - 1) * GPZ + rzA - 1); \
-            const double2 a = p2[0], b = p2[1];                                                                 \
-            v[c][0] = a.x, v[c][1] = a.y, v[c][2] = b.x, v[c][3] = b.y;                                         \
+            const double2 *p2 = reinterpret_cast<const double2 *>(pl + c * GTILE + (ry + DY - 1) * GPZ + rzA - 2); \
+            const double2 a = p2[0], b = p2[1], d = p2[2];                                                      \
+            v[c][0] = a.y, v[c][1] = b.x, v[c][2] = b.y, v[c][3] = d.x;                                         \
         }                                                                                                       \
         if (hph[0] >= 0) stencil_row_dispatch<H, NQ, ISO, 2, DY>(hph[0], v, acc[0][0], acc[0][1]);               \
         if (hph[1] >= 0) stencil_row_dispatch<H, NQ, ISO, 1, DY>(hph[1], v, acc[1][0], acc[1][1]);               \
         if (hph[2] >= 0) stencil_row_dispatch<H, NQ, ISO, 0, DY>(hph[2], v, acc[2][0], acc[2][1]);               \
     }
-            ST_ROW(0)
-            ST_ROW(1)
-            ST_ROW(2)
+                ST_ROW(0)
+                ST_ROW(1)
+                ST_ROW(2)
 #undef ST_ROW
-        }
-        const int k = P - 1;  // the output plane completed by this step
-        const bool kin = (k >= xs);
-        const unsigned qmask = __ballot_sync(0xffffffffu, valid && kin && hph[0] < 0);
-        if (valid && kin && hph[0] >= 0) {
-            const size_t g = ((size_t)k * p.ny + yA) * p.nz + zA;
-            const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + ry * GPZ + rzA;
+            }
+            const int k = P - 1;  // the output plane completed by this step
+            const bool kin = (k >= xs);
+            const int par = P & 1;
+            const unsigned qmask = __ballot_sync(0xffffffffu, valid && kin && hph[0] < 0);
+            if (valid && kin && hph[0] >= 0) {
+                const size_t g = ((size_t)k * p.ny + yA) * p.nz + zA;
+                const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + ry * GPZ + rzA;
+#pragma unroll
+                for (int c = 0; c < H; ++c) {
+                    *reinterpret_cast<double2 *>(p.out + c * p.nloc + g) = make_double2(acc[0][0][c], acc[0][1][c]);
+                    const double2 cv = *reinterpret_cast<const double2 *>(ctr + c * GTILE);
+                    racc[0] += acc[0][0][c] * cv.x + acc[0][1][c] * cv.y;
+                }
+            }
+            if (qmask) {
+                if (valid && kin && hph[0] < 0) qlist[par][wy * 32 + __popc(qmask & ((1u << lane) - 1u))] = (uint16_t)(ry * 128 + rzA);
+            }
+            if (lane == 0) qcnt[par][wy] = __popc(qmask);
+            // rotate the output window
 #pragma unroll
             for (int c = 0; c < H; ++c) {
-                *reinterpret_cast<double2 *>(p.out + c * p.nloc + g) = make_double2(acc[0][0][c], acc[0][1][c]);
-                racc[0] += acc[0][0][c] * ctr[c * GTILE] + acc[0][1][c] * ctr[c * GTILE + 1];
+                acc[0][0][c] = acc[1][0][c], acc[0][1][c] = acc[1][1][c];
+                acc[1][0][c] = acc[2][0][c], acc[1][1][c] = acc[2][1][c];
+                acc[2][0][c] = 0.0, acc[2][1][c] = 0.0;
             }
-        }
-        if (qmask) {
-            if (valid && kin && hph[0] < 0) qlist[wy * 32 + __popc(qmask & ((1u << lane) - 1u))] = (uint16_t)(ry * 128 + rzA);
-        }
-        if (lane == 0) qcnt[wy] = __popc(qmask);
-        // rotate the output window
+            hph[0] = hph[1], hph[1] = hph[2];
+            bar_sync(BAR_CONS, G_CONS);
+            // ---- phase 2: the queued interface nodes of plane k, densely packed onto lanes (exact element form, planes k-1..k+1)
+            int pre[GY + 1];
+            pre[0] = 0;
 #pragma unroll
-        for (int c = 0; c < H; ++c) {
-            acc[0][0][c] = acc[1][0][c], acc[0][1][c] = acc[1][1][c];
-            acc[1][0][c] = acc[2][0][c], acc[1][1][c] = acc[2][1][c];
-            acc[2][0][c] = 0.0, acc[2][1][c] = 0.0;
-        }
-        hph[0] = hph[1], hph[1] = hph[2];
-        __syncthreads();  // (B)
-        // ---- phase 2: the queued interface nodes of plane k, densely packed onto lanes (exact element form, planes k-1..k+1)
-        int pre[GY + 1];
-        pre[0] = 0;
+            for (int w = 0; w < GY; ++w) pre[w + 1] = pre[w] + qcnt[par][w];
+            const int nitems = 2 * pre[GY];
+            for (int n = tid; n < nitems; n += G_CONS) {
+                const int pair = n >> 1;
+                int w = 0, base = 0;
 #pragma unroll
-        for (int w = 0; w < GY; ++w) pre[w + 1] = pre[w] + qcnt[w];
-        const int nitems = 2 * pre[GY];
-        for (int n = tid; n < nitems; n += G_THREADS) {
-            const int pair = n >> 1;
-            int w = 0, base = 0;
+                for (int q = 1; q < GY; ++q)
+                    if (pair >= pre[q]) w = q, base = pre[q];
+                const int code = qlist[par][w * 32 + (pair - base)];
+                const int qry = code >> 7, qrz = (code & 127) + (n & 1);
+                double a1[H];
 #pragma unroll
-            for (int q = 1; q < GY; ++q)
-                if (pair >= pre[q]) w = q, base = pre[q];
-            const int code = qlist[w * 32 + (pair - base)];
-            const int qry = code >> 7, qrz = (code & 127) + (n & 1);
-            double a1[H];
+                for (int c = 0; c < H; ++c) a1[c] = 0.0;
+                node_general<H, NQ>(ring, mring, k, qry, qrz, a1);
+                const size_t g = ((size_t)k * p.ny + (y0 + qry - 1)) * p.nz + (z0 + qrz - 2);
+                const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + qry * GPZ + qrz;
 #pragma unroll
-            for (int c = 0; c < H; ++c) a1[c] = 0.0;
-            node_general<H, NQ>(ring, mring, k, qry, qrz, a1);
-            const size_t g = ((size_t)k * p.ny + (y0 + qry - 1)) * p.nz + (z0 + qrz - 1);
-            const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + qry * GPZ + qrz;
-#pragma unroll
-            for (int c = 0; c < H; ++c) {
-                p.out[c * p.nloc + g] = a1[c];
-                racc[0] += a1[c] * ctr[c * GTILE];
+                for (int c = 0; c < H; ++c) {
+                    p.out[c * p.nloc + g] = a1[c];
+                    racc[0] += a1[c] * ctr[c * GTILE];
+                }
             }
-        }
-        // ---- refill: plane P+1 -> ring slot of plane P-3 (nobody reads it any more), element plane P+2 -> ms ring slot of P-6
-        if (P + 1 <= xe) {
-            combine(P + 1, (P + 1) < xe);
-            ms_put(P + 2);
-            if (P + 2 <= xe) {
-                issue(P + 2);  // lands during the whole next step
-                ms_fetch(P + 3);
-            }
+            // plane P-2 is not needed any more: its slot may take plane P+2
+            if (P >= xs + 1 && P + 2 <= xe) bar_arrive(BAR_EMPTY + ((P + 2) & 3), G_THREADS);
         }
     }
-    cp_async_wait_all();
     if (p.red_out) grid_reduce<1, 1>(racc, scratch, p.part, p.ticket, p.red_out);
 }
 
@@ -451,7 +463,7 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < want) xchunk = (xchunk + 1) / 2;
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
-    const size_t smem = sizeof(double) * (4 * h * GTILE + 2 * h * G_STAGE) + sizeof(uint16_t) * 8 * GETILE + 16;
+    const size_t smem = sizeof(double) * 4 * h * GTILE + sizeof(double2) * 2 * h * G_STG + sizeof(uint16_t) * 8 * GETILE + 16;
     prof_begin(ctx, PC_SWEEP_LINEAR);
     int rc = FANS_ERR_ARG;
 #define ST_CASE(H_, Q_) \
