@@ -145,45 +145,63 @@ __device__ __forceinline__ void rp_get(double2 *a, int tid, const double2 *sm, I
     for (int e = 0; e < rp_elems(N); ++e) a[e] = sm[idx(rp_row<N, S>(tid, e))];
 }
 
+// barrier policy of the stage exchanges: the whole CTA (default) or one named barrier per thread group (x pass: the H component
+// groups run their transforms independently, so one group's butterflies overlap another group's shared-memory exchange)
+struct SyncCta {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct SyncWarp {  // every transform lives inside one warp (z pass, nz <= 512): no CTA barrier at all
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+template <bool NAMED>  // NAMED only when the group is a whole number of warps and not the whole CTA
+struct SyncGroup {
+    int id, count;
+    __device__ __forceinline__ void operator()() const
+    {
+        if (NAMED) asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+        else __syncthreads();
+    }
+};
+
 // Full forward transform of the registers that were loaded with the stage-0 mapping; leaves the last-stage mapping.
 // NC independent transforms (components) share the barriers; sm holds NC tiles of `tile_elems` double2.
-template <int N, int NC, class IDX, int S = 0>
+template <int N, int NC, class IDX, int S = 0, class SYNC = SyncCta>
 __device__ __forceinline__ void rp_forward(double2 (*a)[rp_elems(N)], int tid, double2 *sm, int tile_elems, IDX idx,
-                                           const double2 *__restrict__ tw, int twmul)
+                                           const double2 *__restrict__ tw, int twmul, SYNC sync = SYNC())
 {
     if constexpr (S < rp_nstages(N)) {
         if constexpr (S > 0) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) rp_put<N, S - 1>(a[c], tid, sm + c * tile_elems, idx);
-            __syncthreads();
+            sync();
 #pragma unroll
             for (int c = 0; c < NC; ++c) rp_get<N, S>(a[c], tid, sm + c * tile_elems, idx);
-            if constexpr (S + 1 < rp_nstages(N)) __syncthreads();
+            if constexpr (S + 1 < rp_nstages(N)) sync();
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) rp_stage<N, S, false>(a[c], tid, tw, twmul);
-        rp_forward<N, NC, IDX, S + 1>(a, tid, sm, tile_elems, idx, tw, twmul);
+        rp_forward<N, NC, IDX, S + 1, SYNC>(a, tid, sm, tile_elems, idx, tw, twmul, sync);
     }
 }
 
 // Full inverse transform: registers hold the last-stage mapping on entry, the stage-0 mapping (natural rows) on exit.
 // `first_sync`: the caller has used sm before (needs a barrier before the first put).
-template <int N, int NC, class IDX, int S = rp_nstages(N) - 1>
+template <int N, int NC, class IDX, int S = rp_nstages(N) - 1, class SYNC = SyncCta>
 __device__ __forceinline__ void rp_inverse(double2 (*a)[rp_elems(N)], int tid, double2 *sm, int tile_elems, IDX idx,
-                                           const double2 *__restrict__ tw, int twmul)
+                                           const double2 *__restrict__ tw, int twmul, SYNC sync = SYNC())
 {
     if constexpr (S >= 0) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) rp_stage<N, S, true>(a[c], tid, tw, twmul);
         if constexpr (S > 0) {
-            __syncthreads();  // previous readers of sm are done
+            sync();  // previous readers of sm are done
 #pragma unroll
             for (int c = 0; c < NC; ++c) rp_put<N, S>(a[c], tid, sm + c * tile_elems, idx);
-            __syncthreads();
+            sync();
 #pragma unroll
             for (int c = 0; c < NC; ++c) rp_get<N, S - 1>(a[c], tid, sm + c * tile_elems, idx);
         }
-        rp_inverse<N, NC, IDX, S - 1>(a, tid, sm, tile_elems, idx, tw, twmul);
+        rp_inverse<N, NC, IDX, S - 1, SYNC>(a, tid, sm, tile_elems, idx, tw, twmul, sync);
     }
 }
 

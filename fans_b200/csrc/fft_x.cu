@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
     const int c = threadIdx.x / NTC, tc = threadIdx.x % NTC;
     const int t = tc % T, jt = tc / T;
     const TileIdxX<T> idx{t};
+    using GSync = SyncGroup<(H > 1 && NTC % 32 == 0)>;
+    const GSync gsync{1 + c, NTC};  // the stage exchanges of one component only involve its own thread group
     auto tile_ptr = [&](int w) { return spec + (size_t)c * g.cStride + (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t; };
     auto issue = [&](int w, int buf) {
         const double2 *src = tile_ptr(w);
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
         for (int e = 0; e < E; ++e) a[0][e] = X[e * NTC + tc];
         __syncthreads();  // everybody holds its rows (and is done with the previous tile): both buffers may be overwritten
         if (w + (int)gridDim.x < nWork) issue(w + gridDim.x, cur ^ 1);
-        rp_forward<N, 1>(a, jt, X, 0, idx, tw, 1);
+        rp_forward<N, 1, TileIdxX<T>, 0, GSync>(a, jt, X, 0, idx, tw, 1, gsync);
         // Green operator; storage row of register e after the last stage = jt*E + e
         if (H == 1) {
 #pragma unroll
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
             constexpr size_t NT = (size_t)N * T;
             // packed upper triangle 00,01,02,11,12,22: row c of the symmetric matrix
             const int k0 = (c == 0) ? 0 : (c == 1 ? 1 : 2), k1 = (c == 0) ? 1 : (c == 1 ? 3 : 4), k2 = (c == 0) ? 2 : (c == 1 ? 4 : 5);
-            if (NST > 1) __syncthreads();  // everybody is done reading the last exchange
+            if (NST > 1) gsync();  // this group is done reading its last exchange
 #pragma unroll
             for (int e = 0; e < E; ++e) X[e * NTC + tc] = a[0][e];
             double gc[E][3];  // issued after the put (a[] is dead) so the loads fly while the CTA gathers at the barrier
@@ -92,8 +94,9 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
                 const double2 r0 = S[e * NTC + tc], r1 = S[(H > 1 ? 1 : 0) * (N * T) + e * NTC + tc], r2 = S[(H > 2 ? 2 : 0) * (N * T) + e * NTC + tc];
                 a[0][e] = make_double2(gc[e][0] * r0.x + gc[e][1] * r1.x + gc[e][2] * r2.x, gc[e][0] * r0.y + gc[e][1] * r1.y + gc[e][2] * r2.y);
             }
+            if (NST > 1) __syncthreads();  // the other groups have read this group's slots: its tile may serve the inverse exchanges
         }
-        rp_inverse<N, 1>(a, jt, X, 0, idx, tw, 1);
+        rp_inverse<N, 1, TileIdxX<T>, NST - 1, GSync>(a, jt, X, 0, idx, tw, 1, gsync);
         if (peers.on) {  // plane x belongs to rank x / n0: store it into that rank's x-slab spectrum, block `me`
             const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t;
 #pragma unroll

@@ -14,6 +14,16 @@ struct LineIdx {  // padded line: +1 slot per 8 rows, +1 per 64 rows -> conflict
 __host__ __device__ constexpr int zline_pitch(int NH) { return NH + NH / 8 + NH / 64 + 2; }
 __host__ __device__ constexpr int z_tpl(int NH) { return NH / rp_elems(NH); }
 __host__ __device__ constexpr int z_lpb(int NH) { return z_tpl(NH) >= 256 ? 1 : 256 / z_tpl(NH); }
+// a line is carried by z_tpl threads: up to 32 they sit in one warp and the stage exchanges only need __syncwarp
+template <int NH> struct ZSyncSel { using type = SyncCta; };
+template <> struct ZSyncSel<2> { using type = SyncWarp; };
+template <> struct ZSyncSel<4> { using type = SyncWarp; };
+template <> struct ZSyncSel<8> { using type = SyncWarp; };
+template <> struct ZSyncSel<16> { using type = SyncWarp; };
+template <> struct ZSyncSel<32> { using type = SyncWarp; };
+template <> struct ZSyncSel<64> { using type = SyncWarp; };
+template <> struct ZSyncSel<128> { using type = SyncWarp; };
+template <> struct ZSyncSel<256> { using type = SyncWarp; };
 
 __device__ __forceinline__ size_t spec_line(const SpecGeom &g, int ny, size_t line)
 {
@@ -39,10 +49,12 @@ __global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zf(const double *
     const double2 *in = reinterpret_cast<const double2 *>(real) + line * NH;
 #pragma unroll
     for (int e = 0; e < E; ++e) a[0][e] = valid ? in[rp_row<NH, 0>(jt, e)] : make_double2(0.0, 0.0);
-    rp_forward<NH, 1>(a, jt, sml, 0, idx, tw, 2);  // table length nz = 2 Nh
-    if (NST > 1) __syncthreads();
+    using ZSync = typename ZSyncSel<NH>::type;
+    const ZSync zsync;
+    rp_forward<NH, 1, LineIdx, 0, ZSync>(a, jt, sml, 0, idx, tw, 2, zsync);  // table length nz = 2 Nh
+    if (NST > 1) zsync();
     rp_put<NH, NST - 1>(a[0], jt, sml, idx);
-    __syncthreads();
+    zsync();
     if (!valid) return;
     double2 *out = spec + spec_line(g, ny, line);
     for (int k = jt; k <= NH / 2; k += TPL) {
@@ -86,10 +98,12 @@ __global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zi(const double2 
     } else {
         for (int k = jt; k < NH; k += TPL) sml[idx(k)] = make_double2(0.0, 0.0);
     }
-    __syncthreads();
+    using ZSync = typename ZSyncSel<NH>::type;
+    const ZSync zsync;
+    zsync();
     double2 a[1][E];
     rp_get<NH, NST - 1>(a[0], jt, sml, idx);
-    rp_inverse<NH, 1>(a, jt, sml, 0, idx, tw, 2);
+    rp_inverse<NH, 1, LineIdx, NST - 1, ZSync>(a, jt, sml, 0, idx, tw, 2, zsync);
     double acc[1] = {0.0};
     if (valid) {
         double2 *out = reinterpret_cast<double2 *>(real) + line * NH;

@@ -458,7 +458,7 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     }
     const int gy = (ctx->ny + GY - 1) / GY, gz = (ctx->nz + GZ - 1) / GZ;
     int xchunk = ctx->n0;
-    long want = 48L * FANS_SMS;
+    long want = 24L * FANS_SMS;  // 12 waves of 2 resident CTAs per SM; longer marches amortise the 2-plane run-in
     if (const char *env = getenv("FANS_STENCIL_CTAS")) want = atol(env);
     while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < want) xchunk = (xchunk + 1) / 2;
     p.xchunk = xchunk;
