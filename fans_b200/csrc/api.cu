@@ -311,16 +311,13 @@ static int create_rest(fans_ctx *ctx)
     ctx->kzc = ctx->nz / 2 + 1;
     ctx->kzp = (ctx->kzc + 7) / 8 * 8;
     ctx->gT = fft_x_tile_width(ctx->nx, ctx->h);
-    if (const char *e = getenv("FANS_GT")) {
-        const int v = atoi(e);
-        if ((v == 2 || v == 4 || (v == 8 && ctx->h == 1)) && (size_t)ctx->h * ctx->nx * v * sizeof(double2) <= 200 * 1024 && ctx->h * (ctx->nx / 8) * v <= 1024) ctx->gT = v;
-    }
     ctx->yT = (ctx->ny >= 1024) ? 4 : 8;  // 512: T=8 -> 512 threads, 64 registers, 2 CTAs/SM (1.08 ms vs 1.39 ms with T=4)
     if (const char *e = getenv("FANS_YT")) ctx->yT = (atoi(e) == 4) ? 4 : 8;
     FANS_CHECK(fft_plan_init(ctx, ctx->planx, ctx->nx, ctx->nx));
     FANS_CHECK(fft_plan_init(ctx, ctx->plany, ctx->ny, ctx->ny));
     FANS_CHECK(fft_plan_init(ctx, ctx->planz, ctx->nz / 2, ctx->nz));
-    const size_t spec_elems = (size_t)ctx->h * ctx->n0 * ctx->ny * ctx->kzp;
+    if (const char *env = getenv("FANS_XPAD")) ctx->xpad = atoi(env);
+    const size_t spec_elems = (size_t)ctx->P * ctx->h * ctx->n0 * ((size_t)ctx->n1 * ctx->kzp + ctx->xpad);
     CUDA_TRY(ctx, cudaMalloc(&ctx->spec, sizeof(double2) * spec_elems));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec, 0, sizeof(double2) * spec_elems, ctx->st));
     if (ctx->P > 1) {  // the transposed spectrum: this rank's y rows for all x

@@ -149,7 +149,7 @@ int comm_halo(fans_ctx *ctx, const void *to_prev, void *from_next, const void *t
 int comm_alltoall(fans_ctx *ctx, const double2 *src, double2 *dst)
 {
     const int P = ctx->P;
-    const size_t blk = (size_t)ctx->h * ctx->n0 * ctx->n1 * ctx->kzp;  // double2 elements per block
+    const size_t blk = (size_t)ctx->h * ctx->n0 * ((size_t)ctx->n1 * ctx->kzp + ctx->xpad);  // double2 elements per block
     ncclComm_t c = (ncclComm_t)ctx->cfg.nccl_comm;
     prof_begin(ctx, PC_COMM_A2A);
     CUDA_TRY(ctx, cudaMemcpyAsync(dst + (size_t)ctx->rank * blk, src + (size_t)ctx->rank * blk, sizeof(double2) * blk, cudaMemcpyDeviceToDevice, ctx->st));

@@ -65,6 +65,7 @@ struct fans_ctx {
 
     // spectrum + Green operator
     int kzc = 0, kzp = 0;      // nz/2+1 and padded pitch (complex elements)
+    int xpad = 0;              // complex elements appended to every x plane of the spectrum (FANS_XPAD; measured: no effect on B200)
     double2 *spec = nullptr;   // [h][n0][ny][kzp]   (P==1)   /   transposed [h][n1][nx][kzp] (P>1)
     double *gamma = nullptr;   // tile-major layout, see gamma.cu
     double2 *specB = nullptr;  // P > 1: the transposed spectrum (this rank's y rows, all x), blocks [p][h][n0][n1][kzp]

@@ -208,13 +208,14 @@ __device__ __forceinline__ void rp_inverse(double2 (*a)[rp_elems(N)], int tid, d
 // where the spectrum lives (single GPU: one block; P ranks: P blocks of [h][n0][n1][kzp])
 struct SpecGeom {
     int n0, n1, l2n0, l2n1, kzp, h;
-    size_t cStride;    // n0*n1*kzp          (one component inside a block)
+    size_t xStride;    // n1*kzp + pad       (one x plane; the pad keeps the 2^k-strided rows of the x pass off the same DRAM channels)
+    size_t cStride;    // n0*xStride         (one component inside a block)
     size_t blkStride;  // h*cStride          (one rank block)
 };
 __device__ __forceinline__ size_t spec_row_y(const SpecGeom &g, int y) { return (size_t)(y >> g.l2n1) * g.blkStride + (size_t)(y & (g.n1 - 1)) * g.kzp; }
 __device__ __forceinline__ size_t spec_row_x(const SpecGeom &g, int x)
 {
-    return (size_t)(x >> g.l2n0) * g.blkStride + (size_t)(x & (g.n0 - 1)) * ((size_t)g.n1 * g.kzp);
+    return (size_t)(x >> g.l2n0) * g.blkStride + (size_t)(x & (g.n0 - 1)) * g.xStride;
 }
 
 // Fused transpose: where the last pass before a transpose stores its rows.  on == 0: locally (blocks of this rank's buffer,

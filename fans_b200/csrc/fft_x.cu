@@ -102,13 +102,96 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int row = rp_row<N, 0>(jt, e);
-                peer_select(peers, row >> g.l2n0)[off + (size_t)(row & (g.n0 - 1)) * ((size_t)g.n1 * g.kzp)] = a[0][e];
+                peer_select(peers, row >> g.l2n0)[off + (size_t)(row & (g.n0 - 1)) * g.xStride] = a[0][e];
             }
         } else {
 #pragma unroll
             for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
         }
     }
+}
+
+// Sequential-component variant (H = 3): one thread group of (N/E)*T threads carries the three components through the forward
+// transform one after the other, parks each result in thread-private slots of that component's tile, applies the full symmetric
+// Gamma_hat block to its own frequencies (no cross-thread traffic, no barrier) and runs the three inverse transforms.  A third of
+// the threads and of the registers of k_fft_xg per tile, so TWO independent CTAs fit on an SM and one CTA's butterflies overlap the
+// other's loads, stores and shared-memory exchanges.
+template <int N, int T>
+__global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 * 1024) ? 2 : 1)
+    k_fft_xg_seq(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,
+                 int nWork, PeerTable peers)
+{
+    extern __shared__ double2 sm[];  // [3][N*T]
+    constexpr int H = 3, E = rp_elems(N), TPC = N / E, NST = rp_nstages(N), NG = 6, NTC = TPC * T;
+    constexpr size_t NT = (size_t)N * T;
+    const int tc = threadIdx.x, t = tc % T, jt = tc / T;
+    const TileIdxX<T> idx{t};
+    for (int w = blockIdx.x; w < nWork; w += gridDim.x) {
+        const size_t off = (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t;
+        double2 a[1][E];
+#pragma unroll 1
+        for (int c = 0; c < H; ++c) {
+            double2 *X = sm + c * NT;
+            const double2 *base = spec + (size_t)c * g.cStride + off;
+#pragma unroll
+            for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_x(g, rp_row<N, 0>(jt, e))];
+            rp_forward<N, 1>(a, jt, X, 0, idx, tw, 1);
+            if (NST > 1) __syncthreads();  // everybody is done reading the last exchange of this component
+#pragma unroll
+            for (int e = 0; e < E; ++e) X[e * NTC + tc] = a[0][e];  // storage row of register e = jt*E + e
+        }
+        // Green operator on this thread's own frequencies: packed upper triangle 00,01,02,11,12,22
+        const double *gam = gamma + (size_t)w * NG * NT + tc;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const double *ge = gam + (size_t)e * NTC;
+            const double g00 = __ldg(ge), g01 = __ldg(ge + NT), g02 = __ldg(ge + 2 * NT), g11 = __ldg(ge + 3 * NT), g12 = __ldg(ge + 4 * NT),
+                         g22 = __ldg(ge + 5 * NT);
+            const double2 r0 = sm[e * NTC + tc], r1 = sm[NT + e * NTC + tc], r2 = sm[2 * NT + e * NTC + tc];
+            sm[e * NTC + tc] = make_double2(g00 * r0.x + g01 * r1.x + g02 * r2.x, g00 * r0.y + g01 * r1.y + g02 * r2.y);
+            sm[NT + e * NTC + tc] = make_double2(g01 * r0.x + g11 * r1.x + g12 * r2.x, g01 * r0.y + g11 * r1.y + g12 * r2.y);
+            sm[2 * NT + e * NTC + tc] = make_double2(g02 * r0.x + g12 * r1.x + g22 * r2.x, g02 * r0.y + g12 * r1.y + g22 * r2.y);
+        }
+#pragma unroll 1
+        for (int c = 0; c < H; ++c) {
+            double2 *X = sm + c * NT;
+#pragma unroll
+            for (int e = 0; e < E; ++e) a[0][e] = X[e * NTC + tc];
+            rp_inverse<N, 1>(a, jt, X, 0, idx, tw, 1);  // its first barrier also covers the slot reads above
+            if (peers.on) {
+                const size_t poff = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + off;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int row = rp_row<N, 0>(jt, e);
+                    peer_select(peers, row >> g.l2n0)[poff + (size_t)(row & (g.n0 - 1)) * g.xStride] = a[0][e];
+                }
+            } else {
+                double2 *base = spec + (size_t)c * g.cStride + off;
+#pragma unroll
+                for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
+            }
+        }
+    }
+}
+
+template <int N, int T>
+static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const PeerTable &peers)
+{
+    constexpr int E = rp_elems(N), NTHR = (N / E) * T;
+    const int nTiles = (ctx->kzc + T - 1) / T;
+    const size_t smem = 3 * sizeof(double2) * N * T;
+    static int resident = 0;
+    if (!resident) {
+        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg_seq<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fft_xg_seq<N, T>, NTHR, smem));
+        if (resident < 1) resident = 1;
+    }
+    const int nWork = ctx->n1 * nTiles;
+    int grid = FANS_SMS * resident;
+    if (const char *env = getenv("FANS_XG_GRID")) grid = atoi(env);
+    if (grid > nWork) grid = nWork;
+    k_fft_xg_seq<N, T><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
+    return FANS_OK;
 }
 
 template <int N, int H, int T>
@@ -138,8 +221,12 @@ static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const Pee
 // tile width of the fused x pass for a given (nx, howmany): keeps the exchange tile within ~100 KB
 int fft_x_tile_width(int nx, int h)
 {
-    int T = (h == 1) ? 8 : 4;
+    int T = (h == 1 || (h == 3 && nx >= 64 && !getenv("FANS_XG_OLD"))) ? 8 : 4;
     if (const char *env = getenv("FANS_XG_T")) T = atoi(env);
+    if (h == 3 && nx >= 64 && !getenv("FANS_XG_OLD")) {  // sequential-component variant: one tile buffer of all components
+        while ((3 * (size_t)nx * T * sizeof(double2) > 200 * 1024 || (nx / 8) * T > 1024) && T > 2) T /= 2;
+        return T;
+    }
     while ((2 * (size_t)h * nx * T * sizeof(double2) > 200 * 1024 || h * (nx / 8) * T > 1024) && T > 2) T /= 2;
     return T;
 }
@@ -154,10 +241,12 @@ int fft_pass_x_gamma(fans_ctx *ctx)
     PeerTable peers;
     for (int q = 0; q < 8; ++q) peers.p[q] = ctx->peerA[q];
     peers.me = ctx->rank;
+    const bool seq = ctx->h == 3 && ctx->nx >= 64 && !getenv("FANS_XG_OLD");  // the sequential-component kernel (two CTAs per SM or 128-byte rows)
     peers.on = 0;  // the x pass stays local (in place on the transposed spectrum); the y passes carry both transposes
 #define X_CASE(N_)                                                                                     \
     case N_:                                                                                           \
         if (ctx->h == 1) rc = (T == 8) ? launch_xg<N_, 1, 8>(ctx, specB, g, peers) : (T == 4 ? launch_xg<N_, 1, 4>(ctx, specB, g, peers) : launch_xg<N_, 1, 2>(ctx, specB, g, peers)); \
+        else if (seq && N_ >= 64) rc = (T == 8 && N_ <= 512) ? launch_xg_seq<(N_ <= 512 ? N_ : 64), 8>(ctx, specB, g, peers) : ((T == 4) ? launch_xg_seq<N_, 4>(ctx, specB, g, peers) : launch_xg_seq<N_, 2>(ctx, specB, g, peers));  \
         else rc = (T == 4) ? launch_xg<N_, 3, 4>(ctx, specB, g, peers) : launch_xg<N_, 3, 2>(ctx, specB, g, peers);  \
         break;
     switch (ctx->nx) {

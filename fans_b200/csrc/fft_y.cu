@@ -27,7 +27,7 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T 
     const int tile = b % nTiles;
     b /= nTiles;
     const int xl = b % g.n0, c = b / g.n0;
-    double2 *base = spec + (size_t)c * g.cStride + (size_t)xl * g.n1 * g.kzp + (size_t)tile * T + t;
+    double2 *base = spec + (size_t)c * g.cStride + (size_t)xl * g.xStride + (size_t)tile * T + t;
     const TileIdx<T> idx{t};
     double2 a[1][E];
     (void)TPC;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T 
         for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_y(g, rp_row<N, 0>(jt, e))];
         rp_forward<N, 1>(a, jt, sm, N * T, idx, tw, 1);
         if (peers.on) {  // row y belongs to rank y / n1: store it into that rank's transposed spectrum, block `me`
-            const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)xl * g.n1 * g.kzp + (size_t)tile * T + t;
+            const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)xl * g.xStride + (size_t)tile * T + t;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int row = rp_row<N, NST - 1>(jt, e);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T 
         }
     } else {
         if (peers.on) {  // row y lives in rank (y / n1)'s transposed spectrum, block `me`: pull it over NVLink
-            const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)xl * g.n1 * g.kzp + (size_t)tile * T + t;
+            const size_t off = (size_t)peers.me * g.blkStride + (size_t)c * g.cStride + (size_t)xl * g.xStride + (size_t)tile * T + t;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int row = rp_row<N, NST - 1>(jt, e);
@@ -91,7 +91,8 @@ SpecGeom spec_geom_A(const fans_ctx *ctx)
     g.l2n1 = rp_log2(ctx->n1);
     g.kzp = ctx->kzp;
     g.h = ctx->h;
-    g.cStride = (size_t)ctx->n0 * ctx->n1 * ctx->kzp;
+    g.xStride = (size_t)ctx->n1 * ctx->kzp + ctx->xpad;
+    g.cStride = (size_t)ctx->n0 * g.xStride;
     g.blkStride = (size_t)ctx->h * g.cStride;
     return g;
 }

@@ -30,7 +30,7 @@ __device__ __forceinline__ size_t spec_line(const SpecGeom &g, int ny, size_t li
     const int y = (int)(line % ny);
     const size_t r = line / ny;
     const int xl = (int)(r % g.n0), c = (int)(r / g.n0);
-    return (size_t)c * g.cStride + (size_t)(y >> g.l2n1) * g.blkStride + ((size_t)xl * g.n1 + (y & (g.n1 - 1))) * g.kzp;
+    return (size_t)c * g.cStride + (size_t)(y >> g.l2n1) * g.blkStride + (size_t)xl * g.xStride + (size_t)(y & (g.n1 - 1)) * g.kzp;
 }
 
 template <int NH>
