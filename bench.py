@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 K_BULK, G_SHEAR = [62.5, 222.222], [28.8462, 166.6667]   # test_LinearElastic.json / SURVEY 8d config 2
 G0 = [0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001]
 BYTES_PER_VOXEL_ITER_H3 = 554.0  # 23 F + 2 N with F = 24 B/voxel
+# algorithmic bytes per voxel and launch of the seven passes (h = 3, F = 24 B/voxel)
+ALG_BYTES_PER_VOXEL = {"fft_z_fwd": 48.0, "fft_y_fwd": 48.0, "fft_x_gamma": 72.0, "fft_y_inv": 48.0, "fft_z_inv": 72.0,
+                       "sweep_linear": 98.0, "cg_update": 168.0}
 
 
 def measured_peaks():
@@ -132,13 +135,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--ref-size", type=int, default=64)
-    ap.add_argument("--cpu-size", type=int, default=64)
+    ap.add_argument("--ref-size", type=int, default=96)
+    ap.add_argument("--cpu-size", type=int, default=96)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--grid", default="", help="nx,ny,nz: override the weak-scaling grid (experiments only)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (experiments only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dims = grid_for(args.size, max(world, args.gpus) if args.impl == "reference" else world)
+    if args.grid:
+        dims = [int(x) for x in args.grid.split(",")]
     if args.impl == "reference":
         if rank == 0:
             run_reference(args, dims)
@@ -193,8 +200,7 @@ def main():
     ctx.set_profiling(False)
     nloc = float(n0) * dims[1] * dims[2]
     F = 8.0 * 3 * nloc
-    alg = {"fft_z_fwd": 2 * F, "fft_y_fwd": 2 * F, "fft_x_gamma": 3 * F, "fft_y_inv": 2 * F, "fft_z_inv": 3 * F,
-           "sweep_linear": 4 * F + 2.0 * nloc, "cg_update": 7 * F}
+    alg = {k: v * nloc for k, v in ALG_BYTES_PER_VOXEL.items()}
     iter_classes = {k: v for k, v in prof.items() if k in alg}
     dom = max(iter_classes, key=lambda k: iter_classes[k][0] / iter_classes[k][1])
     dom_ms = iter_classes[dom][0] / iter_classes[dom][1]
@@ -205,6 +211,16 @@ def main():
 
     # e2e: the reference-facing call sequence with HOST buffers (pinned): microstructure + start field in, K iterations,
     # homogenized stress + displacement field out; all copies inside the timed region, wall clock, max over ranks
+    e2e_obj = None
+    if args.no_e2e:
+        sig = ctx.homogenized_stress()
+    else:
+        e2e_obj, sig = e2e_leg(torch, ctx, ms, n0, dims, K, dof, world, barrier, max_over_ranks)
+    finish(args, rank, world, ctx, comm, torch, dims, n0, nloc, K, W, value, t_loop, iter_gbs, peak, which, dom, achieved, dom_ms, prof, cs,
+           e2e_obj, l1 - l0, sig)
+
+
+def e2e_leg(torch, ctx, ms, n0, dims, K, dof, world, barrier, max_over_ranks):
     u_host = torch.zeros((n0, dims[1], dims[2], 3), dtype=torch.float64, pin_memory=True).numpy()
     ctx.upload("u", u_host)
     ctx.solve("cg", 1, 0.0, "Linfinity", "absolute")   # untimed: first-touch of the staging buffer
@@ -220,7 +236,23 @@ def main():
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e = dof * r2["iters"] / t_e2e
+    return {"value": e2e, "unit": "voxel-DOF/s", "h2d_bytes_per_step": world * (ms.nbytes + u_host.nbytes) / K,
+            "d2h_bytes_per_step": world * (u_host.nbytes + sig.nbytes) / K,
+            "what": "set_microstructure + upload u + K CG iterations + homogenized stress + download u, pinned host buffers, wall clock"}, sig
 
+
+def dram_traffic(kernel, nloc):
+    """per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of bench.py's workload,
+    committed under profiles/ as bytes per voxel of the capture (512^3); scaled to this run's voxels per GPU"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_per_voxel.json")))
+        return t["kernels"][kernel] * nloc
+    except Exception:
+        return None
+
+
+def finish(args, rank, world, ctx, comm, torch, dims, n0, nloc, K, W, value, t_loop, iter_gbs, peak, which, dom, achieved, dom_ms, prof, cs,
+           e2e_obj, launches, sig):
     if rank == 0:
         line = {"metric": "voxel_dof_updates_per_s", "value": value, "unit": "voxel-DOF/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * t_loop / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -234,16 +266,15 @@ def main():
                 "hbm_roofline_iteration": {"bytes_per_voxel_iter": BYTES_PER_VOXEL_ITER_H3, "achieved_gbs_per_gpu": iter_gbs, "peak_gbs": peak,
                                             "frac": iter_gbs / peak, "peak_source": which},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": which, "ms_per_launch": dom_ms},
+                             "traffic": dram_traffic(dom, nloc), "peak_source": which, "ms_per_launch": dom_ms,
+                             "algorithmic_bytes": ALG_BYTES_PER_VOXEL[dom] * nloc},
                 "kernel_ms": {k: v[0] / v[1] for k, v in prof.items()},
                 "clocks": cs.summary(),
-                "e2e": {"value": e2e, "unit": "voxel-DOF/s", "h2d_bytes_per_step": world * (ms.nbytes + u_host.nbytes) / K,
-                        "d2h_bytes_per_step": world * (u_host.nbytes + sig.nbytes) / K,
-                        "what": "set_microstructure + upload u + K CG iterations + homogenized stress + download u, pinned host buffers, wall clock"},
-                "gpu_launches": l1 - l0,
+                "e2e": e2e_obj,
+                "gpu_launches": launches,
                 "homogenized_stress": [float(x) for x in sig]}
         if not args.no_cpu and world == 1:
-            rate, it, dt = cpu_port_rate(args.cpu_size, 8)
+            rate, it, dt = cpu_port_rate(args.cpu_size, 6)
             line["cpu_baseline"] = {"value": rate, "unit": "voxel-DOF/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "%d CG iterations on a %d^3 sample of the workload, NumPy/scipy.fft restatement (oracle/), %.1f s"
                                               % (it, args.cpu_size, dt)}

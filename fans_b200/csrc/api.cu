@@ -311,7 +311,7 @@ static int create_rest(fans_ctx *ctx)
     ctx->kzc = ctx->nz / 2 + 1;
     ctx->kzp = (ctx->kzc + 7) / 8 * 8;
     ctx->gT = fft_x_tile_width(ctx->nx, ctx->h);
-    ctx->yT = (ctx->ny >= 1024) ? 4 : 8;  // 512: T=8 -> 512 threads, 64 registers, 2 CTAs/SM (1.08 ms vs 1.39 ms with T=4)
+    ctx->yT = 8;  // 128-byte rows: 512^3: 1.04 ms vs 1.39 ms with T=4; n_y = 1024 over NVLink (2 GPUs): 2.35 / 2.51 ms vs 3.69 / 3.00 ms
     if (const char *e = getenv("FANS_YT")) ctx->yT = (atoi(e) == 4) ? 4 : 8;
     FANS_CHECK(fft_plan_init(ctx, ctx->planx, ctx->nx, ctx->nx));
     FANS_CHECK(fft_plan_init(ctx, ctx->plany, ctx->ny, ctx->ny));

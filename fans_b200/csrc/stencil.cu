@@ -48,6 +48,8 @@ struct StencilParams {
     double *part;
     unsigned int *ticket;
     double *red_out;       // <d_new, K d_new>
+    const double *Ktab;    // phase stiffness table [nq][(8H)^2] in global memory (interface path)
+    const double *Stab;    // 27-point block stencils [nq][27][H][H] in global memory (warps cut by an interface)
     // slab decomposition (world_size > 1): node planes -1 and n0 and element plane -1 come from the neighbour ranks
     const double *halo_lo, *halo_hi;   // [H][ny*nz], already the UPDATED direction (no s/beta combination)
     const uint16_t *ms_lo;             // [ny*nz] phases of element plane -1
@@ -78,6 +80,28 @@ __device__ __forceinline__ void stencil_row(const double (&v)[H][4], double (&ac
                 }
                 accA[i] = fma(S[i * H + j], v[j][dz], accA[i]);
                 accB[i] = fma(S[i * H + j], v[j][dz + 1], accB[i]);
+            }
+    }
+}
+// the same row for a warp whose lanes sit in DIFFERENT phases (the interface cuts through the warp): coefficients per lane from the
+// stencil table in global memory (L1-resident) instead of executing every phase's constant-operand copy one after the other
+template <int H, bool ISO, int DXI, int DY>
+__device__ __forceinline__ void stencil_row_table(const double *__restrict__ Sq, const double (&v)[H][4], double (&accA)[H], double (&accB)[H])
+{
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz) {
+        const double *S = Sq + (DXI * 9 + DY * 3 + dz) * H * H;
+#pragma unroll
+        for (int i = 0; i < H; ++i)
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                if (ISO && H == 3 && i != j) {
+                    const int dd[3] = {DXI, DY, dz};
+                    if (dd[i] == 1 || dd[j] == 1) continue;
+                }
+                const double c = __ldg(S + i * H + j);
+                accA[i] = fma(c, v[j][dz], accA[i]);
+                accB[i] = fma(c, v[j][dz + 1], accB[i]);
             }
     }
 }
@@ -136,6 +160,83 @@ __device__ __forceinline__ void node_general(const double *ring, const uint16_t 
     element_dispatch<H, NQ, 6>(ring, k, ry, rz, EL_PH(0, 1, 1), acc);
     element_dispatch<H, NQ, 7>(ring, k, ry, rz, EL_PH(1, 1, 1), acc);
 #undef EL_PH
+}
+
+// Interface nodes of plane k (queued by the consumers), exact element form (reference semantics: K_phase(element) (u_b - u_node0),
+// include/solver.h:250-261, solverCG.h:98-103).  One (node, element) item per lane: the eight lanes of a node read their element's
+// three rows of K from the phase table in global memory (no phase branches, no divergence) and are summed with shuffles, so a queue
+// of q nodes costs ceil(8 q / 256) short passes of all consumer warps instead of one long serial chain in a few lanes.
+// Not inlined on purpose: its registers must not compete with the accumulators of the homogeneous path.
+struct IfaceArgs {
+    const double *ring, *Ktab;
+    const uint16_t *mring, *qlist;
+    const int *qcnt;
+    double *out;
+    size_t nloc;
+    int ny, nz, y0, z0, k;
+};
+template <int H>
+__device__ __noinline__ double interface_phase(const IfaceArgs a, int tid)
+{
+    constexpr int ND = 8 * H;
+    int pre[GY + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int w = 0; w < GY; ++w) pre[w + 1] = pre[w] + a.qcnt[w];
+    const int nitems = 16 * pre[GY];  // pair x 2 nodes x 8 elements
+    double dot = 0.0;
+    for (int n0 = 0; n0 < nitems; n0 += G_CONS) {
+        const int n = n0 + tid;
+        const bool on = n < nitems;
+        double acc[H];
+#pragma unroll
+        for (int c = 0; c < H; ++c) acc[c] = 0.0;
+        int qry = 0, qrz = 0;
+        if (on) {
+            const int pair = n >> 4, A = n & 7;
+            int w = 0, base = 0;
+#pragma unroll
+            for (int q = 1; q < GY; ++q)
+                if (pair >= pre[q]) w = q, base = pre[q];
+            const int code = a.qlist[w * 32 + (pair - base)];
+            qry = code >> 7, qrz = (code & 127) + ((n >> 3) & 1);
+            const int ox = A & 1, oy = (A >> 1) & 1, oz = (A >> 2) & 1;
+            const int ph = a.mring[((a.k - ox + 8) & 7) * GETILE + (qry - oy) * (GZ + 1) + (qrz - 1 - oz)];
+            const double *Krow = a.Ktab + (size_t)ph * (ND * ND) + (size_t)(H * A) * ND;
+            const double *p0 = a.ring + (size_t)((a.k - ox + 4) & 3) * H * GTILE + (qry - oy) * GPZ + (qrz - oz);
+            const double *p1 = a.ring + (size_t)((a.k - ox + 5) & 3) * H * GTILE + (qry - oy) * GPZ + (qrz - oz);
+            double u0[H];
+#pragma unroll
+            for (int c = 0; c < H; ++c) u0[c] = p0[c * GTILE];
+#pragma unroll
+            for (int b = 1; b < 8; ++b) {
+                const double *pb = ((b & 1) ? p1 : p0) + ((b >> 1) & 1) * GPZ + ((b >> 2) & 1);
+                double w3[H];
+#pragma unroll
+                for (int c = 0; c < H; ++c) w3[c] = pb[c * GTILE] - u0[c];
+#pragma unroll
+                for (int i = 0; i < H; ++i)
+#pragma unroll
+                    for (int j = 0; j < H; ++j) acc[i] = fma(__ldg(Krow + i * ND + H * b + j), w3[j], acc[i]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+            acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+            acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+            acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+        }
+        if (on && (n & 7) == 0) {
+            const size_t g = ((size_t)a.k * a.ny + (a.y0 + qry - 1)) * a.nz + (a.z0 + qrz - 2);
+            const double *ctr = a.ring + (size_t)((a.k + 4) & 3) * H * GTILE + qry * GPZ + qrz;
+#pragma unroll
+            for (int c = 0; c < H; ++c) {
+                a.out[c * a.nloc + g] = acc[c];
+                dot += acc[c] * ctr[c * GTILE];
+            }
+        }
+    }
+    return dot;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
@@ -297,6 +398,16 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
                 hph[2] = homog ? ph : -1;
             }
             const double *pl = ring + (size_t)((P + 4) & 3) * H * GTILE;
+            // bit j: the homogeneous lanes of this warp do not all share one phase for output plane j (warp-uniform decision)
+            int mixed = 0;
+            if (NQ > 1) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const unsigned act = __ballot_sync(0xffffffffu, hph[j] >= 0);
+                    const int first = __shfl_sync(0xffffffffu, hph[j], act ? (__ffs(act) - 1) : 0);
+                    if (act && !__all_sync(0xffffffffu, hph[j] < 0 || hph[j] == first)) mixed |= 1 << j;
+                }
+            }
             if (hph[0] >= 0 || hph[1] >= 0 || hph[2] >= 0) {
                 double v[H][4];
 #define ST_ROW(DY)                                                                                              \
@@ -307,9 +418,18 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
             const double2 a = p2[0], b = p2[1], d = p2[2];                                                      \
             v[c][0] = a.y, v[c][1] = b.x, v[c][2] = b.y, v[c][3] = d.x;                                         \
         }                                                                                                       \
-        if (hph[0] >= 0) stencil_row_dispatch<H, NQ, ISO, 2, DY>(hph[0], v, acc[0][0], acc[0][1]);               \
-        if (hph[1] >= 0) stencil_row_dispatch<H, NQ, ISO, 1, DY>(hph[1], v, acc[1][0], acc[1][1]);               \
-        if (hph[2] >= 0) stencil_row_dispatch<H, NQ, ISO, 0, DY>(hph[2], v, acc[2][0], acc[2][1]);               \
+        if (hph[0] >= 0) {                                                                                      \
+            if (mixed & 1) stencil_row_table<H, ISO, 2, DY>(p.Stab + hph[0] * (27 * H * H), v, acc[0][0], acc[0][1]); \
+            else stencil_row_dispatch<H, NQ, ISO, 2, DY>(hph[0], v, acc[0][0], acc[0][1]);                       \
+        }                                                                                                       \
+        if (hph[1] >= 0) {                                                                                      \
+            if (mixed & 2) stencil_row_table<H, ISO, 1, DY>(p.Stab + hph[1] * (27 * H * H), v, acc[1][0], acc[1][1]); \
+            else stencil_row_dispatch<H, NQ, ISO, 1, DY>(hph[1], v, acc[1][0], acc[1][1]);                       \
+        }                                                                                                       \
+        if (hph[2] >= 0) {                                                                                      \
+            if (mixed & 4) stencil_row_table<H, ISO, 0, DY>(p.Stab + hph[2] * (27 * H * H), v, acc[2][0], acc[2][1]); \
+            else stencil_row_dispatch<H, NQ, ISO, 0, DY>(hph[2], v, acc[2][0], acc[2][1]);                       \
+        }                                                                                                       \
     }
                 ST_ROW(0)
                 ST_ROW(1)
@@ -343,30 +463,16 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
             }
             hph[0] = hph[1], hph[1] = hph[2];
             bar_sync(BAR_CONS, G_CONS);
-            // ---- phase 2: the queued interface nodes of plane k, densely packed onto lanes (exact element form, planes k-1..k+1)
-            int pre[GY + 1];
-            pre[0] = 0;
+            // ---- phase 2: the queued interface nodes of plane k (exact element form over planes k-1..k+1)
+            {
+                int any = 0;
 #pragma unroll
-            for (int w = 0; w < GY; ++w) pre[w + 1] = pre[w] + qcnt[par][w];
-            const int nitems = 2 * pre[GY];
-            for (int n = tid; n < nitems; n += G_CONS) {
-                const int pair = n >> 1;
-                int w = 0, base = 0;
-#pragma unroll
-                for (int q = 1; q < GY; ++q)
-                    if (pair >= pre[q]) w = q, base = pre[q];
-                const int code = qlist[par][w * 32 + (pair - base)];
-                const int qry = code >> 7, qrz = (code & 127) + (n & 1);
-                double a1[H];
-#pragma unroll
-                for (int c = 0; c < H; ++c) a1[c] = 0.0;
-                node_general<H, NQ>(ring, mring, k, qry, qrz, a1);
-                const size_t g = ((size_t)k * p.ny + (y0 + qry - 1)) * p.nz + (z0 + qrz - 2);
-                const double *ctr = ring + (size_t)((k + 4) & 3) * H * GTILE + qry * GPZ + qrz;
-#pragma unroll
-                for (int c = 0; c < H; ++c) {
-                    p.out[c * p.nloc + g] = a1[c];
-                    racc[0] += a1[c] * ctr[c * GTILE];
+                for (int w = 0; w < GY; ++w) any |= qcnt[par][w];
+                if (any) {
+                    IfaceArgs ia;
+                    ia.ring = ring, ia.Ktab = p.Ktab, ia.mring = mring, ia.qlist = qlist[par], ia.qcnt = qcnt[par], ia.out = p.out;
+                    ia.nloc = p.nloc, ia.ny = p.ny, ia.nz = p.nz, ia.y0 = y0, ia.z0 = z0, ia.k = k;
+                    racc[0] += interface_phase<H>(ia, tid);
                 }
             }
             // plane P-2 is not needed any more: its slot may take plane P+2
@@ -379,6 +485,7 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
 // ------------------------------------------------------------------------------------------------
 static uint64_t g_stencil_stamp = 0;
 static bool g_stencil_iso = false;
+static double *g_stencil_Stab = nullptr;  // device copy of the stencil table (same content as c_S)
 
 // 27-point block stencil of a homogeneous neighbourhood from the element matrix K (8h x 8h, node-major):
 //   S[delta][i][j] = sum over local nodes a with b = a + delta inside the element of K[h a + i][h b + j]
@@ -439,6 +546,8 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
         // synchronous copies: the host vector dies at scope exit
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
         CUDA_TRY(ctx, cudaMemcpyToSymbol(c_S, S.data(), sizeof(double) * S.size()));
+        if (!g_stencil_Stab) CUDA_TRY(ctx, cudaMalloc(&g_stencil_Stab, sizeof(double) * STENCIL_MAXQ * 27 * 9));
+        CUDA_TRY(ctx, cudaMemcpy(g_stencil_Stab, S.data(), sizeof(double) * S.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(ctx, cudaMemcpyToSymbol(c_KQ, ctx->K_host.data(), sizeof(double) * (size_t)ctx->n_k * nd * nd));
         g_stencil_stamp = ctx->const_stamp;
         const char *env = getenv("FANS_STENCIL_ISO");
@@ -449,6 +558,8 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     p.n0 = ctx->n0, p.ny = ctx->ny, p.nz = ctx->nz, p.nloc = ctx->nloc;
     p.d_old = d_old, p.s = s_in, p.d_new = d_new, p.beta = beta_dev, p.out = out;
     p.phidx = ctx->phidx;
+    p.Ktab = ctx->d_K;
+    p.Stab = g_stencil_Stab;
     p.nq = ctx->n_k;
     p.part = ctx->d_part, p.ticket = ctx->d_ticket, p.red_out = red_out;
     if (ctx->P > 1) {

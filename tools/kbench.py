@@ -15,10 +15,17 @@ ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--tag", default="")
 ap.add_argument("--fe", default="HEX8")
+ap.add_argument("--ms", default="ellipsoid", help="ellipsoid | homogeneous | layers")
 args = ap.parse_args()
 n = args.size
 dims = [n, n, n]
 ms = simple.ellipsoid_microstructure(dims)
+if args.ms == "homogeneous":
+    ms[...] = 0
+    ms[0, 0, 0] = 1
+elif args.ms == "layers":
+    ms[...] = 0
+    ms[n // 4: 3 * n // 4] = 1
 ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], [62.5, 222.222], [28.8462, 166.6667], args.fe, 0)
 ctx.set_gradient([0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001])
 ctx.solve("cg", 3, 0.0, "Linfinity", "absolute")
