@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfans_gpu.so")
+LIB_PATH = os.environ.get("FANS_GPU_LIB") or os.path.join(_HERE, "lib", "libfans_gpu.so")  # FANS_GPU_LIB: another build of the same library (kernel A/B runs)
 
 FANS_MAX_PARAMS = 84
 

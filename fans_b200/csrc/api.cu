@@ -327,6 +327,18 @@ static int create_rest(fans_ctx *ctx)
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     FANS_CHECK(comm_map_peers(ctx));
+    if (ctx->P > 1 && ctx->p2p && ctx->h > 1) {  // component pipeline of the slab convolution (solve.cu, conv_run_pipelined)
+        int lo = 0, hi = 0;
+        CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->st2, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < 8; ++i) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_gate, sizeof(int)));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_gate, 0, sizeof(int), ctx->st));
+        ctx->pipe = 1;
+        ctx->y_grid = 96;  // SMs given to an NVLink-bound y pass while a z pass runs beside it (4 GPUs, 512x1024x1024: 64 -> 21.16, 96 -> 20.54, 120 -> 20.98, no pipeline 21.83 ms/iteration)
+        if (const char *e = getenv("FANS_PIPE")) ctx->pipe = atoi(e) ? 1 : 0;
+        if (const char *e = getenv("FANS_Y_GRID")) ctx->y_grid = atoi(e);
+    }
 
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * (1 << 20)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_red, sizeof(double) * S_COUNT));
@@ -372,6 +384,10 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_loop0) cudaEventDestroy(ctx->ev_loop0);
     if (ctx->ev_loop1) cudaEventDestroy(ctx->ev_loop1);
+    for (int i = 0; i < 8; ++i)
+        if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
+    if (ctx->st2) cudaStreamDestroy(ctx->st2);
+    if (ctx->d_gate) cudaFree(ctx->d_gate);
     if (ctx->own_stream && ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }

@@ -52,6 +52,14 @@ struct fans_ctx {
     cudaStream_t st = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_loop0 = nullptr, ev_loop1 = nullptr;
+    // component pipeline of the convolution over slabs (solve.cu, conv_run): the NVLink-bound y passes of component c run on `st2`
+    // on a limited number of SMs while the HBM-bound z pass of the neighbouring component runs on `st`
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_pipe[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int *d_gate = nullptr;      // device word a y pass sets when its first CTA is resident (k_gate on `st` waits for it)
+    int gate_seq = 0;
+    int pipe = 0;               // 1: pipelined convolution (P > 1, fused transposes, h > 1)
+    int y_grid = 0;             // CTAs of the persistent y pass in the pipeline (0: one CTA per tile)
 
     double *field[FANS_N_FIELDS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_alt = nullptr;   // ping-pong partner of D (fused d = s + beta d must not update in place)
@@ -176,7 +184,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double *scratch)
 // (ticket counter) folds them in fixed block order and writes out[0..NV). "one grid-level reduce".
 template <int NV, int NSUM>
 __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *scratch, double *part, unsigned int *ticket,
-                                            double *out)
+                                            double *out, bool accumulate = false)
 {
     block_reduce<NV, NSUM>(v, scratch);
     __shared__ bool is_last;
@@ -206,7 +214,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *scratch, do
         block_reduce<NV, NSUM>(acc, scratch);
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) out[i] = acc[i];
+            for (int i = 0; i < NV; ++i) out[i] = (accumulate && i < NSUM) ? out[i] + acc[i] : acc[i];
             *ticket = 0u;
         }
     }

@@ -17,20 +17,19 @@ struct TileIdx {  // swizzled [row][t] tile: conflict-free butterflies for T = 4
     }
 };
 
+// one (component, x plane, kz tile) of the y pass; b = ((c - c0) * n0 + xl) * nTiles + tile
 template <int N, int T, bool INV>
-__global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T >= 512) ? (1024 / ((N / rp_elems(N)) * T)) : 1) k_fft_y(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles, PeerTable peers)
+__device__ __forceinline__ void y_tile(double2 *__restrict__ spec, const double2 *__restrict__ tw, const SpecGeom &g, int nTiles, const PeerTable &peers,
+                                       int b, int c0, double2 *sm)
 {
-    extern __shared__ double2 sm[];
-    constexpr int E = rp_elems(N), TPC = N / E, NST = rp_nstages(N);
+    constexpr int E = rp_elems(N), NST = rp_nstages(N);
     const int t = threadIdx.x % T, jt = threadIdx.x / T;
-    int b = blockIdx.x;
     const int tile = b % nTiles;
     b /= nTiles;
-    const int xl = b % g.n0, c = b / g.n0;
+    const int xl = b % g.n0, c = c0 + b / g.n0;
     double2 *base = spec + (size_t)c * g.cStride + (size_t)xl * g.xStride + (size_t)tile * T + t;
     const TileIdx<T> idx{t};
     double2 a[1][E];
-    (void)TPC;
     if (!INV) {
 #pragma unroll
         for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_y(g, rp_row<N, 0>(jt, e))];
@@ -64,20 +63,60 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T 
     }
 }
 
+#define Y_BOUNDS __launch_bounds__((N / rp_elems(N)) * T, ((N / rp_elems(N)) * T >= 512) ? (1024 / ((N / rp_elems(N)) * T)) : 1)
+
+// whole spectrum, one tile per CTA
+template <int N, int T, bool INV>
+__global__ void Y_BOUNDS k_fft_y(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles, PeerTable peers)
+{
+    extern __shared__ double2 sm[];
+    y_tile<N, T, INV>(spec, tw, g, nTiles, peers, blockIdx.x, 0, sm);
+}
+
+// Component range and persistent grid (slab pipeline, solve.cu): `c0` first component, `nWork` tiles of this launch; a grid smaller
+// than nWork loops.  `gate` (optional): word set to `gate_val` by the first CTA as soon as it is resident, so a k_gate launch on
+// another stream can hold back a concurrent kernel until this one owns its SMs.
+template <int N, int T, bool INV>
+__global__ void Y_BOUNDS k_fft_y_part(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles, PeerTable peers, int c0,
+                                      int nWork, int *gate, int gate_val)
+{
+    extern __shared__ double2 sm[];
+    if (gate && blockIdx.x == 0 && threadIdx.x == 0) {
+        *reinterpret_cast<volatile int *>(gate) = gate_val;
+        __threadfence();
+    }
+    for (int w = blockIdx.x; w < nWork; w += gridDim.x) {
+        y_tile<N, T, INV>(spec, tw, g, nTiles, peers, w, c0, sm);
+        __syncthreads();  // the exchange tile is reused by the next tile
+    }
+}
+
 template <int N, int T>
-static int launch_y(fans_ctx *ctx, bool inverse, const SpecGeom &g, const PeerTable &peers)
+static int launch_y(fans_ctx *ctx, bool inverse, const SpecGeom &g, const PeerTable &peers, const YLaunch &yl)
 {
     constexpr int E = rp_elems(N);
     const int nTiles = (ctx->kzc + T - 1) / T;
     const size_t smem = sizeof(double2) * N * T;
-    const unsigned grid = (unsigned)((size_t)ctx->h * ctx->n0 * nTiles);
+    const int nWork = (int)((size_t)yl.nc * ctx->n0 * nTiles);
+    const unsigned grid = (unsigned)((yl.grid > 0 && yl.grid < nWork) ? yl.grid : nWork);
     const int nthr = (N / E) * T;
-    if (!inverse) {
-        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fft_y<N, T, false><<<grid, nthr, smem, ctx->st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers);
-    } else {
-        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y<N, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fft_y<N, T, true><<<grid, nthr, smem, ctx->st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers);
+    if (grid == (unsigned)nWork && yl.c0 == 0 && !yl.gate) {  // whole-spectrum launch: one tile per CTA
+        if (!inverse) {
+            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fft_y<N, T, false><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers);
+        } else {
+            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y<N, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fft_y<N, T, true><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers);
+        }
+    } else {  // component-range / persistent form (slab pipeline)
+        constexpr int NP = N;
+        if (!inverse) {
+            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y_part<NP, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fft_y_part<NP, T, false><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers, yl.c0, nWork, yl.gate, yl.gate_val);
+        } else {
+            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y_part<NP, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fft_y_part<NP, T, true><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers, yl.c0, nWork, yl.gate, yl.gate_val);
+        }
     }
     return FANS_OK;
 }
@@ -98,7 +137,10 @@ SpecGeom spec_geom_A(const fans_ctx *ctx)
 }
 
 // y pass (forward or inverse) on the local x-slab
-int fft_pass_y(fans_ctx *ctx, bool inverse)
+int fft_pass_y(fans_ctx *ctx, bool inverse) { return fft_pass_y_part(ctx, inverse, YLaunch{ctx->st, 0, ctx->h, 0, nullptr, 0}); }
+
+// the same for the components [c0, c0 + nc) on stream yl.st with at most yl.grid CTAs (0: one per tile)
+int fft_pass_y_part(fans_ctx *ctx, bool inverse, const YLaunch &yl)
 {
     prof_begin(ctx, inverse ? PC_FFT_Y_INV : PC_FFT_Y_FWD);
     const SpecGeom g = spec_geom_A(ctx);
@@ -110,7 +152,7 @@ int fft_pass_y(fans_ctx *ctx, bool inverse)
     peers.on = (ctx->P > 1 && ctx->p2p) ? 1 : 0;  // forward: push rows to their owners; inverse: pull them back
 #define Y_CASE(N_)                                                         \
     case N_:                                                               \
-        rc = (T == 8) ? launch_y<N_, 8>(ctx, inverse, g, peers) : launch_y<N_, 4>(ctx, inverse, g, peers); \
+        rc = (T == 8) ? launch_y<N_, 8>(ctx, inverse, g, peers, yl) : launch_y<N_, 4>(ctx, inverse, g, peers, yl); \
         break;
     switch (ctx->ny) {
         Y_CASE(4) Y_CASE(8) Y_CASE(16) Y_CASE(32) Y_CASE(64) Y_CASE(128) Y_CASE(256) Y_CASE(512) Y_CASE(1024)

@@ -8,6 +8,17 @@ int  fft_plan_init(fans_ctx *ctx, FftPlan &p, int N, int ntab);
 void fft_plan_free(FftPlan &p);
 int  fft_pass_z_fwd(fans_ctx *ctx, const double *in);
 int  fft_pass_y(fans_ctx *ctx, bool inverse);
+struct YLaunch {  // one launch of the y pass: stream, component range, CTA cap, optional start signal (see k_fft_y)
+    cudaStream_t st;
+    int c0, nc, grid;
+    int *gate;
+    int gate_val;
+};
+int  fft_pass_y_part(fans_ctx *ctx, bool inverse, const YLaunch &yl);
+int  fft_pass_z_fwd_part(fans_ctx *ctx, const double *in, int c0, int nc, cudaStream_t st);
+int  fft_pass_z_inv_part(fans_ctx *ctx, double *out, double scale, const double *dotw, double *red_out, int c0, int nc, bool accumulate,
+                         cudaStream_t st);
+int  conv_gate(fans_ctx *ctx, int gate_val, cudaStream_t st);
 int  fft_pass_x_gamma(fans_ctx *ctx);
 int  fft_pass_z_inv(fans_ctx *ctx, double *out, double scale, const double *dotw, double *red_out);
 int  fft_x_tile_width(int nx, int h);

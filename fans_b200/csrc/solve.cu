@@ -31,6 +31,60 @@ static int write_scalar(fans_ctx *ctx, int slot, double v)
     return FANS_OK;
 }
 
+// Holds back the stream until the device word `gate` reaches gate_val (set by the first resident CTA of a y pass on the other
+// stream), bounded by a ~10 ms timeout so a failed launch can never hang the device.
+__global__ void k_gate(const int *gate, int gate_val)
+{
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile int *>(gate) < gate_val && clock64() - t0 < 20000000LL) __nanosleep(200);
+}
+int conv_gate(fans_ctx *ctx, int gate_val, cudaStream_t st)
+{
+    k_gate<<<1, 1, 0, st>>>(ctx->d_gate, gate_val);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+// Slab convolution as a component pipeline (world_size > 1, fused transposes).  The y passes are NVLink-bound (7/8 of the spectrum
+// leaves the GPU at 8 ranks) and the z passes HBM-bound, and the `howmany` components are independent up to the Green operator:
+//     st :  zf(0)        | gate zf(1)          | gate zf(2)          |      barrier  x.Gamma  barrier |         zi(0)        | zi(1)        | zi(2)
+//     st2:        yf(0) ------------- yf(1) ------------- yf(2) ----/                                  yi(0) -- yi(1) ------- yi(2) ------/
+// A y pass runs persistent on y_grid SMs (its 1024-thread CTAs own the whole register file of an SM); k_gate releases the next z
+// pass only once that y pass is resident, so the block scheduler hands the z pass the REMAINING SMs instead of starving the y pass.
+static int conv_run_pipelined(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out)
+{
+    const int h = ctx->h;
+    cudaStream_t s1 = ctx->st, s2 = ctx->st2;
+    cudaEvent_t *ev = ctx->ev_pipe;
+    for (int c = 0; c < h; ++c) {
+        if (c > 0) FANS_CHECK(conv_gate(ctx, ctx->gate_seq, s1));  // y pass of component c-1 is resident
+        FANS_CHECK(fft_pass_z_fwd_part(ctx, in, c, 1, s1));
+        CUDA_TRY(ctx, cudaEventRecord(ev[c], s1));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(s2, ev[c], 0));
+        FANS_CHECK(fft_pass_y_part(ctx, false, YLaunch{s2, c, 1, c + 1 < h ? ctx->y_grid : 0, ctx->d_gate, ++ctx->gate_seq}));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ev[3], s2));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s1, ev[3], 0));
+    FANS_CHECK(comm_barrier(ctx));
+    FANS_CHECK(fft_pass_x_gamma(ctx));
+    FANS_CHECK(comm_barrier(ctx));
+    CUDA_TRY(ctx, cudaEventRecord(ev[4], s1));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s2, ev[4], 0));
+    for (int c = 0; c < h; ++c) {
+        FANS_CHECK(fft_pass_y_part(ctx, true, YLaunch{s2, c, 1, c > 0 ? ctx->y_grid : 0, ctx->d_gate, ++ctx->gate_seq}));
+        CUDA_TRY(ctx, cudaEventRecord(ev[5 + c], s2));
+    }
+    for (int c = 0; c < h; ++c) {
+        CUDA_TRY(ctx, cudaStreamWaitEvent(s1, ev[5 + c], 0));
+        if (c + 1 < h) FANS_CHECK(conv_gate(ctx, ctx->gate_seq - (h - 2 - c), s1));  // y pass of component c+1 is resident
+        FANS_CHECK(fft_pass_z_inv_part(ctx, out, scale, dotw, red_out, c, 1, c > 0, s1));
+    }
+    if (red_out) FANS_CHECK(comm_allreduce(ctx, red_out, red_out, 1, false));
+    else FANS_CHECK(comm_barrier(ctx));
+    return FANS_OK;
+}
+
 // out = scale * Gamma * in ;  optional red_out[0] = <dotw, out>
 int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out)
 {
@@ -38,6 +92,7 @@ int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const d
         fans_set_error(ctx, FANS_ERR_STATE, "fundamental solution not built: call fans_set_reference_stiffness first");
         return FANS_ERR_STATE;
     }
+    if (ctx->pipe && !ctx->prof) return conv_run_pipelined(ctx, in, out, scale, dotw, red_out);
     FANS_CHECK(fft_pass_z_fwd(ctx, in));
     FANS_CHECK(fft_pass_y(ctx, false));
     // x-slabs -> y-slabs (FFTW_MPI_TRANSPOSED_OUT) and back (FFTW_MPI_TRANSPOSED_IN).  Fused form: the y / x pass has already

@@ -30,6 +30,9 @@
 #ifndef STENCIL_MINB
 #define STENCIL_MINB 2
 #endif
+#ifndef STENCIL_MIXED_TABLE
+#define STENCIL_MIXED_TABLE 0   // 1: warps cut by an interface take per-lane coefficients from the table in global memory (measured slower)
+#endif
 
 __constant__ double c_S[STENCIL_MAXQ * 27 * 9];   // [q][delta][i][j]
 __constant__ double c_KQ[STENCIL_MAXQ * 576];      // [q][row][col]  (8h x 8h, h <= 3)
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
             const double *pl = ring + (size_t)((P + 4) & 3) * H * GTILE;
             // bit j: the homogeneous lanes of this warp do not all share one phase for output plane j (warp-uniform decision)
             int mixed = 0;
-            if (NQ > 1) {
+            if (STENCIL_MIXED_TABLE && NQ > 1) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const unsigned act = __ballot_sync(0xffffffffu, hph[j] >= 0);
@@ -419,15 +422,15 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
             v[c][0] = a.y, v[c][1] = b.x, v[c][2] = b.y, v[c][3] = d.x;                                         \
         }                                                                                                       \
         if (hph[0] >= 0) {                                                                                      \
-            if (mixed & 1) stencil_row_table<H, ISO, 2, DY>(p.Stab + hph[0] * (27 * H * H), v, acc[0][0], acc[0][1]); \
+            if (STENCIL_MIXED_TABLE && (mixed & 1)) stencil_row_table<H, ISO, 2, DY>(p.Stab + hph[0] * (27 * H * H), v, acc[0][0], acc[0][1]); \
             else stencil_row_dispatch<H, NQ, ISO, 2, DY>(hph[0], v, acc[0][0], acc[0][1]);                       \
         }                                                                                                       \
         if (hph[1] >= 0) {                                                                                      \
-            if (mixed & 2) stencil_row_table<H, ISO, 1, DY>(p.Stab + hph[1] * (27 * H * H), v, acc[1][0], acc[1][1]); \
+            if (STENCIL_MIXED_TABLE && (mixed & 2)) stencil_row_table<H, ISO, 1, DY>(p.Stab + hph[1] * (27 * H * H), v, acc[1][0], acc[1][1]); \
             else stencil_row_dispatch<H, NQ, ISO, 1, DY>(hph[1], v, acc[1][0], acc[1][1]);                       \
         }                                                                                                       \
         if (hph[2] >= 0) {                                                                                      \
-            if (mixed & 4) stencil_row_table<H, ISO, 0, DY>(p.Stab + hph[2] * (27 * H * H), v, acc[2][0], acc[2][1]); \
+            if (STENCIL_MIXED_TABLE && (mixed & 4)) stencil_row_table<H, ISO, 0, DY>(p.Stab + hph[2] * (27 * H * H), v, acc[2][0], acc[2][1]); \
             else stencil_row_dispatch<H, NQ, ISO, 0, DY>(hph[2], v, acc[2][0], acc[2][1]);                       \
         }                                                                                                       \
     }

@@ -42,7 +42,9 @@ def test_fundamental_solution(problem, materials, fe):
     ctx.close()
 
 
-@pytest.mark.parametrize("shape", [(16, 32, 64), (64, 16, 8), (8, 8, 128), (32, 32, 32)])
+# the long-axis shapes reach the largest transforms of every pass (the tile shapes / kernel variants the 512^3 and 1024^3 runs use)
+@pytest.mark.parametrize("shape", [(16, 32, 64), (64, 16, 8), (8, 8, 128), (32, 32, 32), (512, 8, 16), (1024, 8, 8), (8, 1024, 16),
+                                   (8, 512, 8), (8, 8, 1024), (4, 8, 512)])
 @pytest.mark.parametrize("problem,materials", [("thermal", THERMAL), ("mechanical", ELASTIC)])
 def test_convolution(problem, materials, shape):
     sol, ctx = make(problem, materials, "HEX8", shape)

@@ -25,17 +25,22 @@ def _ngpu():
         return 0
 
 
-# (ranks, fused transposes): 1 = the y passes push / pull their rows through peer-mapped memory over NVLink (the product path),
-# 0 = plain ncclSend/ncclRecv block all-to-all (FANS_P2P=0)
-@pytest.fixture(scope="module", params=[(2, 1), (2, 0), (4, 1), (8, 1)], ids=lambda p: "P%d-%s" % (p[0], "fused" if p[1] else "nccl"))
+# (ranks, fused transposes, variant): fused 1 = the y passes push / pull their rows through peer-mapped memory over NVLink (the product
+# path, with the component pipeline of solve.cu conv_run_pipelined), 0 = plain ncclSend/ncclRecv block all-to-all (FANS_P2P=0);
+# variant "persist": the pipelined y passes loop over their tiles on 5 CTAs, "seq": fused transposes without the pipeline (FANS_PIPE=0)
+VARIANT_ENV = {"": {}, "persist": {"FANS_Y_GRID": "5"}, "seq": {"FANS_PIPE": "0"}}
+
+
+@pytest.fixture(scope="module", params=[(2, 1, ""), (2, 1, "persist"), (2, 1, "seq"), (2, 0, ""), (4, 1, ""), (8, 1, "")],
+                ids=lambda p: "P%d-%s%s" % (p[0], "fused" if p[1] else "nccl", "-" + p[2] if p[2] else ""))
 def run(request, tmp_path_factory):
-    P, fused = request.param
+    P, fused, variant = request.param
     if _ngpu() < P:
         pytest.skip("needs %d GPUs" % P)
-    out = tmp_path_factory.mktemp("mgpu%d_%d" % (P, fused))
+    out = tmp_path_factory.mktemp("mgpu%d_%d%s" % (P, fused, variant))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(P), "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + 2 * P + fused), os.path.join(HERE, "mgpu_worker.py"), str(out)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, FANS_P2P=str(fused)))
+           "--master-port", str(29500 + 2 * P + fused + 20 * list(VARIANT_ENV).index(variant)), os.path.join(HERE, "mgpu_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, FANS_P2P=str(fused), **VARIANT_ENV[variant]))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return P, str(out)
 
