@@ -121,6 +121,38 @@ def test_residual_and_linear_operator(problem, materials, fe, shape):
     ctx.close()
 
 
+@pytest.mark.parametrize("problem,materials", [("thermal", THERMAL), ("mechanical", ELASTIC)])
+@pytest.mark.parametrize("ms_kind", ["layers", "layers+inclusion", "homogeneous+voxel"])
+def test_linear_operator_uniform_tiles(problem, materials, ms_kind):
+    """Microstructures with whole (8 x 64) tiles of one phase: the stencil's branch-free uniform-tile step, its hand-over to the
+    per-node classification at layer boundaries and around an inclusion, and the fused d = s + beta d / <d, K d> CG step on top."""
+    shape = (24, 16, 128)
+    ms = np.zeros(shape, dtype=np.uint16)
+    if ms_kind.startswith("layers"):
+        ms[6:15] = 1
+    if ms_kind == "layers+inclusion":
+        ms[9:12, 3:6, 70:90] = 0
+        ms[18:21, 8:16, 0:5] = 1
+    if ms_kind == "homogeneous+voxel":
+        ms[23, 15, 127] = 1
+    sol = fo.OracleSolver(ms, [1.0, 2.0, 1.5], problem, materials, "HEX8", "cg", "small", EP, 100)
+    ctx = util.ctx_from_oracle(sol)
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal(ctx.field_shape) * 1e-3
+    ctx.upload("u", u)
+    ctx.apply_linear("rnew", "u")
+    assert rel_err(ctx.download("rnew"), sol.apply_linear(u)) < FIELD_TOL
+    g0 = np.array(G0[sol.n_str])
+    sol.set_gradient(g0)
+    ctx.set_gradient(g0)
+    sol.solve()
+    res = ctx.solve("cg", 100, EP["tolerance"], EP["measure"], EP["type"])
+    assert abs(res["iters"] - sol.iter) <= 1
+    assert rel_err(ctx.homogenized_stress(), sol.get_homogenized_stress()) < SCALAR_TOL
+    assert rel_err(ctx.download("u"), sol.u) < FIELD_TOL
+    ctx.close()
+
+
 @pytest.mark.parametrize("problem,materials,fe,g0", [
     ("thermal", THERMAL, "HEX8R", [0.01, 0.02, -0.01]),
     ("thermal", THERMAL, "HEX8", [0.01, 0.02, -0.01]),
