@@ -126,7 +126,7 @@ def test_residual_and_linear_operator(problem, materials, fe, shape):
 def test_linear_operator_uniform_tiles(problem, materials, ms_kind):
     """Microstructures with whole (8 x 64) tiles of one phase: the stencil's branch-free uniform-tile step, its hand-over to the
     per-node classification at layer boundaries and around an inclusion, and the fused d = s + beta d / <d, K d> CG step on top."""
-    shape = (24, 16, 128)
+    shape = (32, 16, 128)
     ms = np.zeros(shape, dtype=np.uint16)
     if ms_kind.startswith("layers"):
         ms[6:15] = 1
@@ -134,7 +134,7 @@ def test_linear_operator_uniform_tiles(problem, materials, ms_kind):
         ms[9:12, 3:6, 70:90] = 0
         ms[18:21, 8:16, 0:5] = 1
     if ms_kind == "homogeneous+voxel":
-        ms[23, 15, 127] = 1
+        ms[31, 15, 127] = 1
     sol = fo.OracleSolver(ms, [1.0, 2.0, 1.5], problem, materials, "HEX8", "cg", "small", EP, 100)
     ctx = util.ctx_from_oracle(sol)
     rng = np.random.default_rng(11)
