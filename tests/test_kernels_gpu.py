@@ -145,6 +145,7 @@ def test_linear_operator_uniform_tiles(problem, materials, ms_kind):
     g0 = np.array(G0[sol.n_str])
     sol.set_gradient(g0)
     ctx.set_gradient(g0)
+    ctx.zero("u")  # both solves start from u = 0
     sol.solve()
     res = ctx.solve("cg", 100, EP["tolerance"], EP["measure"], EP["type"])
     assert abs(res["iters"] - sol.iter) <= 1
