@@ -201,7 +201,9 @@ def main():
     nloc = float(n0) * dims[1] * dims[2]
     F = 8.0 * 3 * nloc
     alg = {k: v * nloc for k, v in ALG_BYTES_PER_VOXEL.items()}
-    iter_classes = {k: v for k, v in prof.items() if k in alg}
+    # the y passes carry the x<->y transposes over NVLink when world > 1: they are NVLink-bound there (nvlink_roofline below), the
+    # HBM roofline object is then quoted for the dominant HBM-bound kernel
+    iter_classes = {k: v for k, v in prof.items() if k in alg and not (world > 1 and k.startswith("fft_y"))}
     dom = max(iter_classes, key=lambda k: iter_classes[k][0] / iter_classes[k][1])
     dom_ms = iter_classes[dom][0] / iter_classes[dom][1]
     peaks, which = measured_peaks()
@@ -273,6 +275,18 @@ def finish(args, rank, world, ctx, comm, torch, dims, n0, nloc, K, W, value, t_l
                 "e2e": e2e_obj,
                 "gpu_launches": launches,
                 "homogenized_stress": [float(x) for x in sig]}
+        if world > 1:
+            # bytes each GPU sends (forward push) / receives (inverse pull) per transpose: its spectrum minus the block it keeps
+            kzp = (dims[2] // 2 + 1 + 7) // 8 * 8
+            tb = 16.0 * 3 * n0 * dims[1] * kzp * (world - 1) / world
+            km = line["kernel_ms"]
+            t_y = (km["fft_y_fwd"] + km["fft_y_inv"]) * 1e-3
+            line["nvlink_roofline"] = {"bound": "nvlink", "kernels": "fft_y_fwd + fft_y_inv (transposes fused into the y passes, peer stores / loads)",
+                                       "bytes_per_gpu_per_transpose": tb, "achieved": 2.0 * tb / t_y / 1e9, "peak": 900.0, "unit": "GB/s per direction",
+                                       "frac": 2.0 * tb / t_y / 1e9 / 900.0, "peak_source": "NVLink 5 nominal, per direction per GPU",
+                                       "ms_both_transposes": 1e3 * t_y,
+                                       "note": "kernel times from the profiling run (passes one after the other); in the timed loop the z passes "
+                                               "of the neighbouring component overlap them (component pipeline)"}
         if not args.no_cpu and world == 1:
             rate, it, dt = cpu_port_rate(args.cpu_size, 6)
             line["cpu_baseline"] = {"value": rate, "unit": "voxel-DOF/s", "cores": os.cpu_count(), "kind": "port",

@@ -71,11 +71,21 @@ __device__ __forceinline__ void inv_sym3(const double C[6] /*00,11,22,01,02,12*/
     Ci[5] = (C[3] * C[4] - C[0] * C[5]) * id;
 }
 
+// History values of ONE Gauss point staged ahead of time in thread-private shared-memory slots (sweep.cu issues the cp.async of
+// Gauss point g+1 while g is evaluated): slot v < 13 = committed value of variable v (hist_t), slot 13 + (v - 6) = CURRENT value of
+// variable v in 6..12 (hist; J2Plasticity accumulates psi / psi_bar on every call).  s == nullptr: read global memory directly.
+#define FANS_HIST_STAGE_SLOTS 20
+struct HistStage {
+    const double *s;
+    int stride;
+    __device__ __forceinline__ double operator()(int slot) const { return s[slot * stride]; }
+};
+
 // One Gauss point.  e: strain-like input, s: stress-like output.
 template <int NSTR>
 __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&e)[NSTR], double (&s)[NSTR], double *hist,
                                              const double *hist_t, int *pflag, size_t nloc, int ngp, int gp, size_t el,
-                                             bool write_state, int *fault)
+                                             bool write_state, int *fault, const HistStage hs = HistStage{nullptr, 0})
 {
     const double *P = pd.params;
     if (pd.model == FANS_MAT_LINEAR) {
@@ -132,10 +142,10 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             double ept[6], pbt[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                ept[i] = hist_t[((size_t)i * ngp + gp) * nloc + el];
-                pbt[i] = hist_t[((size_t)(7 + i) * ngp + gp) * nloc + el];
+                ept[i] = hs.s ? hs(i) : hist_t[((size_t)i * ngp + gp) * nloc + el];
+                pbt[i] = hs.s ? hs(7 + i) : hist_t[((size_t)(7 + i) * ngp + gp) * nloc + el];
             }
-            const double psit = hist_t[((size_t)6 * ngp + gp) * nloc + el];
+            const double psit = hs.s ? hs(6) : hist_t[((size_t)6 * ngp + gp) * nloc + el];
             double ee[6], st[6], dev[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) ee[i] = e[i % NSTR] - ept[i];
@@ -186,9 +196,11 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
                 for (int i = 0; i < 6; ++i) {
                     hist[((size_t)i * ngp + gp) * nloc + el] = ept[i] + gam * nvec[i];
                     // quirk (J2Plasticity.h:103-104): psi / psi_bar ACCUMULATE on every call
-                    hist[((size_t)(7 + i) * ngp + gp) * nloc + el] -= gam * nvec[i];
+                    const size_t ib = ((size_t)(7 + i) * ngp + gp) * nloc + el;
+                    hist[ib] = (hs.s ? hs(14 + i) : hist[ib]) - gam * nvec[i];
                 }
-                hist[((size_t)6 * ngp + gp) * nloc + el] += gam * SQRT_TWO_THIRDS;
+                const size_t ip = ((size_t)6 * ngp + gp) * nloc + el;
+                hist[ip] = (hs.s ? hs(13) : hist[ip]) + gam * SQRT_TWO_THIRDS;
             }
             return;
         }
@@ -197,8 +209,8 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             const double K = P[0], G = P[1], sy0 = P[2], Kiso = P[3];
             double ep[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) ep[i] = hist_t[((size_t)i * ngp + gp) * nloc + el];
-            const double q_in = hist_t[((size_t)6 * ngp + gp) * nloc + el];
+            for (int i = 0; i < 6; ++i) ep[i] = hs.s ? hs(i) : hist_t[((size_t)i * ngp + gp) * nloc + el];
+            const double q_in = hs.s ? hs(6) : hist_t[((size_t)6 * ngp + gp) * nloc + el];
             const double lam = K - 2.0 / 3.0 * G;
             const double tr = e[0] + e[1] + e[2];
             double sg[6], sd[6];

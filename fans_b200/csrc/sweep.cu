@@ -43,6 +43,7 @@ struct SweepParams {
     int ngp, bbar;
     double *hist, *hist_t;
     int *pflag;
+    int hstage;              // 1: history of Gauss point g+1 is staged in shared memory (cp.async) while g is evaluated
     int *fault;
     // reductions
     double *part;
@@ -54,6 +55,14 @@ struct SweepParams {
     const double *in_hi;         // node plane n0 of the input (= plane 0 of the next rank), [H][ny*nz], final values
     double *out_hi;              // contributions of this rank's last element plane to node plane n0 (sent to the next rank)
 };
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 __device__ __forceinline__ int wrapi(int v, int n)
 {
@@ -68,6 +77,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
     constexpr int ND = 8 * H;
     double *ring = smem;                   // [2][H][NTILE]
     double *stg = smem + 2 * H * NTILE;    // [ND][NELT]
+    double *hstg = stg + ND * NELT;        // [2][FANS_HIST_STAGE_SLOTS][SWEEP_THREADS] thread-private history staging (only if p.hstage)
     __shared__ double scratch[32 * (MODE == SW_STRAINSTRESS ? NSTR : 1)];
 
     const int tid = threadIdx.x;
@@ -226,8 +236,36 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                     mc = t * (1.0 / 3.0);
                 }
                 const bool wr = own_valid && x >= xs;  // only the owner of an element updates its history / flags
+                // History staging: a thread evaluates its 8 Gauss points one after the other and would pay one DRAM round trip per
+                // point (a single 320-thread CTA per SM cannot hide it); instead the values of point g+1 travel global -> shared
+                // with cp.async while point g is evaluated.  nT committed values (hist_t), current values of variables 6..12 for J2.
+                const bool st_j2 = (pd.model == FANS_MAT_J2_LINEAR_ISO || pd.model == FANS_MAT_J2_NONLIN_ISO);
+                const int nT = (p.hstage && MODE != SW_LINEAR && NSTR == 6) ? (st_j2 ? 13 : (pd.model == FANS_MAT_J2NEW_LINEAR_ISO ? 7 : 0)) : 0;
+                double *hmine = hstg + tid;
+                auto hist_issue = [&](int g, int buf) {
+                    double *dst = hmine + (size_t)buf * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
+#pragma unroll
+                    for (int v = 0; v < 13; ++v)
+                        if (v < nT) cp_async8(dst + v * SWEEP_THREADS, p.hist_t + ((size_t)v * p.ngp + g) * p.nloc + e);
+                    if (st_j2) {
+#pragma unroll
+                        for (int v = 6; v < 13; ++v) cp_async8(dst + (13 + v - 6) * SWEEP_THREADS, p.hist + ((size_t)v * p.ngp + g) * p.nloc + e);
+                    }
+                    cp_async_commit();
+                };
+                if (nT) hist_issue(0, 0);
 #pragma unroll 1
                 for (int g = 0; g < p.ngp; ++g) {
+                    HistStage hs{nullptr, SWEEP_THREADS};
+                    if (nT) {
+                        if (g + 1 < p.ngp) {
+                            hist_issue(g + 1, (g + 1) & 1);
+                            cp_async_wait_1();
+                        } else {
+                            cp_async_wait_0();
+                        }
+                        hs.s = hmine + (size_t)(g & 1) * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
+                    }
                     const double *bg = c_bg + g * 24;
                     double Hm[H][3];
 #pragma unroll
@@ -249,7 +287,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                     }
 #pragma unroll
                     for (int i = 0; i < NSTR; ++i) eps[i] += p.g0[i];
-                    material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.ngp, g, e, wr, p.fault);
+                    material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.ngp, g, e, wr, p.fault, hs);
                     if (MODE == SW_STRAINSTRESS) {
 #pragma unroll
                         for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
@@ -438,7 +476,8 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < 4L * FANS_SMS) xchunk = (xchunk + 1) / 2;
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
-    const size_t smem = sizeof(double) * (2 * ctx->h * NTILE + 8 * ctx->h * NELT);
+    p.hstage = (ctx->any_history && mode != SW_LINEAR && !(getenv("FANS_HIST_STAGE") && atoi(getenv("FANS_HIST_STAGE")) == 0)) ? 1 : 0;
+    const size_t smem = sizeof(double) * (2 * ctx->h * NTILE + 8 * ctx->h * NELT + (p.hstage ? 2 * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS : 0));
     int rc = FANS_ERR_ARG;
 #define SW_DISPATCH(H_, N_)                                                                       \
     do {                                                                                          \

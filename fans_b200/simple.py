@@ -73,3 +73,51 @@ def linear_thermal_context(ms, Lbox, conductivity, fe_type="HEX8", device=-1):
     ctx.set_microstructure(ms)
     ctx.set_reference_stiffness(np.eye(3) * k.mean())
     return ctx
+
+
+def fiber_microstructure(n, n_fibers=64, vf=0.4, seed=1234):
+    """Synthetic config-3 image: unidirectional fibres along z — n_fibers non-overlapping periodic discs in the x-y
+    plane, radius n*sqrt(vf/(n_fibers*pi)), centres by random sequential addition; phase 1 = fibre, phase 0 = matrix."""
+    rng = np.random.default_rng(seed)
+    r = n * np.sqrt(vf / (n_fibers * np.pi))
+    centres = []
+    while len(centres) < n_fibers:
+        c = rng.uniform(0.0, n, size=2)
+        ok = True
+        for q in centres:
+            d = np.abs(c - q)
+            d = np.minimum(d, n - d)
+            if d[0] ** 2 + d[1] ** 2 < (2.0 * r) ** 2:
+                ok = False
+                break
+        if ok:
+            centres.append(c)
+    x = np.arange(n) + 0.5
+    plane = np.zeros((n, n), dtype=np.uint16)
+    for q in centres:
+        dx = np.abs(x - q[0])
+        dx = np.minimum(dx, n - dx)
+        dy = np.abs(x - q[1])
+        dy = np.minimum(dy, n - dy)
+        plane |= ((dx[:, None] ** 2 + dy[None, :] ** 2) <= r * r).astype(np.uint16)
+    return np.ascontiguousarray(np.broadcast_to(plane[:, :, None], (n, n, n)))
+
+
+def j2_fiber_context(ms, Lbox, fe_type="HEX8", device=-1, gdims=None, comm=None):
+    """Config 3: phase 0 = J2ViscoPlastic_NonLinearIsotropicHardening with the parameters of test/input_files/test_J2Plasticity.json,
+    phase 1 = LinearElasticIsotropic fibres (K = 222.222, G = 166.6667).  Reference stiffness = mean over the two material groups of
+    their elastic tangents (MaterialManager.h:177-205)."""
+    K0, G0, K1, G1 = 62.5, 28.8462, 222.222, 166.6667
+    ctx = L.Context(gdims if gdims is not None else ms.shape, Lbox, 3, 6, fe_type, device, comm)
+    d0 = L.PhaseDesc()
+    d0.model, d0.local_mat, d0.group_n_mat = L.MAT_J2_NONLIN, 0, 1
+    for k, v in enumerate([K0, G0, 0.1, 0.0, 0.0, 1.0, 0.01, 0.15, 1000.0]):   # K, G, sigma_y, K_iso, H, eta, dt, sigma_inf, delta
+        d0.params[k] = v
+    d1 = L.PhaseDesc()
+    d1.model, d1.local_mat, d1.group_n_mat = L.MAT_LINEAR, 0, 1
+    for k, v in enumerate(elastic_tangent(K1 - 2.0 / 3.0 * G1, G1).reshape(-1)):
+        d1.params[k] = v
+    ctx.set_materials([d0, d1])
+    ctx.set_microstructure(ms)
+    ctx.set_reference_stiffness(0.5 * (elastic_tangent(K0 - 2.0 / 3.0 * G0, G0) + elastic_tangent(K1 - 2.0 / 3.0 * G1, G1)))
+    return ctx
