@@ -380,6 +380,8 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     fft_plan_free(ctx->planz);
     prof_resolve(ctx);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+    for (auto &pr : ctx->conv_pending) cudaEventDestroy(pr.first), cudaEventDestroy(pr.second);
+    for (cudaEvent_t e : ctx->conv_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_loop0) cudaEventDestroy(ctx->ev_loop0);

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/fans_gpu.h"
 
@@ -127,6 +128,10 @@ struct fans_ctx {
     std::vector<ProfRec> prof_pending;
     double prof_ms[FANS_PROF_CLASSES] = {0};
     int64_t prof_n[FANS_PROF_CLASSES] = {0};
+
+    // device time inside convolution() (the reference's "FFT Time per iteration", solver.h:293): one event pair per call, resolved by fans_solve
+    std::vector<cudaEvent_t> conv_pool;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_pending;
 
     std::string err;
     int64_t launches = 0;

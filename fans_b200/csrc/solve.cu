@@ -31,6 +31,21 @@ static int write_scalar(fans_ctx *ctx, int slot, double v)
     return FANS_OK;
 }
 
+// sums (and recycles) the event pairs conv_run left since the last call; the stream must have been synchronised past them
+static double conv_time_resolve(fans_ctx *ctx)
+{
+    double total = 0.0;
+    for (auto &pr : ctx->conv_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) total += ms;
+        else cudaGetLastError();
+        ctx->conv_pool.push_back(pr.first);
+        ctx->conv_pool.push_back(pr.second);
+    }
+    ctx->conv_pending.clear();
+    return total;
+}
+
 // Holds back the stream until the device word `gate` reaches gate_val (set by the first resident CTA of a y pass on the other
 // stream), bounded by a ~10 ms timeout so a failed launch can never hang the device.
 __global__ void k_gate(const int *gate, int gate_val)
@@ -92,6 +107,29 @@ int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const d
         fans_set_error(ctx, FANS_ERR_STATE, "fundamental solution not built: call fans_set_reference_stiffness first");
         return FANS_ERR_STATE;
     }
+    // event pair around the whole convolution (on ctx->st: the pipelined form joins its second stream before it returns)
+    auto conv_event = [&]() {
+        cudaEvent_t e = nullptr;
+        if (!ctx->conv_pool.empty()) {
+            e = ctx->conv_pool.back();
+            ctx->conv_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        cudaEventRecord(e, ctx->st);
+        return e;
+    };
+    if (ctx->conv_pending.size() > 1024) {  // many convolutions outside a solve: do not let the event pairs pile up
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+        conv_time_resolve(ctx);
+    }
+    const cudaEvent_t ev_a = conv_event();
+    struct ConvTimer {
+        fans_ctx *c;
+        cudaEvent_t a;
+        decltype(conv_event) &mk;
+        ~ConvTimer() { c->conv_pending.emplace_back(a, mk()); }
+    } conv_timer{ctx, ev_a, conv_event};
     if (ctx->pipe && !ctx->prof) return conv_run_pipelined(ctx, in, out, scale, dotw, red_out);
     FANS_CHECK(fft_pass_z_fwd(ctx, in));
     FANS_CHECK(fft_pass_y(ctx, false));
@@ -347,6 +385,8 @@ extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_
         for (int i = 0; i <= p->n_it; ++i) err_hist[i] = 0.0;
     ErrState es{p->measure, p->err_type, 0.0, err_hist, 0};
     const int evals0 = ctx->n_residual_evals;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    conv_time_resolve(ctx);  // drop the pairs of convolutions issued outside a solve (fans_convolution)
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->st));
     int rc;
     if (p->method == FANS_METHOD_CG) rc = solve_cg(ctx, p, res, es);
@@ -365,8 +405,7 @@ extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_loop0, ctx->ev_loop1));
     res->loop_ms = ms;
     prof_resolve(ctx);
-    res->fft_ms = ctx->prof_ms[PC_FFT_Z_FWD] + ctx->prof_ms[PC_FFT_Y_FWD] + ctx->prof_ms[PC_FFT_X_GAMMA] + ctx->prof_ms[PC_FFT_Y_INV] +
-                  ctx->prof_ms[PC_FFT_Z_INV];
+    res->fft_ms = conv_time_resolve(ctx);
     res->iters = es.iter;
     res->n_residual_evals = ctx->n_residual_evals - evals0;
     return FANS_OK;

@@ -112,7 +112,7 @@ typedef struct {
     int32_t n_residual_evals; /* number of compute_residual / K.d sweeps */
     double  err_last;         /* last value returned by compute_error */
     double  elapsed_ms;       /* device time of internalSolve (CUDA events) */
-    double  fft_ms;           /* device time inside convolution() (solver.h:293 "Total FFT Time"); needs fans_set_profiling */
+    double  fft_ms;           /* device time inside convolution() (solver.h:293 "Total FFT Time"), CUDA events around every call */
     double  loop_ms;          /* device time of the iteration loop alone (after the initial residual), CUDA events */
 } fans_solve_result;
 

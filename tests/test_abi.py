@@ -86,3 +86,33 @@ def test_product_never_imports_oracle():
                 if re.search(r"fans_oracle|oracle/|import oracle", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_fibre_image_generator():
+    """fans_b200.simple.fiber_microstructure (BASELINE config 3 image): deterministic, z-invariant, 64 periodic non-overlapping discs
+    at the requested volume fraction."""
+    import numpy as np
+    from fans_b200 import simple
+    ms = simple.fiber_microstructure(64)
+    assert ms.dtype == np.uint16 and ms.shape == (64, 64, 64) and set(np.unique(ms)) == {0, 1}
+    assert (ms == ms[:, :, :1]).all()                       # fibres run along z, the reference's fastest axis
+    assert abs(float(ms.mean()) - 0.4) < 0.03               # discs are rasterised on 64^2 pixels
+    assert (simple.fiber_microstructure(64) == ms).all()    # seeded
+    # separate discs: many periodic connected components of the fibre phase, never more than the number of fibres
+    plane = ms[:, :, 0].astype(bool)
+    lab = -np.ones(plane.shape, dtype=int)
+    n = 0
+    for i, j in zip(*np.nonzero(plane)):
+        if lab[i, j] >= 0:
+            continue
+        stack = [(i, j)]
+        lab[i, j] = n
+        while stack:
+            a, b = stack.pop()
+            for da, db in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+                c, d = (a + da) % 64, (b + db) % 64
+                if plane[c, d] and lab[c, d] < 0:
+                    lab[c, d] = n
+                    stack.append((c, d))
+        n += 1
+    assert 20 <= n <= 64    # discs at distance ~2r touch on the raster and merge; a broken generator gives 1 blob or > 64 specks
