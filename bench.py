@@ -224,6 +224,7 @@ def main():
 
 def e2e_leg(torch, ctx, ms, n0, dims, K, dof, world, barrier, max_over_ranks):
     u_host = torch.zeros((n0, dims[1], dims[2], 3), dtype=torch.float64, pin_memory=True).numpy()
+    ms = torch.from_numpy(ms.view("int16")).pin_memory().numpy().view("uint16")   # every host buffer of the timed region is pinned
     ctx.upload("u", u_host)
     ctx.solve("cg", 1, 0.0, "Linfinity", "absolute")   # untimed: first-touch of the staging buffer
     u_host[...] = 0.0

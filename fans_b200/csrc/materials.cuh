@@ -193,15 +193,15 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
 #pragma unroll
             for (int i = 0; i < 6; ++i) s[i % NSTR] = st[i] - gam * 2 * G * nvec[i];
             if (write_state) {
+                double *hb = hist + (size_t)gp * nloc + el;   // variable v of this Gauss point: hb[v * vs]
+                const size_t vs = (size_t)ngp * nloc;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    hist[((size_t)i * ngp + gp) * nloc + el] = ept[i] + gam * nvec[i];
+                    hb[i * vs] = ept[i] + gam * nvec[i];
                     // quirk (J2Plasticity.h:103-104): psi / psi_bar ACCUMULATE on every call
-                    const size_t ib = ((size_t)(7 + i) * ngp + gp) * nloc + el;
-                    hist[ib] = (hs.s ? hs(14 + i) : hist[ib]) - gam * nvec[i];
+                    hb[(7 + i) * vs] = (hs.s ? hs(14 + i) : hb[(7 + i) * vs]) - gam * nvec[i];
                 }
-                const size_t ip = ((size_t)6 * ngp + gp) * nloc + el;
-                hist[ip] = (hs.s ? hs(13) : hist[ip]) + gam * SQRT_TWO_THIRDS;
+                hb[6 * vs] = (hs.s ? hs(13) : hb[6 * vs]) + gam * SQRT_TWO_THIRDS;
             }
             return;
         }

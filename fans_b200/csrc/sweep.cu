@@ -244,12 +244,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                 double *hmine = hstg + tid;
                 auto hist_issue = [&](int g, int buf) {
                     double *dst = hmine + (size_t)buf * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
+                    const size_t vs = (size_t)p.ngp * p.nloc, go = (size_t)g * p.nloc + e;   // variable v of Gauss point g: [v * vs + go]
+                    const double *bt = p.hist_t + go, *bc = p.hist + go;
 #pragma unroll
                     for (int v = 0; v < 13; ++v)
-                        if (v < nT) cp_async8(dst + v * SWEEP_THREADS, p.hist_t + ((size_t)v * p.ngp + g) * p.nloc + e);
+                        if (v < nT) cp_async8(dst + v * SWEEP_THREADS, bt + v * vs);
                     if (st_j2) {
 #pragma unroll
-                        for (int v = 6; v < 13; ++v) cp_async8(dst + (13 + v - 6) * SWEEP_THREADS, p.hist + ((size_t)v * p.ngp + g) * p.nloc + e);
+                        for (int v = 6; v < 13; ++v) cp_async8(dst + (13 + v - 6) * SWEEP_THREADS, bc + v * vs);
                     }
                     cp_async_commit();
                 };
