@@ -5,6 +5,7 @@
 //     results_dir/<dataset>_results/<prefix>/load<L>/time_step<T>/<name>.bin   + results_dir/index.jsonl (name, dtype, dims; "xyz" order)
 // following the reference's HDF5 group layout (include/reader.h:331-351).
 //     FANS_gpu --describe input.json [ms.u16 nx ny nz]   prints what the host derives from the input (no GPU needed).
+//     FANS_gpu <input.json> results.h5 ...                writes the reference's HDF5 results layout instead (h5write.hpp).
 #include <sys/stat.h>
 
 #include <cstdio>
@@ -12,6 +13,7 @@
 #include <fstream>
 #include <iostream>
 
+#include "h5write.hpp"
 #include "solver.hpp"
 
 using namespace fans;
@@ -47,6 +49,67 @@ struct DirSink : ResultsSink {
         index.flush();
     }
 };
+
+// HDF5 results file with the reference's layout (include/reader.h:173-351): <dataset>/load<L>/time_step<T>/<name>; fields are
+// transposed from the solver's [X][Y][Z][extra] to [Z][Y][X][extra] and tagged permute_order = "zyx" exactly like Reader::WriteSlab.
+struct H5Sink : ResultsSink {
+    h5w::Writer w;
+    std::string dataset;
+    H5Sink(const std::string &file, const std::string &ds) : w(file), dataset(ds) {}
+    void write(const std::string &name, int load_idx, int time_idx, const std::string &dtype, const std::vector<size_t> &dims, const void *data,
+               bool is_field) override
+    {
+        const std::string path = dataset + "/load" + std::to_string(load_idx) + "/time_step" + std::to_string(time_idx) + "/" + name;
+        std::vector<uint64_t> d(dims.begin(), dims.end());
+        if (!is_field || dims.size() < 3) {
+            w.add_dataset(path, dtype, d, data);
+            return;
+        }
+        const size_t X = dims[0], Y = dims[1], Z = dims[2], esz = h5w::Writer::elem_size(dtype);
+        size_t extra = 1;
+        for (size_t i = 3; i < dims.size(); ++i) extra *= dims[i];
+        const size_t row = extra * esz;
+        std::vector<unsigned char> t(X * Y * Z * row);
+        const unsigned char *src = (const unsigned char *)data;
+        for (size_t x = 0; x < X; ++x)
+            for (size_t y = 0; y < Y; ++y)
+                for (size_t z = 0; z < Z; ++z) std::memcpy(&t[((z * Y + y) * X + x) * row], src + ((x * Y + y) * Z + z) * row, row);
+        d[0] = Z, d[2] = X;
+        w.add_dataset(path, dtype, d, t.data(), "permute_order", "zyx");
+    }
+};
+
+// writes a small file exercising every feature of h5write.hpp (nested groups, many entries per group, all element types, field
+// transpose + attribute); tests/test_host_cpp.py parses it back with an independent reader.  No GPU needed.
+static int h5_selftest(const char *file)
+{
+    H5Sink sink(file, "/img/4x3x2/ms_results/run1");
+    const size_t X = 4, Y = 3, Z = 2;
+    std::vector<double> f(X * Y * Z * 3);
+    std::vector<uint16_t> ms(X * Y * Z);
+    for (size_t x = 0; x < X; ++x)
+        for (size_t y = 0; y < Y; ++y)
+            for (size_t z = 0; z < Z; ++z) {
+                ms[(x * Y + y) * Z + z] = (uint16_t)(100 * x + 10 * y + z);
+                for (size_t c = 0; c < 3; ++c) f[((x * Y + y) * Z + z) * 3 + c] = 1000.0 * x + 100.0 * y + 10.0 * z + c + 0.5;
+            }
+    for (int t = 0; t < 40; ++t) {  // 40 time steps: more entries than the default leaf size of libhdf5 groups
+        std::vector<double> sa(6);
+        for (int i = 0; i < 6; ++i) sa[i] = t + 0.125 * i;
+        sink.write("stress_average", 0, t, "f64", {6}, sa.data(), false);
+    }
+    sink.write("displacement", 0, 0, "f64", {X, Y, Z, 3}, f.data(), true);
+    sink.write("microstructure", 0, 0, "u16", {X, Y, Z, 1}, ms.data(), true);
+    std::vector<float> ff = {1.5f, -2.25f, 3.0f};
+    std::vector<int> ii = {-7, 0, 123456};
+    sink.write("some_floats", 1, 0, "f32", {3}, ff.data(), false);
+    sink.write("plastic_flag_like", 1, 0, "i32", {3}, ii.data(), false);
+    std::vector<double> C(36);
+    for (int i = 0; i < 36; ++i) C[i] = i * i;
+    sink.write("homogenized_tangent", 1, 0, "f64", {6, 6}, C.data(), false);
+    sink.w.close();
+    return 0;
+}
 
 static void load_raw_ms(Reader &reader, const char *file, int nx, int ny, int nz)
 {
@@ -91,7 +154,7 @@ static int describe(Reader &reader)
 }
 
 // runSolver, src/main.cpp:9-46
-static void runSolver(Reader &reader, DirSink &sink)
+static void runSolver(Reader &reader, ResultsSink &sink)
 {
     for (size_t load_path_idx = 0; load_path_idx < reader.load_cases.size(); ++load_path_idx) {
         MaterialManager *matmanager = createMaterialManager(reader);
@@ -125,16 +188,24 @@ int main(int argc, char **argv)
             else reader.ReadMS(reader.howmany());
             return describe(reader);
         }
+        if (argc == 3 && std::strcmp(argv[1], "--h5selftest") == 0) return h5_selftest(argv[2]);
         if (argc != 3 && argc != 7) {
-            fprintf(stderr, "Usage: %s <input_file.json> <results_dir> [ms.u16 nx ny nz]\n", argv[0]);
+            fprintf(stderr, "Usage: %s <input_file.json> <results_dir | results.h5> [ms.u16 nx ny nz]\n", argv[0]);
             return 10;
         }
         Reader reader;
         reader.ReadInputFile(argv[1]);
         if (argc == 7) load_raw_ms(reader, argv[3], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]));
         else reader.ReadMS(reader.howmany());
-        DirSink sink(argv[2], reader.dataset_name);
-        runSolver(reader, sink);
+        const std::string out = argv[2];
+        if (out.size() > 3 && out.compare(out.size() - 3, 3, ".h5") == 0) {  // HDF5 results file like the reference's
+            H5Sink sink(out, reader.dataset_name);
+            runSolver(reader, sink);
+            sink.w.close();
+        } else {  // directory of raw arrays + index.jsonl
+            DirSink sink(out, reader.dataset_name);
+            runSolver(reader, sink);
+        }
         return 0;
     } catch (const std::exception &e) {
         fprintf(stderr, "ERROR: %s\n", e.what());

@@ -78,3 +78,36 @@ def test_h5mini_reads_the_reference_microstructure(exe, tmp_path):
     d = json.loads(out.stdout)
     assert d["dims"] == [32, 32, 32]
     assert np.allclose(d["volume_fractions"], [1 - 8744 / 32768, 8744 / 32768])
+
+
+def test_h5_results_writer(exe, tmp_path):
+    """fans_b200/host/h5write.hpp: `FANS_gpu --h5selftest` writes an HDF5 results file with the reference's layout (nested groups, 40
+    time steps, f64 / f32 / u16 / i32, fields transposed to [Z][Y][X][extra] + permute_order = "zyx", include/reader.h:173-351);
+    tests/h5_minireader.py — an independent reader written from the format specification, which also walks the reference's own
+    sphere32.h5 — parses it back."""
+    import h5_minireader as h5
+    out = tmp_path / "selftest.h5"
+    r = subprocess.run([exe, "--h5selftest", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    f = h5.H5File(str(out))
+    w = f.walk()
+    base = "/img/4x3x2/ms_results/run1"
+    assert len(w) == 45
+    for t in range(40):
+        a, attrs = w["%s/load0/time_step%d/stress_average" % (base, t)]
+        assert a.dtype == np.float64 and np.array_equal(a, t + 0.125 * np.arange(6)) and attrs == {}
+    x, y, z, c = np.meshgrid(np.arange(4), np.arange(3), np.arange(2), np.arange(3), indexing="ij")
+    field_xyz = 1000.0 * x + 100.0 * y + 10.0 * z + c + 0.5
+    d, attrs = w[base + "/load0/time_step0/displacement"]
+    assert attrs == {"permute_order": "zyx"} and d.shape == (2, 3, 4, 3)
+    assert np.array_equal(d, np.transpose(field_xyz, (2, 1, 0, 3)))         # [Z][Y][X][extra]
+    m, attrs = w[base + "/load0/time_step0/microstructure"]
+    assert m.dtype == np.uint16 and m.shape == (2, 3, 4, 1) and attrs == {"permute_order": "zyx"}
+    assert np.array_equal(m[..., 0], np.transpose(100 * x[..., 0] + 10 * y[..., 0] + z[..., 0], (2, 1, 0)))
+    assert np.array_equal(w[base + "/load1/time_step0/some_floats"][0], np.array([1.5, -2.25, 3.0], dtype=np.float32))
+    assert np.array_equal(w[base + "/load1/time_step0/plastic_flag_like"][0], np.array([-7, 0, 123456], dtype=np.int32))
+    assert np.array_equal(w[base + "/load1/time_step0/homogenized_tangent"][0], (np.arange(36.0) ** 2).reshape(6, 6))
+    # the same reader walks a file written by the real HDF5 library (h5py): the reference's fixture
+    ref = "/root/reference/test/microstructures/sphere32.h5"
+    if os.path.exists(ref):
+        assert list(h5.H5File(ref).walk()) == ["/sphere/32x32x32/ms"]

@@ -60,3 +60,29 @@ def test_cli_scenario(tmp_path, name, steps):
         sa, ea = load("stress_average", 0, 0), load("strain_average", 0, 0)
         assert np.allclose(C @ ea, sa, rtol=1e-4, atol=1e-1) and np.allclose(C, C.T, rtol=1e-5, atol=1e-8)
         assert np.linalg.eigvalsh(C).min() > 0
+
+
+def test_cli_hdf5_results(tmp_path):
+    """FANS_gpu <input.json> results.h5: the reference's results file (include/reader.h:173-351) — same numbers as the directory sink,
+    fields stored [Z][Y][X][extra] with permute_order = "zyx"."""
+    import h5_minireader as h5
+    cfg = gu.reference_input("LinearElastic")
+    cfg["macroscale_loading"] = [lc[:1] for lc in cfg["macroscale_loading"]]
+    exe = cpp_host.build()
+    ms = tmp_path / "ms.u16"
+    gu.sphere32().tofile(ms)
+    inp = tmp_path / "in.json"
+    inp.write_text(json.dumps(cfg))
+    out = tmp_path / "results.h5"
+    r = subprocess.run([exe, str(inp), str(out), str(ms), "32", "32", "32"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    w = h5.H5File(str(out)).walk()
+    g = [x for x in gu.oracle_scenario("LinearElastic") if x["step"] == 0][0]
+    pre = [k for k in w if k.endswith("/load%d/time_step0/stress_average" % g["load_case"])][0].rsplit("/", 1)[0]
+    assert "_results/" in pre
+    assert rel_err(w[pre + "/stress_average"][0], g["stress_average"]) < 1e-9
+    stress, attrs = w[pre + "/stress"]
+    assert attrs == {"permute_order": "zyx"} and stress.shape == (32, 32, 32, 6)
+    assert np.allclose(stress.reshape(-1, 6).mean(0), w[pre + "/stress_average"][0], rtol=1e-5, atol=1e-8)
+    msr, _ = w[pre + "/microstructure"]
+    assert np.array_equal(msr[..., 0], np.transpose(gu.sphere32(), (2, 1, 0)))
