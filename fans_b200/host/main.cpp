@@ -75,6 +75,7 @@ struct H5Sink : ResultsSink {
             for (size_t y = 0; y < Y; ++y)
                 for (size_t z = 0; z < Z; ++z) std::memcpy(&t[((z * Y + y) * X + x) * row], src + ((x * Y + y) * Z + z) * row, row);
         d[0] = Z, d[2] = X;
+        if (d.size() == 3) d.push_back(1);  // scalar fields carry an explicit extra dimension of 1 (solver.h:667-668: writeSlab(..., {1}))
         w.add_dataset(path, dtype, d, t.data(), "permute_order", "zyx");
     }
 };
@@ -99,7 +100,7 @@ static int h5_selftest(const char *file)
         sink.write("stress_average", 0, t, "f64", {6}, sa.data(), false);
     }
     sink.write("displacement", 0, 0, "f64", {X, Y, Z, 3}, f.data(), true);
-    sink.write("microstructure", 0, 0, "u16", {X, Y, Z, 1}, ms.data(), true);
+    sink.write("microstructure", 0, 0, "u16", {X, Y, Z}, ms.data(), true);
     std::vector<float> ff = {1.5f, -2.25f, 3.0f};
     std::vector<int> ii = {-7, 0, 123456};
     sink.write("some_floats", 1, 0, "f32", {3}, ff.data(), false);
