@@ -121,3 +121,25 @@ def j2_fiber_context(ms, Lbox, fe_type="HEX8", device=-1, gdims=None, comm=None)
     ctx.set_microstructure(ms)
     ctx.set_reference_stiffness(0.5 * (elastic_tangent(K0 - 2.0 / 3.0 * G0, G0) + elastic_tangent(K1 - 2.0 / 3.0 * G1, G1)))
     return ctx
+
+
+def voronoi_microstructure(dims, n_seeds=None, seed=2024, x0=0, n0=None):
+    """Synthetic config-4 image: "polycrystal-like" periodic Voronoi tessellation, phase = grain label mod 2.
+    n_seeds defaults to 512 scaled with the volume relative to 1024^3 (grain size ~128 voxels).  Returns the slab [x0, x0 + n0)."""
+    from scipy.spatial import cKDTree
+    nx, ny, nz = dims
+    n0 = nx if n0 is None else n0
+    if n_seeds is None:
+        n_seeds = max(8, int(round(512.0 * nx * ny * nz / 1024.0 ** 3)))
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0.0, 1.0, size=(n_seeds, 3)) * np.array([nx, ny, nz], dtype=np.float64)
+    tree = cKDTree(pts, boxsize=[nx, ny, nz])   # periodic nearest neighbour
+    yy, zz = np.meshgrid(np.arange(ny) + 0.5, np.arange(nz) + 0.5, indexing="ij")
+    q = np.empty((ny * nz, 3))
+    q[:, 1], q[:, 2] = yy.ravel(), zz.ravel()
+    ms = np.empty((n0, ny, nz), dtype=np.uint16)
+    for i in range(n0):
+        q[:, 0] = x0 + i + 0.5
+        _, lab = tree.query(q, workers=-1)
+        ms[i] = (lab % 2).reshape(ny, nz)
+    return ms

@@ -15,7 +15,7 @@ ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--tag", default="")
 ap.add_argument("--fe", default="HEX8")
-ap.add_argument("--ms", default="ellipsoid", help="ellipsoid | homogeneous | layers")
+ap.add_argument("--ms", default="ellipsoid", help="ellipsoid | homogeneous | layers | voronoi")
 args = ap.parse_args()
 n = args.size
 dims = [n, n, n]
@@ -23,6 +23,8 @@ ms = simple.ellipsoid_microstructure(dims)
 if args.ms == "homogeneous":
     ms[...] = 0
     ms[0, 0, 0] = 1
+elif args.ms == "voronoi":
+    ms = simple.voronoi_microstructure(dims)
 elif args.ms == "layers":
     ms[...] = 0
     ms[n // 4: 3 * n // 4] = 1
