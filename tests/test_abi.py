@@ -116,3 +116,24 @@ def test_fibre_image_generator():
                     stack.append((c, d))
         n += 1
     assert 20 <= n <= 64    # discs at distance ~2r touch on the raster and merge; a broken generator gives 1 blob or > 64 specks
+
+
+def test_voronoi_image_generator():
+    """fans_b200.simple.voronoi_microstructure (BASELINE config 4 image): deterministic, two phases, slab-wise generation equals the
+    full image (what every rank of the multi-GPU bench relies on), periodic in every direction."""
+    import numpy as np
+    from fans_b200 import simple
+    dims = (32, 16, 24)
+    ms = simple.voronoi_microstructure(dims, n_seeds=12)
+    assert ms.dtype == np.uint16 and ms.shape == dims and set(np.unique(ms)) == {0, 1}
+    assert 0.2 < float(ms.mean()) < 0.8
+    lo, hi = simple.voronoi_microstructure(dims, n_seeds=12, x0=0, n0=16), simple.voronoi_microstructure(dims, n_seeds=12, x0=16, n0=16)
+    assert np.array_equal(np.concatenate([lo, hi]), ms)
+    # periodic: the image of the seeds shifted by one period is the same image
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(2024)
+    pts = rng.uniform(0.0, 1.0, size=(12, 3)) * np.array(dims, dtype=np.float64)
+    img = np.concatenate([pts + np.array(s) * np.array(dims) for s in np.ndindex(3, 3, 3)]) - np.array(dims)   # 27 periodic copies
+    x, y, z = np.meshgrid(*(np.arange(n) + 0.5 for n in dims), indexing="ij")
+    _, lab = cKDTree(img).query(np.stack([x.ravel(), y.ravel(), z.ravel()], 1))
+    assert np.array_equal(((lab % 12) % 2).reshape(dims).astype(np.uint16), ms)
