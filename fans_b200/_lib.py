@@ -309,6 +309,10 @@ class Context:
             out = np.empty((nx, ny, nz, 6))
         elif name == "isotropic_hardening_variable":
             out = np.empty((nx, ny, nz))
+        elif name in ("plastic_strain_gp", "kinematic_hardening_variable_gp"):   # every Gauss point, J2Plasticity.h:298-307
+            out = np.empty((nx, ny, nz, self.n_gp, 6))
+        elif name == "isotropic_hardening_variable_gp":
+            out = np.empty((nx, ny, nz, self.n_gp))
         elif name == "fundamental_solution":  # global frequency grid; only this rank's y rows are filled when world_size > 1
             out = np.zeros((ny, self.gdims[0], nz // 2 + 1, self.h * (self.h + 1) // 2))
         else:

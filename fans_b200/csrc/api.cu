@@ -846,6 +846,29 @@ extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t
             }
         return FANS_OK;
     }
+    if (n == "plastic_strain_gp" || n == "kinematic_hardening_variable_gp" || n == "isotropic_hardening_variable_gp") {
+        // all Gauss-point values of the committed state, [element][gp][component] (J2Plasticity.h:279-307: writeSlab(..., {n_gp, n_str}))
+        if (!ctx->hist_t) {
+            fans_set_error(ctx, FANS_ERR_STATE, "no history-dependent model present");
+            return FANS_ERR_STATE;
+        }
+        const int first = (n == "plastic_strain_gp") ? 0 : (n == "isotropic_hardening_variable_gp" ? 6 : 7);
+        const int cnt = (n == "isotropic_hardening_variable_gp") ? 1 : 6;
+        if (first + cnt > ctx->n_hist) {
+            fans_set_error(ctx, FANS_ERR_STATE, n + " is not a variable of the active model");
+            return FANS_ERR_STATE;
+        }
+        if (!need(sizeof(double) * cnt * ctx->ngp * N)) return FANS_ERR_ARG;
+        std::vector<double> tmp((size_t)cnt * ctx->ngp * N);
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->hist_t + (size_t)first * ctx->ngp * N, sizeof(double) * cnt * ctx->ngp * N,
+                                      cudaMemcpyDeviceToHost, ctx->st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+        double *o = (double *)dst;
+        for (size_t v = 0; v < N; ++v)
+            for (int g = 0; g < ctx->ngp; ++g)
+                for (int k = 0; k < cnt; ++k) o[(v * ctx->ngp + g) * cnt + k] = tmp[((size_t)k * ctx->ngp + g) * N + v];
+        return FANS_OK;
+    }
     if (n == "fundamental_solution") {
         if (!ctx->gamma_ready) {
             fans_set_error(ctx, FANS_ERR_STATE, "reference stiffness not set");

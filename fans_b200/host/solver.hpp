@@ -255,6 +255,24 @@ class Solver {
             std::vector<char> buf(N * extra * esz);
             if (fans_get_field(ctx, nm, buf.data(), buf.size()) == FANS_OK) sink.write(nm, load_idx, time_idx, dt, gd(extra), buf.data(), true);
         };
+        if (want("mpi_rank")) {  // solver.h:666-667
+            std::vector<int> ranks(N, world_rank);
+            sink.write("mpi_rank", load_idx, time_idx, "i32", gd(1), ranks.data(), true);
+        }
+        // all Gauss points of the committed history, extra dims {n_gp, n_str} / {n_gp} (J2Plasticity.h:298-307)
+        auto try_field_gp = [&](const char *nm, size_t ncomp) {
+            if (!want(nm)) return;
+            const size_t ngp = reader.FE_type == "HEX8R" ? 1 : 8;  // matmodel.h:104-155: one Gauss point for HEX8R, 2x2x2 otherwise
+            std::vector<double> buf(N * ngp * ncomp);
+            if (fans_get_field(ctx, nm, buf.data(), buf.size() * sizeof(double)) != FANS_OK) return;
+            std::vector<size_t> d = g;
+            d.push_back(ngp);
+            if (ncomp > 1) d.push_back(ncomp);
+            sink.write(nm, load_idx, time_idx, "f64", d, buf.data(), true);
+        };
+        try_field_gp("plastic_strain_gp", 6);
+        try_field_gp("isotropic_hardening_variable_gp", 1);
+        try_field_gp("kinematic_hardening_variable_gp", 6);
         try_field("plastic_flag", "f32", 1, 4);
         try_field("plastic_strain", "f64", 6, 8);
         try_field("isotropic_hardening_variable", "f64", 1, 8);

@@ -121,3 +121,27 @@ def test_neg_jacobian_is_reported():
     with pytest.raises(L.FansError, match="Negative Jacobian"):
         ctx.residual("r", "u")
     ctx.close()
+
+
+def test_history_gauss_point_outputs():
+    """plastic_strain_gp / isotropic_hardening_variable_gp / kinematic_hardening_variable_gp (J2Plasticity.h:279-307): every Gauss point of
+    the committed state, [element][gp][component]; their Gauss-point means are the element outputs, and they match the oracle's state."""
+    ms = util.two_phase_ms(0, 11, (16, 8, 32))
+    cfg = cfg_for([MODELS["j2_lin"], EL1], "HEX8", "cg", LOAD)
+    sol = fo.OracleSolver(ms, cfg["microstructure"]["L"], cfg["problem_type"], cfg["materials"], cfg["FE_type"], cfg["method"], "small",
+                          cfg["error_parameters"], cfg["n_it"])
+    ctx = util.ctx_from_oracle(sol)
+    ep = cfg["error_parameters"]
+    for g in cfg["macroscale_loading"][0]:
+        sol.set_gradient(g)
+        ctx.set_gradient(g)
+        sol.solve()
+        ctx.solve("cg", cfg["n_it"], ep["tolerance"], ep["measure"], ep["type"])
+    eg = ctx.get_field("plastic_strain_gp")
+    assert eg.shape == ms.shape + (8, 6) and np.abs(eg).max() > 1e-6          # the plastic branch really ran
+    assert rel_err(eg.mean(-2), ctx.get_field("plastic_strain")) < 1e-12
+    assert rel_err(ctx.get_field("isotropic_hardening_variable_gp").mean(-1), ctx.get_field("isotropic_hardening_variable")) < 1e-12
+    assert rel_err(ctx.get_field("kinematic_hardening_variable_gp").mean(-2), ctx.get_field("kinematic_hardening_variable")) < 1e-12
+    m = sol.models[0]
+    assert rel_err(eg, m.ep_t.reshape(eg.shape)) < 1e-8   # oracle state: [element][gp][component]
+    ctx.close()
