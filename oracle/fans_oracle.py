@@ -811,8 +811,10 @@ class OracleSolver:
         res_e = np.zeros_like(ue)
         for gi in self.phase_K:
             el = self.el_of_model[gi]
-            K = self.phase_K[gi][self.local_of_el[el]]
-            res_e[el] = np.einsum("mij,mj->mi", K, ue[el])
+            loc = self.local_of_el[el]
+            for m in np.unique(loc):          # one dense product per phase: res_e = K_phase ue  (LinearModel::phase_stiffness)
+                sel = el[loc == m]
+                res_e[sel] = ue[sel] @ self.phase_K[gi][m].T
         return self._scatter(res_e)
 
     # ---------------- Green operator (solver.h:144-204) -----------------------------------
