@@ -260,6 +260,8 @@ inline bool h5mini_read_dataset(const std::string &file, const std::string &data
                 if (val == "xyz" || val == "zyx") permute_order = val;
             }
         }
+        // a results file stores scalar fields as [Z][Y][X][1] (include/solver.h:667-668): trailing dimensions of extent 1 are dropped
+        while (rank > 3 && dsz[rank - 1] == 1) --rank;
         if (rank != 3 || elem < 1 || elem > 8 || layout_class < 0) {
             err = "dataset must be a rank-3 integer array";
             return false;

@@ -107,6 +107,15 @@ def test_h5_results_writer(exe, tmp_path):
     assert np.array_equal(w[base + "/load1/time_step0/some_floats"][0], np.array([1.5, -2.25, 3.0], dtype=np.float32))
     assert np.array_equal(w[base + "/load1/time_step0/plastic_flag_like"][0], np.array([-7, 0, 123456], dtype=np.int32))
     assert np.array_equal(w[base + "/load1/time_step0/homogenized_tangent"][0], (np.arange(36.0) ** 2).reshape(6, 6))
+    # the C++ microstructure reader (h5mini.hpp, validated on the reference's h5py-written fixture) resolves the symbol-table groups of
+    # the written file and reads the [Z][Y][X][1] field back as an image (permute_order = "zyx" -> dims X, Y, Z)
+    cfg = gu.reference_input("LinearElastic")
+    cfg["microstructure"] = {"filepath": str(out), "datasetname": base + "/load0/time_step0/microstructure", "L": [1.0, 1.0, 1.0]}
+    inp = tmp_path / "in_h5.json"
+    inp.write_text(json.dumps(cfg))
+    r = subprocess.run([exe, "--describe", str(inp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout)["dims"] == [4, 3, 2]
     # the same reader walks a file written by the real HDF5 library (h5py): the reference's fixture
     ref = "/root/reference/test/microstructures/sphere32.h5"
     if os.path.exists(ref):
