@@ -370,7 +370,7 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     for (int f = 0; f < FANS_N_FIELDS; ++f)
         if (ctx->field[f]) cudaFree(ctx->field[f]);
     void *ptrs[] = {ctx->specB, ctx->ms_lo, ctx->halo_send_lo, ctx->halo_send_hi, ctx->halo_lo, ctx->halo_hi, ctx->d_alt, ctx->stage_io, ctx->ms, ctx->phidx, ctx->spec, ctx->gamma, ctx->d_phase, ctx->d_K, ctx->phase_lut,
-                    ctx->hist, ctx->hist_t, ctx->pflag, ctx->d_part, ctx->d_red, ctx->d_ticket, ctx->d_flag, ctx->d_C};
+                    ctx->hist, ctx->hist_t, ctx->hidx, ctx->pflag, ctx->d_part, ctx->d_red, ctx->d_ticket, ctx->d_flag, ctx->d_C};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
@@ -416,6 +416,7 @@ extern "C" int fans_set_microstructure(fans_ctx *ctx, const uint16_t *ms)
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     ctx->ms_ready = true;
+    ctx->hist_ready = false;  // the compact history index follows the phase image
     return FANS_OK;
 }
 
@@ -450,6 +451,25 @@ extern "C" int fans_set_materials(fans_ctx *ctx, int32_t n_phases, const fans_ph
             elem_stiffness(E, ph[i].params, K);
             Ktab.insert(Ktab.end(), K.begin(), K.end());
             Ctab.insert(Ctab.end(), ph[i].params, ph[i].params + ns * ns);
+            // exactly isotropic tangent (what LinearElasticIsotropic / LinearThermalIsotropic build, LinearElastic.h:33-34,
+            // LinearThermal.h:24-31): the Gauss-point law then is the reference's own closed form instead of a dense C.eps
+            const double *Cm = ph[i].params;
+            bool iso = (ns == 6 || ns == 3);
+            if (ns == 6) {
+                const double lam = Cm[1], mu2 = Cm[3 * 6 + 3];
+                for (int r = 0; r < 6 && iso; ++r)
+                    for (int c = 0; c < 6; ++c) {
+                        const double want = (r < 3 && c < 3 ? lam : 0.0) + (r == c ? mu2 : 0.0);
+                        if (Cm[r * 6 + c] != want) iso = false;
+                    }
+                d.params[0] = lam, d.params[1] = mu2;
+            } else if (ns == 3) {
+                for (int r = 0; r < 3 && iso; ++r)
+                    for (int c = 0; c < 3; ++c)
+                        if (Cm[r * 3 + c] != (r == c ? Cm[0] : 0.0)) iso = false;
+                d.params[0] = Cm[0];
+            }
+            d.lin_iso = iso ? 1 : 0;
             break;
         }
         case FANS_MAT_PSEUDOPLASTIC_LINEAR:
@@ -477,6 +497,7 @@ extern "C" int fans_set_materials(fans_ctx *ctx, int32_t n_phases, const fans_ph
             return FANS_ERR_MATERIAL;
         }
         for (int k = 0; k < npar; ++k) d.params[k] = ph[i].params[k];
+        d.has_hist = (ph[i].model == FANS_MAT_J2_LINEAR_ISO || ph[i].model == FANS_MAT_J2_NONLIN_ISO || ph[i].model == FANS_MAT_J2NEW_LINEAR_ISO);
         if (ph[i].model != FANS_MAT_LINEAR) all_lin = false;
     }
     ctx->phases.assign(ph, ph + n_phases);
@@ -500,24 +521,15 @@ extern "C" int fans_set_materials(fans_ctx *ctx, int32_t n_phases, const fans_ph
     if (ctx->d_phase) cudaFree(ctx->d_phase), ctx->d_phase = nullptr;
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_phase, sizeof(PhaseDev) * n_phases));
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_phase, dev.data(), sizeof(PhaseDev) * n_phases, cudaMemcpyHostToDevice));
-    // internal variables: MaterialManager::initialize_internal_variables (solver.h:139) — for EVERY element
+    // internal variables: MaterialManager::initialize_internal_variables (solver.h:139).  The reference allocates them for EVERY
+    // element of every model (J2Plasticity.h:47-56); here only the elements whose phase reads them get storage (history_prepare)
     if (ctx->hist) cudaFree(ctx->hist), ctx->hist = nullptr;
     if (ctx->hist_t) cudaFree(ctx->hist_t), ctx->hist_t = nullptr;
     if (ctx->pflag) cudaFree(ctx->pflag), ctx->pflag = nullptr;
     ctx->n_hist = nhist;
-    if (nhist > 0) {
-        const size_t bytes = sizeof(double) * nhist * ctx->ngp * ctx->nloc;
-        size_t fr = 0, tot = 0;
-        cudaMemGetInfo(&fr, &tot);
-        if (2 * bytes > fr) {
-            fans_set_error(ctx, FANS_ERR_CUDA, "history variables need " + std::to_string(2 * bytes >> 20) + " MiB, only " + std::to_string(fr >> 20) + " MiB free");
-            return FANS_ERR_CUDA;
-        }
-        CUDA_TRY(ctx, cudaMalloc(&ctx->hist, bytes));
-        CUDA_TRY(ctx, cudaMalloc(&ctx->hist_t, bytes));
-        CUDA_TRY(ctx, cudaMemset(ctx->hist, 0, bytes));
-        CUDA_TRY(ctx, cudaMemset(ctx->hist_t, 0, bytes));
-    }
+    ctx->hist_ready = false;
+    ctx->has_hist_host.assign(n_phases, 0);
+    for (int i = 0; i < n_phases; ++i) ctx->has_hist_host[i] = (uint8_t)dev[i].has_hist;
     if (any_flag) {
         CUDA_TRY(ctx, cudaMalloc(&ctx->pflag, sizeof(int) * ctx->ngp * ctx->nloc));
         CUDA_TRY(ctx, cudaMemset(ctx->pflag, 0, sizeof(int) * ctx->ngp * ctx->nloc));
@@ -573,6 +585,108 @@ extern "C" int fans_get_gradient(fans_ctx *ctx, double *g0)
 {
     if (!ctx || !g0) return FANS_ERR_ARG;
     for (int i = 0; i < ctx->nstr; ++i) g0[i] = ctx->g0[i];
+    return FANS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compact history storage: hidx[element] = running index over the elements whose phase carries history (memory order), so the
+// history arrays of BASELINE config 3 (J2 matrix, elastic fibres, 512^3) shrink with the J2 volume fraction and stay coalesced
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hist_rowcount(const uint16_t *__restrict__ ph, const uint8_t *__restrict__ has, int nz, size_t nrows, unsigned *cnt)
+{
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int lane = threadIdx.x & 31;
+    unsigned n = 0;
+    for (int z = lane; z < nz; z += 32) n += has[ph[row * nz + z]];
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) cnt[row] = n;
+}
+__global__ void k_hist_fill(const uint16_t *__restrict__ ph, const uint8_t *__restrict__ has, int nz, size_t nrows,
+                            const unsigned *__restrict__ rowoff, unsigned *__restrict__ hidx)
+{
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int lane = threadIdx.x & 31;
+    unsigned off = rowoff[row];
+    for (int z0 = 0; z0 < nz; z0 += 32) {
+        const int z = z0 + lane;
+        const bool f = (z < nz) && has[ph[row * nz + z]];
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (z < nz) hidx[row * nz + z] = f ? off + __popc(m & ((1u << lane) - 1u)) : 0xffffffffu;
+        off += __popc(m);
+    }
+}
+
+int history_prepare(fans_ctx *ctx)
+{
+    if (ctx->hist_ready || ctx->n_hist == 0) return FANS_OK;
+    if (!ctx->ms_ready || !ctx->materials_ready) {
+        fans_set_error(ctx, FANS_ERR_STATE, "microstructure and materials must be set before the history variables exist");
+        return FANS_ERR_STATE;
+    }
+    if (ctx->hist) cudaFree(ctx->hist), ctx->hist = nullptr;
+    if (ctx->hist_t) cudaFree(ctx->hist_t), ctx->hist_t = nullptr;
+    const size_t nrows = (size_t)ctx->n0 * ctx->ny;
+    uint8_t *d_has = nullptr;
+    unsigned *d_cnt = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_has, ctx->n_phases));
+    CUDA_TRY(ctx, cudaMalloc(&d_cnt, sizeof(unsigned) * nrows));
+    if (!ctx->hidx) CUDA_TRY(ctx, cudaMalloc(&ctx->hidx, sizeof(unsigned) * ctx->nloc));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_has, ctx->has_hist_host.data(), ctx->n_phases, cudaMemcpyHostToDevice, ctx->st));
+    const unsigned nb = (unsigned)((nrows + 7) / 8);
+    k_hist_rowcount<<<nb, 256, 0, ctx->st>>>(ctx->phidx, d_has, ctx->nz, nrows, d_cnt);
+    std::vector<unsigned> cnt(nrows);
+    CUDA_TRY(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(unsigned) * nrows, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    size_t run = 0;
+    for (size_t r = 0; r < nrows; ++r) {
+        const unsigned c = cnt[r];
+        cnt[r] = (unsigned)run;
+        run += c;
+    }
+    ctx->nh = run;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_cnt, cnt.data(), sizeof(unsigned) * nrows, cudaMemcpyHostToDevice, ctx->st));
+    k_hist_fill<<<nb, 256, 0, ctx->st>>>(ctx->phidx, d_has, ctx->nz, nrows, d_cnt, ctx->hidx);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    cudaFree(d_has);
+    cudaFree(d_cnt);
+    CUDA_TRY(ctx, cudaGetLastError());
+    const size_t bytes = sizeof(double) * ctx->n_hist * ctx->ngp * (ctx->nh ? ctx->nh : 1);
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    if (2 * bytes > fr) {
+        fans_set_error(ctx, FANS_ERR_CUDA, "history variables need " + std::to_string(2 * bytes >> 20) + " MiB, only " + std::to_string(fr >> 20) + " MiB free");
+        return FANS_ERR_CUDA;
+    }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->hist, bytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->hist_t, bytes));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist, 0, bytes, ctx->st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist_t, 0, bytes, ctx->st));
+    ctx->hist_ready = true;
+    return FANS_OK;
+}
+
+// history variables [first, first + cnt) of the committed state, expanded to every element (zero where the phase has none):
+// out[(v * ngp + g) * cnt + k]
+static int history_expand(fans_ctx *ctx, int first, int cnt, std::vector<double> &out)
+{
+    FANS_CHECK(history_prepare(ctx));
+    const size_t N = ctx->nloc, nh = ctx->nh;
+    const int ngp = ctx->ngp;
+    std::vector<double> tmp((size_t)cnt * ngp * (nh ? nh : 1));
+    std::vector<unsigned> idx(N);
+    if (nh) CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->hist_t + (size_t)first * ngp * nh, sizeof(double) * cnt * ngp * nh, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(idx.data(), ctx->hidx, sizeof(unsigned) * N, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    out.assign((size_t)cnt * ngp * N, 0.0);
+    for (size_t v = 0; v < N; ++v) {
+        const unsigned he = idx[v];
+        if (he == 0xffffffffu) continue;
+        for (int g = 0; g < ngp; ++g)
+            for (int k = 0; k < cnt; ++k) out[(v * ngp + g) * cnt + k] = tmp[((size_t)k * ngp + g) * nh + he];
+    }
     return FANS_OK;
 }
 
@@ -739,8 +853,10 @@ extern "C" int fans_commit_history(fans_ctx *ctx)
 {
     if (!ctx) return FANS_ERR_ARG;
     cudaSetDevice(ctx->device);
-    if (ctx->n_hist > 0)
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hist_t, ctx->hist, sizeof(double) * ctx->n_hist * ctx->ngp * ctx->nloc, cudaMemcpyDeviceToDevice, ctx->st));
+    if (ctx->n_hist > 0) {
+        FANS_CHECK(history_prepare(ctx));
+        if (ctx->nh) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hist_t, ctx->hist, sizeof(double) * ctx->n_hist * ctx->ngp * ctx->nh, cudaMemcpyDeviceToDevice, ctx->st));
+    }
     return FANS_OK;
 }
 
@@ -821,52 +937,36 @@ extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t
         }
         return FANS_OK;
     }
-    if (n == "plastic_strain" || n == "kinematic_hardening_variable" || n == "isotropic_hardening_variable") {
-        if (!ctx->hist_t) {
+    if (n == "plastic_strain" || n == "kinematic_hardening_variable" || n == "isotropic_hardening_variable" ||
+        n == "plastic_strain_gp" || n == "kinematic_hardening_variable_gp" || n == "isotropic_hardening_variable_gp") {
+        // J2Plasticity.h:245-322: element outputs are the Gauss-point means of the committed (_t) values; the *_gp outputs are all
+        // Gauss-point values [element][gp][component] (J2Plasticity.h:279-307: writeSlab(..., {n_gp, n_str}))
+        if (ctx->n_hist == 0) {
             fans_set_error(ctx, FANS_ERR_STATE, "no history-dependent model present");
             return FANS_ERR_STATE;
         }
-        const int first = (n == "plastic_strain") ? 0 : (n == "isotropic_hardening_variable" ? 6 : 7);
-        const int cnt = (n == "isotropic_hardening_variable") ? 1 : 6;
+        const bool gp = n.size() > 3 && n.compare(n.size() - 3, 3, "_gp") == 0;
+        const std::string base = gp ? n.substr(0, n.size() - 3) : n;
+        const int first = (base == "plastic_strain") ? 0 : (base == "isotropic_hardening_variable" ? 6 : 7);
+        const int cnt = (base == "isotropic_hardening_variable") ? 1 : 6;
         if (first + cnt > ctx->n_hist) {
             fans_set_error(ctx, FANS_ERR_STATE, n + " is not a variable of the active model");
             return FANS_ERR_STATE;
         }
-        if (!need(sizeof(double) * cnt * N)) return FANS_ERR_ARG;
-        std::vector<double> tmp((size_t)cnt * ctx->ngp * N);
-        CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->hist_t + (size_t)first * ctx->ngp * N, sizeof(double) * cnt * ctx->ngp * N,
-                                      cudaMemcpyDeviceToHost, ctx->st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
-        double *o = (double *)dst;  // J2Plasticity.h:245-322: GP mean of the committed (_t) values
-        for (size_t v = 0; v < N; ++v)
-            for (int k = 0; k < cnt; ++k) {
-                double s = 0.0;
-                for (int g = 0; g < ctx->ngp; ++g) s += tmp[((size_t)k * ctx->ngp + g) * N + v];
-                o[v * cnt + k] = s / ctx->ngp;
-            }
-        return FANS_OK;
-    }
-    if (n == "plastic_strain_gp" || n == "kinematic_hardening_variable_gp" || n == "isotropic_hardening_variable_gp") {
-        // all Gauss-point values of the committed state, [element][gp][component] (J2Plasticity.h:279-307: writeSlab(..., {n_gp, n_str}))
-        if (!ctx->hist_t) {
-            fans_set_error(ctx, FANS_ERR_STATE, "no history-dependent model present");
-            return FANS_ERR_STATE;
-        }
-        const int first = (n == "plastic_strain_gp") ? 0 : (n == "isotropic_hardening_variable_gp" ? 6 : 7);
-        const int cnt = (n == "isotropic_hardening_variable_gp") ? 1 : 6;
-        if (first + cnt > ctx->n_hist) {
-            fans_set_error(ctx, FANS_ERR_STATE, n + " is not a variable of the active model");
-            return FANS_ERR_STATE;
-        }
-        if (!need(sizeof(double) * cnt * ctx->ngp * N)) return FANS_ERR_ARG;
-        std::vector<double> tmp((size_t)cnt * ctx->ngp * N);
-        CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->hist_t + (size_t)first * ctx->ngp * N, sizeof(double) * cnt * ctx->ngp * N,
-                                      cudaMemcpyDeviceToHost, ctx->st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+        if (!need(sizeof(double) * cnt * (gp ? ctx->ngp : 1) * N)) return FANS_ERR_ARG;
+        std::vector<double> all;
+        FANS_CHECK(history_expand(ctx, first, cnt, all));
         double *o = (double *)dst;
-        for (size_t v = 0; v < N; ++v)
-            for (int g = 0; g < ctx->ngp; ++g)
-                for (int k = 0; k < cnt; ++k) o[(v * ctx->ngp + g) * cnt + k] = tmp[((size_t)k * ctx->ngp + g) * N + v];
+        if (gp) {
+            memcpy(o, all.data(), sizeof(double) * all.size());
+        } else {
+            for (size_t v = 0; v < N; ++v)
+                for (int k = 0; k < cnt; ++k) {
+                    double sum = 0.0;
+                    for (int g = 0; g < ctx->ngp; ++g) sum += all[(v * ctx->ngp + g) * cnt + k];
+                    o[v * cnt + k] = sum / ctx->ngp;
+                }
+        }
         return FANS_OK;
     }
     if (n == "fundamental_solution") {

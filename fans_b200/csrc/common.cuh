@@ -41,6 +41,7 @@ struct FftPlan {
 struct PhaseDev {  // device copy of one fans_phase_desc (params trimmed)
     int    model, local_mat, group_n_mat, k_index;  // k_index: slot of the phase stiffness in the K table (linear) or -1
     const double *tangent;                          // linear phases: device pointer to C (n_str x n_str, row-major)
+    int    lin_iso, has_hist;                       // lin_iso: linear phase whose tangent is exactly isotropic (params = lambda, 2 mu / conductivity)
     double params[12];
 };
 
@@ -103,9 +104,13 @@ struct fans_ctx {
     bool materials_ready = false, ms_ready = false;
     uint64_t const_stamp = 0;   // identifies this ctx's content of the __constant__ tables
 
-    // history (dense per element, SoA [var][gp][element])
+    // history: compact over the elements whose phase carries history, SoA [var][gp][compact element]
     double *hist = nullptr, *hist_t = nullptr;
     int n_hist = 0;             // doubles per GP
+    unsigned *hidx = nullptr;   // [nloc] compact history index of an element, 0xffffffff: its phase has no history
+    size_t nh = 0;              // number of history-bearing elements of this slab
+    bool hist_ready = false;    // hidx / hist / hist_t match the current microstructure + materials
+    std::vector<uint8_t> has_hist_host;  // per phase: its model carries history
     int *pflag = nullptr;       // plastic_flag [gp][element]
 
     // mixed BC

@@ -34,6 +34,9 @@ uint64_t sweep_new_stamp();
 int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const double *s_in, double *d_new,
               const double *beta_dev, double *red_out, double *eps_out, double *sig_out);
 
+// api.cu: (re)builds the compact history index + arrays when microstructure or materials changed since the last build
+int history_prepare(fans_ctx *ctx);
+
 // vecops.cu
 int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const double *d, const double *s);
 int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev);

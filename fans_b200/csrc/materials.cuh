@@ -1,6 +1,7 @@
 // materials.cuh — Gauss-point material laws evaluated in registers (one call = one Matmodel::get_sigma).
-// Each branch cites the reference get_sigma it restates.  History lives in SoA arrays
-//   hist[(var*ngp + gp)*nloc + element]   (current)  and  hist_t (committed),  element fastest => coalesced.
+// Each branch cites the reference get_sigma it restates.  History lives in COMPACT SoA arrays over the elements whose phase
+// carries history (hidx[element] = compact index, built in api.cu; elastic phases such as fibres cost no history memory):
+//   hist[(var*ngp + gp)*nh + hel]   (current)  and  hist_t (committed),  compact element index fastest => coalesced.
 #pragma once
 #include "common.cuh"
 
@@ -84,11 +85,27 @@ struct HistStage {
 // One Gauss point.  e: strain-like input, s: stress-like output.
 template <int NSTR>
 __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&e)[NSTR], double (&s)[NSTR], double *hist,
-                                             const double *hist_t, int *pflag, size_t nloc, int ngp, int gp, size_t el,
-                                             bool write_state, int *fault, const HistStage hs = HistStage{nullptr, 0})
+                                             const double *hist_t, int *pflag, size_t nloc, size_t nh, int ngp, int gp, size_t el,
+                                             size_t hel, bool write_state, int *fault, const HistStage hs = HistStage{nullptr, 0})
 {
+    // nloc / el address the dense per-element arrays (plastic_flag), nh / hel the compact history arrays
     const double *P = pd.params;
     if (pd.model == FANS_MAT_LINEAR) {
+        if (pd.lin_iso) {
+            if (NSTR == 6) {
+                // LinearElasticIsotropic::get_sigma (LinearElastic.h:43-53): params = lambda, 2 mu
+                const double buf1 = P[0] * (e[0] + e[1] + e[2]), buf2 = P[1];
+#pragma unroll
+                for (int i = 0; i < NSTR; ++i) s[i] = (i < 3 ? buf1 : 0.0) + buf2 * e[i];
+                return;
+            }
+            if (NSTR == 3) {
+                // LinearThermalIsotropic::get_sigma (LinearThermal.h:35-40): params = conductivity
+#pragma unroll
+                for (int i = 0; i < NSTR; ++i) s[i] = P[0] * e[i];
+                return;
+            }
+        }
         // sigma = C eps with the phase tangent (LinearThermal.h:35-40,104-107; LinearElastic.h:43-53,141-144)
         const double *C = pd.tangent;
 #pragma unroll
@@ -142,10 +159,10 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             double ept[6], pbt[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                ept[i] = hs.s ? hs(i) : hist_t[((size_t)i * ngp + gp) * nloc + el];
-                pbt[i] = hs.s ? hs(7 + i) : hist_t[((size_t)(7 + i) * ngp + gp) * nloc + el];
+                ept[i] = hs.s ? hs(i) : hist_t[((size_t)i * ngp + gp) * nh + hel];
+                pbt[i] = hs.s ? hs(7 + i) : hist_t[((size_t)(7 + i) * ngp + gp) * nh + hel];
             }
-            const double psit = hs.s ? hs(6) : hist_t[((size_t)6 * ngp + gp) * nloc + el];
+            const double psit = hs.s ? hs(6) : hist_t[((size_t)6 * ngp + gp) * nh + hel];
             double ee[6], st[6], dev[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) ee[i] = e[i % NSTR] - ept[i];
@@ -193,8 +210,8 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
 #pragma unroll
             for (int i = 0; i < 6; ++i) s[i % NSTR] = st[i] - gam * 2 * G * nvec[i];
             if (write_state) {
-                double *hb = hist + (size_t)gp * nloc + el;   // variable v of this Gauss point: hb[v * vs]
-                const size_t vs = (size_t)ngp * nloc;
+                double *hb = hist + (size_t)gp * nh + hel;   // variable v of this Gauss point: hb[v * vs]
+                const size_t vs = (size_t)ngp * nh;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     hb[i * vs] = ept[i] + gam * nvec[i];
@@ -210,8 +227,8 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             const double K = P[0], G = P[1], sy0 = P[2], Kiso = P[3];
             double ep[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) ep[i] = hs.s ? hs(i) : hist_t[((size_t)i * ngp + gp) * nloc + el];
-            const double q_in = hs.s ? hs(6) : hist_t[((size_t)6 * ngp + gp) * nloc + el];
+            for (int i = 0; i < 6; ++i) ep[i] = hs.s ? hs(i) : hist_t[((size_t)i * ngp + gp) * nh + hel];
+            const double q_in = hs.s ? hs(6) : hist_t[((size_t)6 * ngp + gp) * nh + hel];
             const double lam = K - 2.0 / 3.0 * G;
             const double tr = e[0] + e[1] + e[2];
             double sg[6], sd[6];
@@ -233,9 +250,9 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             for (int i = 0; i < 6; ++i) {
                 const double nn = sd[i] * is_t;
                 s[i % NSTR] = sg[i] - dgam * 2.0 * G * nn;
-                if (write_state) hist[((size_t)i * ngp + gp) * nloc + el] = ep[i] + dgam * nn;
+                if (write_state) hist[((size_t)i * ngp + gp) * nh + hel] = ep[i] + dgam * nn;
             }
-            if (write_state) hist[((size_t)6 * ngp + gp) * nloc + el] = q_in + SQRT_TWO_THIRDS * dgam;
+            if (write_state) hist[((size_t)6 * ngp + gp) * nh + hel] = q_in + SQRT_TWO_THIRDS * dgam;
             return;
         }
     }

@@ -13,6 +13,7 @@
 // The assembly order is fixed => bitwise reproducible results.  Halo voxels are re-read from shared memory only.
 #include "internal.h"
 #include "materials.cuh"
+#include <cmath>
 
 #define TY 8
 #define TZ 32
@@ -42,7 +43,10 @@ struct SweepParams {
     double vw;               // v_e / n_gp
     int ngp, bbar;
     double *hist, *hist_t;
+    const unsigned *hidx;    // compact history index per element (0xffffffff: none)
+    size_t nh;               // history-bearing elements (stride of the compact history arrays)
     int *pflag;
+    double gm, gp, il[3];    // sum-factorised path: Gauss coordinates 0.5 -/+ sqrt(3)/6 and 1 / element length per axis
     int hstage;              // 1: history of Gauss point g+1 is staged in shared memory (cp.async) while g is evaluated
     int *fault;
     // reductions
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                     for (int c = 0; c < H; ++c) ue[c] = 0.0;
                 }  // SW_STRAINSTRESS keeps the absolute ue (solver.h:507,723)
                 const PhaseDev &pd = p.phases[ph];
+                const size_t he = (pd.has_hist && p.hidx) ? (size_t)p.hidx[e] : 0;
                 double res[ND];
 #pragma unroll
                 for (int i = 0; i < ND; ++i) res[i] = 0.0;
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                 double *hmine = hstg + tid;
                 auto hist_issue = [&](int g, int buf) {
                     double *dst = hmine + (size_t)buf * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
-                    const size_t vs = (size_t)p.ngp * p.nloc, go = (size_t)g * p.nloc + e;   // variable v of Gauss point g: [v * vs + go]
+                    const size_t vs = (size_t)p.ngp * p.nh, go = (size_t)g * p.nh + he;   // variable v of Gauss point g: [v * vs + go]
                     const double *bt = p.hist_t + go, *bc = p.hist + go;
 #pragma unroll
                     for (int v = 0; v < 13; ++v)
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                     }
 #pragma unroll
                     for (int i = 0; i < NSTR; ++i) eps[i] += p.g0[i];
-                    material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.ngp, g, e, wr, p.fault, hs);
+                    material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.nh, p.ngp, g, e, he, wr, p.fault, hs);
                     if (MODE == SW_STRAINSTRESS) {
 #pragma unroll
                         for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
@@ -391,6 +396,337 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sum-factorised sweep for the 8-point elements (HEX8, BBAR), residual and strain/stress modes.
+//
+// The trilinear shape functions are tensor products, so  eps = B ue  and  res = B^T sigma  (include/matmodel.h:190-201) factor per
+// axis: d/dx of the interpolant does not depend on the x coordinate of the Gauss point, etc.  Per element and displacement
+// component the 8 Gauss-point gradients are 3 x 4 distinct values, obtained from nodal differences by two 2-term interpolations
+// (weights N(0.5 -/+ sqrt(3)/6)); the transpose runs the same steps backwards on Gauss-point sums of the stress tensor.  That is
+// ~400 FP64 operations per element for both directions instead of the 1152 FMAs of the dense 48x24 products.
+// The Gauss points are visited in two halves (gz = 0, 1; a real loop, so the law code exists 4 times, not 8); what survives a half
+// is 12 + 12 + 12 doubles (z-derivative values, their stress sums, the first half's nodal x/y forces).
+// Node planes travel global -> shared with cp.async into a 3-slot ring, one plane ahead of the element plane being evaluated.
+// Tiling, halo-element recomputation and the fixed-order nodal assembly are those of k_sweep above.
+// ------------------------------------------------------------------------------------------------
+template <int H, int NSTR, int MODE>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_sf(const SweepParams p)
+{
+    extern __shared__ double smem[];
+    constexpr int ND = 8 * H;
+    constexpr int NR = (MODE == SW_STRAINSTRESS) ? NSTR : 1;
+    double *ring = smem;                   // [3][H][NTILE]
+    double *stg = smem + 3 * H * NTILE;    // [ND][NELT]
+    double *hstg = stg + ND * NELT;        // [2][FANS_HIST_STAGE_SLOTS][SWEEP_THREADS] (only if p.hstage)
+    __shared__ double scratch[32 * NR];
+
+    const int tid = threadIdx.x;
+    const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TY;
+    const int xs = blockIdx.z * p.xchunk;
+    const int xe = min(xs + p.xchunk, p.n0);
+    const bool own = tid < TY * TZ;
+    int ely, elz;
+    bool has_el = true;
+    if (own) {
+        ely = tid / TZ;
+        elz = tid % TZ;
+    } else {
+        const int hh = tid - TY * TZ;
+        if (hh < TZ + 1) {
+            ely = -1;
+            elz = hh - 1;
+        } else if (hh < TZ + 1 + TY) {
+            ely = hh - (TZ + 1);
+            elz = -1;
+        } else {
+            ely = 0;
+            elz = 0;
+            has_el = false;
+        }
+    }
+    const int ey = wrapi(y0 + ely, p.ny), ez = wrapi(z0 + elz, p.nz);
+    const bool own_valid = own && (y0 + ely < p.ny) && (z0 + elz < p.nz);
+    const int eidx = (ely + 1) * (TZ + 1) + (elz + 1);
+    const int n00 = (ely + 1) * (TZ + 2) + (elz + 1);
+
+    double carry[H];
+#pragma unroll
+    for (int c = 0; c < H; ++c) carry[c] = 0.0;
+    double racc[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) racc[i] = 0.0;
+
+    // plane loader: node plane xp (periodic in x / upper slab halo) -> ring slot, asynchronous; one commit group per call
+    auto issue_plane = [&](int xp, int slot) {
+        if (xp <= xe) {
+            const int xg = wrapi(xp, p.n0);
+            const bool hal = p.in_hi && xp >= p.n0;
+            for (int i = tid; i < NTILE; i += SWEEP_THREADS) {
+                const int ry = i / (TZ + 2), rz = i % (TZ + 2);
+                const int y = wrapi(y0 - 1 + ry, p.ny), z = wrapi(z0 - 1 + rz, p.nz);
+                const size_t g = ((size_t)xg * p.ny + y) * p.nz + z;
+#pragma unroll
+                for (int c = 0; c < H; ++c)
+                    cp_async8(&ring[(slot * H + c) * NTILE + i],
+                              hal ? &p.in_hi[(size_t)c * p.ny * p.nz + (size_t)y * p.nz + z] : &p.in[c * p.nloc + g]);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const double wm = p.gm, wp = p.gp;   // N_0(xi = m) = N_1(xi = p) = wp ; N_1(xi = m) = N_0(xi = p) = wm
+    const double ilx = p.il[0], ily = p.il[1], ilz = p.il[2];
+
+    int sa = 0, sb = 1, sc = 2;  // ring slots of node planes x, x+1, x+2
+    issue_plane(xs - 1, sa);
+    issue_plane(xs, sb);
+    for (int x = xs - 1; x < xe; ++x) {
+        issue_plane(x + 2, sc);
+        cp_async_wait_1();       // planes x and x+1 have landed (this thread's copies) ...
+        __syncthreads();         // ... and everybody else's
+        const bool skip_lo = p.in_hi && x < 0;
+        const bool do_el = has_el && !skip_lo && (MODE != SW_STRAINSTRESS || (own_valid && x >= xs));
+        if (skip_lo && has_el && MODE != SW_STRAINSTRESS) {
+#pragma unroll
+            for (int i = 0; i < ND; ++i) stg[i * NELT + eidx] = 0.0;
+        }
+        if (do_el) {
+            const double *rA = ring + (size_t)sa * H * NTILE + n00, *rB = ring + (size_t)sb * H * NTILE + n00;
+            // nodal value of component c at local node (bx, by, bz): plane bx, tile offset by*(TZ+2) + bz  (include/solver.h:333-340)
+#define UN(c, bx, by, bz) (((bx) ? rB : rA)[(c) * NTILE + (by) * (TZ + 2) + (bz)])
+            const int xg = wrapi(x, p.n0);
+            const size_t e = ((size_t)xg * p.ny + ey) * p.nz + ez;
+            const PhaseDev &pd = p.phases[p.phidx[e]];
+            const size_t he = (pd.has_hist && p.hidx) ? (size_t)p.hidx[e] : 0;
+            const bool wr = own_valid && x >= xs;
+
+            // ---- z derivative at (gx, gy), the same for both gz: GZ[c][gx][gy]
+            double GZ[H][2][2];
+#pragma unroll
+            for (int c = 0; c < H; ++c) {
+                const double d00 = UN(c, 0, 0, 1) - UN(c, 0, 0, 0), d01 = UN(c, 0, 1, 1) - UN(c, 0, 1, 0);
+                const double d10 = UN(c, 1, 0, 1) - UN(c, 1, 0, 0), d11 = UN(c, 1, 1, 1) - UN(c, 1, 1, 0);
+                const double e00 = (wp * d00 + wm * d10) * ilz, e01 = (wp * d01 + wm * d11) * ilz;   // gx = 0, by = 0 / 1
+                const double e10 = (wm * d00 + wp * d10) * ilz, e11 = (wm * d01 + wp * d11) * ilz;   // gx = 1
+                GZ[c][0][0] = wp * e00 + wm * e01;
+                GZ[c][0][1] = wm * e00 + wp * e01;
+                GZ[c][1][0] = wp * e10 + wm * e11;
+                GZ[c][1][1] = wm * e10 + wp * e11;
+            }
+            // B-bar: centre value of the volumetric row (include/matmodel.h:113-140), as in k_sweep
+            double mc = 0.0, Qsum = 0.0;
+            if (p.bbar && NSTR > 3) {
+                double t = 0.0;
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int bx = a & 1, by = (a >> 1) & 1, bz = (a >> 2) & 1;
+                    if (NSTR == 6) {
+                        t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
+                        t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN((H > 1 ? 1 : 0), bx, by, bz), t);
+                        t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN((H > 2 ? 2 : 0), bx, by, bz), t);
+                    } else {
+                        t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
+                        t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN(0, bx, by, bz), t);
+                        t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN(0, bx, by, bz), t);
+                    }
+                }
+                mc = t * (1.0 / 3.0);
+            }
+            // history staging (see k_sweep): the values of Gauss point g+1 travel global -> shared while g is evaluated
+            const bool st_j2 = (pd.model == FANS_MAT_J2_LINEAR_ISO || pd.model == FANS_MAT_J2_NONLIN_ISO);
+            const int nT = (p.hstage && NSTR == 6) ? (st_j2 ? 13 : (pd.model == FANS_MAT_J2NEW_LINEAR_ISO ? 7 : 0)) : 0;
+            double *hmine = hstg + tid;
+            auto hist_issue = [&](int g, int buf) {
+                double *dst = hmine + (size_t)buf * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
+                const size_t vs = (size_t)8 * p.nh, go = (size_t)g * p.nh + he;
+                const double *bt = p.hist_t + go, *bc = p.hist + go;
+#pragma unroll
+                for (int v = 0; v < 13; ++v)
+                    if (v < nT) cp_async8(dst + v * SWEEP_THREADS, bt + v * vs);
+                if (st_j2) {
+#pragma unroll
+                    for (int v = 6; v < 13; ++v) cp_async8(dst + (13 + v - 6) * SWEEP_THREADS, bc + v * vs);
+                }
+                cp_async_commit();
+            };
+            if (nT) hist_issue(0, 0);
+
+            double TZs[H][2][2];   // sum over gz of T[c][z] at (gx, gy)
+            double Q0[H][2][2], Q1[H][2][2];   // nodal x/y forces of the two halves before the z interpolation: [c][bx][by]
+            double esum[NSTR], ssum[NSTR];
+#pragma unroll
+            for (int i = 0; i < NSTR; ++i) esum[i] = 0.0, ssum[i] = 0.0;
+#pragma unroll
+            for (int c = 0; c < H; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) TZs[c][i >> 1][i & 1] = 0.0, Q0[c][i >> 1][i & 1] = 0.0, Q1[c][i >> 1][i & 1] = 0.0;
+
+#pragma unroll 1
+            for (int gzi = 0; gzi < 2; ++gzi) {
+                const double wz0 = gzi ? wm : wp, wz1 = gzi ? wp : wm;   // N_0(gz), N_1(gz)
+                double GX[H][2], GY[H][2];   // d/dx at gy, d/dy at gx (this gz)
+#pragma unroll
+                for (int c = 0; c < H; ++c) {
+                    const double a00 = wz0 * UN(c, 0, 0, 0) + wz1 * UN(c, 0, 0, 1), a01 = wz0 * UN(c, 0, 1, 0) + wz1 * UN(c, 0, 1, 1);
+                    const double a10 = wz0 * UN(c, 1, 0, 0) + wz1 * UN(c, 1, 0, 1), a11 = wz0 * UN(c, 1, 1, 0) + wz1 * UN(c, 1, 1, 1);
+                    const double dx0 = (a10 - a00) * ilx, dx1 = (a11 - a01) * ilx;   // by = 0 / 1
+                    const double dy0 = (a01 - a00) * ily, dy1 = (a11 - a10) * ily;   // bx = 0 / 1
+                    GX[c][0] = wp * dx0 + wm * dx1;
+                    GX[c][1] = wm * dx0 + wp * dx1;
+                    GY[c][0] = wp * dy0 + wm * dy1;
+                    GY[c][1] = wm * dy0 + wp * dy1;
+                }
+                double TX[H][2], TY_[H][2];   // sums over gx of T[c][x] at gy ; over gy of T[c][y] at gx
+#pragma unroll
+                for (int c = 0; c < H; ++c) TX[c][0] = TX[c][1] = TY_[c][0] = TY_[c][1] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int gx = k & 1, gy = k >> 1;
+                    const int g = 4 * gzi + k;   // Gauss point number gx + 2 gy + 4 gz (include/matmodel.h:109-111)
+                    HistStage hs{nullptr, SWEEP_THREADS};
+                    if (nT) {
+                        if (g + 1 < 8) {
+                            hist_issue(g + 1, (g + 1) & 1);
+                            cp_async_wait_1();
+                        } else {
+                            cp_async_wait_0();
+                        }
+                        hs.s = hmine + (size_t)(g & 1) * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
+                    }
+                    double Hm[H][3];
+#pragma unroll
+                    for (int c = 0; c < H; ++c) Hm[c][0] = GX[c][gy], Hm[c][1] = GY[c][gx], Hm[c][2] = GZ[c][gx][gy];
+                    double eps[NSTR], sig[NSTR];
+                    strain_from_grad<H, NSTR>(Hm, eps);
+                    if (p.bbar && NSTR > 3) {
+                        const double m = (eps[0] + eps[1] + eps[2]) * (1.0 / 3.0);
+                        eps[0] += mc - m;
+                        eps[1] += mc - m;
+                        eps[2] += mc - m;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NSTR; ++i) eps[i] += p.g0[i];
+                    material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.nh, 8, g, e, he, wr, p.fault, hs);
+                    if (MODE == SW_STRAINSTRESS) {
+#pragma unroll
+                        for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
+                    } else {
+                        if (p.bbar && NSTR > 3) {
+                            const double qv = (sig[0] + sig[1] + sig[2]) * (1.0 / 3.0);
+                            sig[0] -= qv;
+                            sig[1] -= qv;
+                            sig[2] -= qv;
+                            Qsum += qv;
+                        }
+                        double Tm[H][3];
+                        stress_tensor<H, NSTR>(sig, Tm);
+#pragma unroll
+                        for (int c = 0; c < H; ++c) {
+                            TX[c][gy] += Tm[c][0];
+                            TY_[c][gx] += Tm[c][1];
+                            TZs[c][gx][gy] += Tm[c][2];
+                        }
+                    }
+                }
+                if (MODE != SW_STRAINSTRESS) {
+                    // transpose of the x / y interpolations of this half: Q[c][bx][by] = -/+ ilx RX[c][by] -/+ ily RY[c][bx]
+#pragma unroll
+                    for (int c = 0; c < H; ++c) {
+                        const double rx0 = (wp * TX[c][0] + wm * TX[c][1]) * ilx, rx1 = (wm * TX[c][0] + wp * TX[c][1]) * ilx;     // by = 0 / 1
+                        const double ry0 = (wp * TY_[c][0] + wm * TY_[c][1]) * ily, ry1 = (wm * TY_[c][0] + wp * TY_[c][1]) * ily; // bx = 0 / 1
+                        Q0[c][0][0] = Q1[c][0][0], Q0[c][0][1] = Q1[c][0][1], Q0[c][1][0] = Q1[c][1][0], Q0[c][1][1] = Q1[c][1][1];
+                        Q1[c][0][0] = -rx0 - ry0;
+                        Q1[c][0][1] = -rx1 + ry0;
+                        Q1[c][1][0] = rx0 - ry1;
+                        Q1[c][1][1] = rx1 + ry1;
+                    }
+                }
+            }
+            if (MODE == SW_RESIDUAL) {
+                // z part: RZ[c][bx][by] = ilz sum_gx,gy N_bx(gx) N_by(gy) TZs ; node (bx,by,bz): N_bz(gz0) Q0 + N_bz(gz1) Q1 -/+ RZ
+                double res[ND];
+#pragma unroll
+                for (int c = 0; c < H; ++c) {
+                    const double f00 = (wp * TZs[c][0][0] + wm * TZs[c][1][0]) * ilz, f01 = (wp * TZs[c][0][1] + wm * TZs[c][1][1]) * ilz;  // bx = 0, gy = 0 / 1
+                    const double f10 = (wm * TZs[c][0][0] + wp * TZs[c][1][0]) * ilz, f11 = (wm * TZs[c][0][1] + wp * TZs[c][1][1]) * ilz;  // bx = 1
+                    const double rz[2][2] = {{wp * f00 + wm * f01, wm * f00 + wp * f01}, {wp * f10 + wm * f11, wm * f10 + wp * f11}};
+#pragma unroll
+                    for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+                        for (int by = 0; by < 2; ++by) {
+                            res[H * (bx + 2 * by) + c] = wp * Q0[c][bx][by] + wm * Q1[c][bx][by] - rz[bx][by];
+                            res[H * (bx + 2 * by + 4) + c] = wm * Q0[c][bx][by] + wp * Q1[c][bx][by] + rz[bx][by];
+                        }
+                }
+                if (p.bbar && NSTR > 3) {
+                    double sq[NSTR];
+#pragma unroll
+                    for (int i = 0; i < NSTR; ++i) sq[i] = (i < 3) ? Qsum : 0.0;
+                    double Tm[H][3];
+                    stress_tensor<H, NSTR>(sq, Tm);
+                    const double *bc = c_bg + 8 * 24;
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int c = 0; c < H; ++c) {
+                            double s = res[H * a + c];
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) s = fma(bc[j * 8 + a], Tm[c][j], s);
+                            res[H * a + c] = s;
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < ND; ++i) stg[i * NELT + eidx] = res[i] * p.vw;
+            } else if (wr) {  // SW_STRAINSTRESS: element averages of the owned elements
+#pragma unroll
+                for (int i = 0; i < NSTR; ++i) {
+                    const double ev = esum[i] * 0.125, sv = ssum[i] * 0.125;
+                    if (p.eps_out) p.eps_out[i * p.nloc + e] = ev;
+                    if (p.sig_out) p.sig_out[i * p.nloc + e] = sv;
+                    racc[i] += sv;
+                }
+            }
+#undef UN
+        }
+        __syncthreads();
+        if (MODE != SW_STRAINSTRESS) {
+            if (own) {
+                double outv[H], nxt[H];
+#pragma unroll
+                for (int c = 0; c < H; ++c) outv[c] = carry[c], nxt[c] = 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int by = b & 1, bz = b >> 1;
+                    const int ee = eidx - by * (TZ + 1) - bz;
+                    const int i0 = 2 * by + 4 * bz;
+#pragma unroll
+                    for (int c = 0; c < H; ++c) {
+                        outv[c] += stg[(H * i0 + c) * NELT + ee];
+                        nxt[c] += stg[(H * (i0 + 1) + c) * NELT + ee];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < H; ++c) carry[c] = nxt[c];
+                if (own_valid && x >= xs) {
+                    const size_t g = ((size_t)x * p.ny + ey) * p.nz + ez;
+#pragma unroll
+                    for (int c = 0; c < H; ++c) p.out[c * p.nloc + g] = outv[c];
+                }
+            }
+        }
+        const int t = sa;
+        sa = sb, sb = sc, sc = t;
+    }
+    cp_async_wait_0();
+    if (MODE != SW_STRAINSTRESS && p.out_hi && xe == p.n0 && own_valid) {
+#pragma unroll
+        for (int c = 0; c < H; ++c) p.out_hi[(size_t)c * p.ny * p.nz + (size_t)ey * p.nz + ez] = carry[c];
+    }
+    if (p.red_out) {
+        if constexpr (MODE == SW_STRAINSTRESS) grid_reduce<NSTR, NSTR>(racc, scratch, p.part, p.ticket, p.red_out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static uint64_t g_const_stamp = 0;  // which ctx content currently sits in c_bg / c_K
@@ -410,9 +746,19 @@ static int upload_constants(fans_ctx *ctx)
 }
 
 template <int H, int NSTR, int MODE>
-static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t smem)
+static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t smem, bool sf)
 {
     prof_begin(ctx, MODE == SW_LINEAR ? PC_SWEEP_LINEAR : (MODE == SW_RESIDUAL ? PC_SWEEP_RESIDUAL : PC_SWEEP_STRAINSTRESS));
+    if constexpr (MODE != SW_LINEAR) {
+        if (sf) {  // 8-point elements: sum-factorised gradient / divergence
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_sf<H, NSTR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sweep_sf<H, NSTR, MODE><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
+            prof_end(ctx);
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaGetLastError());
+            return FANS_OK;
+        }
+    }
     if (MODE == SW_LINEAR && ctx->k_in_const) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_sweep<H, NSTR, MODE, true><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
@@ -463,9 +809,15 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.vw = ctx->ve / ctx->ngp;
     p.ngp = ctx->ngp;
     p.bbar = (ctx->fe == FANS_FE_BBAR);
+    if (ctx->any_history && mode != SW_LINEAR) FANS_CHECK(history_prepare(ctx));
     p.hist = ctx->hist;
     p.hist_t = ctx->hist_t;
+    p.hidx = ctx->hidx;
+    p.nh = ctx->nh;
     p.pflag = ctx->pflag;
+    p.gm = 0.5 - sqrt(3.0) / 6.0;   // include/matmodel.h:109-111
+    p.gp = 0.5 + sqrt(3.0) / 6.0;
+    for (int d = 0; d < 3; ++d) p.il[d] = 1.0 / ctx->le[d];
     p.fault = ctx->d_flag;
     p.part = ctx->d_part;
     p.ticket = ctx->d_ticket;
@@ -479,13 +831,15 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
     p.hstage = (ctx->any_history && mode != SW_LINEAR && !(getenv("FANS_HIST_STAGE") && atoi(getenv("FANS_HIST_STAGE")) == 0)) ? 1 : 0;
-    const size_t smem = sizeof(double) * (2 * ctx->h * NTILE + 8 * ctx->h * NELT + (p.hstage ? 2 * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS : 0));
+    // the 8-point elements take the sum-factorised kernel (FANS_SWEEP_DENSE=1: the dense B products of k_sweep, for A/B runs)
+    const bool sf = mode != SW_LINEAR && ctx->ngp == 8 && !(getenv("FANS_SWEEP_DENSE") && atoi(getenv("FANS_SWEEP_DENSE")) != 0);
+    const size_t smem = sizeof(double) * ((sf ? 3 : 2) * ctx->h * NTILE + 8 * ctx->h * NELT + (p.hstage ? 2 * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS : 0));
     int rc = FANS_ERR_ARG;
-#define SW_DISPATCH(H_, N_)                                                                       \
-    do {                                                                                          \
-        if (mode == SW_LINEAR) rc = launch_sweep<H_, N_, SW_LINEAR>(ctx, p, grid, smem);          \
-        else if (mode == SW_RESIDUAL) rc = launch_sweep<H_, N_, SW_RESIDUAL>(ctx, p, grid, smem); \
-        else rc = launch_sweep<H_, N_, SW_STRAINSTRESS>(ctx, p, grid, smem);                      \
+#define SW_DISPATCH(H_, N_)                                                                           \
+    do {                                                                                              \
+        if (mode == SW_LINEAR) rc = launch_sweep<H_, N_, SW_LINEAR>(ctx, p, grid, smem, sf);          \
+        else if (mode == SW_RESIDUAL) rc = launch_sweep<H_, N_, SW_RESIDUAL>(ctx, p, grid, smem, sf); \
+        else rc = launch_sweep<H_, N_, SW_STRAINSTRESS>(ctx, p, grid, smem, sf);                      \
     } while (0)
     if (ctx->h == 1 && ctx->nstr == 3) SW_DISPATCH(1, 3);
     else if (ctx->h == 3 && ctx->nstr == 6) SW_DISPATCH(3, 6);

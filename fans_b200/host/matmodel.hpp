@@ -335,41 +335,18 @@ class J2PlasticityNew_LinearIsotropicHardening : public Matmodel {  // J2Plastic
 };
 
 // ---------------- finite strain (LargeStrainMechModel.h) ----------------
-static const int MANDEL_IJ[6][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 1}, {0, 2}, {1, 2}};
-
-// LargeStrainMechModel.h:105-180 verbatim, including the Q >= P-only sum
-static inline Mat compute_spatial_tangent(const double F[3][3], const double S[3][3], const Mat &C_mandel)
+// Reference medium of the finite-strain models: A = dP/dF evaluated by LargeStrainMechModel.h:105-180 at F = I, S = 0 with the
+// isotropic material tangent C = lambda 1x1 + 2 mu I_sym, in closed form.  The reference sums dE_PQ/dF_kL over P <= Q only
+// (LargeStrainMechModel.h:146-147), so a shear pair (k != L) picks up HALF the tensor component C_iJkL = mu:
+//   A(3i+i, 3k+k) = lambda + 2 mu delta_ik ;   A(3i+J, 3i+J) = A(3i+J, 3J+i) = mu / 2   (i != J) ;   everything else 0.
+// This fixes the Green operator and with it the iteration counts, so the halved shear entries are kept on purpose.
+static inline Mat spatial_tangent_at_identity(double lambda, double mu)
 {
     Mat A(9, 9);
-    auto mandel = [](int a, int b) {
-        for (int idx = 0; idx < 6; ++idx)
-            if ((MANDEL_IJ[idx][0] == a && MANDEL_IJ[idx][1] == b) || (MANDEL_IJ[idx][0] == b && MANDEL_IJ[idx][1] == a)) return idx;
-        return -1;
-    };
     for (int i = 0; i < 3; ++i)
-        for (int J = 0; J < 3; ++J) {
-            const int row = 3 * i + J;
-            for (int k = 0; k < 3; ++k)
-                for (int L = 0; L < 3; ++L) {
-                    const int col = 3 * k + L;
-                    if (i == k) A(row, col) += S[L][J];
-                    for (int M = 0; M < 3; ++M) {
-                        const int MJ = mandel(M, J);
-                        if (MJ < 0) continue;
-                        for (int P = 0; P < 3; ++P)
-                            for (int Q = P; Q < 3; ++Q) {
-                                const int PQ = mandel(P, Q);
-                                if (PQ < 0) continue;
-                                double C_val = C_mandel(MJ, PQ);
-                                if (MJ >= 3) C_val /= std::sqrt(2.0);
-                                if (PQ >= 3) C_val /= std::sqrt(2.0);
-                                double dE = 0.0;
-                                if (Q == L) dE += 0.5 * F[k][P];
-                                if (P == L) dE += 0.5 * F[k][Q];
-                                A(row, col) += F[i][M] * C_val * dE;
-                            }
-                    }
-                }
+        for (int k = 0; k < 3; ++k) {
+            A(3 * i + i, 3 * k + k) = lambda + (i == k ? 2.0 * mu : 0.0);
+            if (i != k) A(3 * i + k, 3 * i + k) = A(3 * i + k, 3 * k + i) = 0.5 * mu;
         }
     return A;
 }
@@ -395,16 +372,13 @@ class LargeStrainMechModel : public Matmodel {
     Mat get_reference_stiffness() const override
     {
         Mat kapparef(9, 9);
-        const double I3[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-        const double S0[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
         for (int m = 0; m < n_mat; ++m) {
-            const Mat A = compute_spatial_tangent(I3, S0, material_tangent_at_identity(m));
+            const Mat A = spatial_tangent_at_identity(lambda[m], mu[m]);
             for (int q = 0; q < 81; ++q) kapparef.a[q] += A.a[q];
         }
         for (auto &v : kapparef.a) v /= (double)n_mat;
         return kapparef;
     }
-    virtual Mat material_tangent_at_identity(int m) const { return iso_tangent(lambda[m], mu[m]); }
 };
 
 class SaintVenantKirchhoff : public LargeStrainMechModel {  // SaintVenantKirchhoff.h
@@ -421,21 +395,6 @@ class SaintVenantKirchhoff : public LargeStrainMechModel {  // SaintVenantKirchh
 class CompressibleNeoHookean : public LargeStrainMechModel {  // CompressibleNeoHookean.h
   public:
     using LargeStrainMechModel::LargeStrainMechModel;
-    Mat material_tangent_at_identity(int m) const override  // CompressibleNeoHookean.h:50-92 evaluated at F = I
-    {
-        const double f[6] = {1.0, 1.0, 1.0, std::sqrt(2.0), std::sqrt(2.0), std::sqrt(2.0)};
-        const double Ci[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-        const double cm[6] = {1.0, 1.0, 1.0, 0.0, 0.0, 0.0};
-        Mat C(6, 6);
-        for (int a = 0; a < 6; ++a)
-            for (int b = 0; b < 6; ++b) {
-                const int I = MANDEL_IJ[a][0], J = MANDEL_IJ[a][1], K = MANDEL_IJ[b][0], L = MANDEL_IJ[b][1];
-                const double pp1 = cm[a] * cm[b];
-                const double pp2 = (Ci[I][K] * Ci[J][L] + Ci[I][L] * Ci[J][K]) * f[a] * f[b];
-                C(a, b) = lambda[m] * pp1 + (mu[m] - lambda[m] * 0.0) * pp2;
-            }
-        return C;
-    }
     void fill_desc(int i, fans_phase_desc &d) const override
     {
         d.model = FANS_MAT_NEOHOOKE;

@@ -123,6 +123,38 @@ def j2_fiber_context(ms, Lbox, fe_type="HEX8", device=-1, gdims=None, comm=None)
     return ctx
 
 
+def spatial_tangent_at_identity(lam, mu):
+    """Reference medium of the finite-strain models in closed form: dP/dF of LargeStrainMechModel.h:105-180 at F = I, S = 0 for the
+    isotropic tangent (lam, mu).  The reference sums dE_PQ/dF_kL over P <= Q only, so shear pairs carry mu / 2 (kept on purpose: it
+    fixes the Green operator and the iteration counts).  Same formula as fans_b200/host/matmodel.hpp."""
+    A = np.zeros((9, 9))
+    for i in range(3):
+        for k in range(3):
+            A[3 * i + i, 3 * k + k] = lam + (2.0 * mu if i == k else 0.0)
+            if i != k:
+                A[3 * i + k, 3 * i + k] = A[3 * i + k, 3 * k + i] = 0.5 * mu
+    return A
+
+
+def neohooke_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1, gdims=None, comm=None, model=None):
+    """Config 5: CompressibleNeoHookean (or SaintVenantKirchhoff with model=L.MAT_SVK) on phases 0..len(bulk)-1, one material
+    group; reference stiffness = mean over the group's materials of the spatial tangent at F = I (LargeStrainMechModel.h:66-86)."""
+    bulk = np.asarray(bulk, dtype=np.float64)
+    mu = np.asarray(shear, dtype=np.float64)
+    lam = bulk - (2.0 / 3.0) * mu
+    ctx = L.Context(gdims if gdims is not None else ms.shape, Lbox, 3, 9, fe_type, device, comm)
+    descs = []
+    for i in range(len(bulk)):
+        d = L.PhaseDesc()
+        d.model, d.local_mat, d.group_n_mat = (L.MAT_NEOHOOKE if model is None else model), i, len(bulk)
+        d.params[0], d.params[1] = lam[i], mu[i]
+        descs.append(d)
+    ctx.set_materials(descs)
+    ctx.set_microstructure(ms)
+    ctx.set_reference_stiffness(np.mean([spatial_tangent_at_identity(lam[i], mu[i]) for i in range(len(bulk))], axis=0))
+    return ctx
+
+
 def voronoi_microstructure(dims, n_seeds=None, seed=2024, x0=0, n0=None):
     """Synthetic config-4 image: "polycrystal-like" periodic Voronoi tessellation, phase = grain label mod 2.
     n_seeds defaults to 512 scaled with the volume relative to 1024^3 (grain size ~128 voxels).  Returns the slab [x0, x0 + n0)."""
