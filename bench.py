@@ -5,7 +5,11 @@ Metric (BASELINE.json): voxel-DOF updates/s (and CG iterations/s) of a two-phase
 inclusion) on 512^3 voxels PER GPU, with the fraction of the measured HBM roofline.  A "step" is ONE CG iteration
 (convolution: 5 FFT passes with the fused Green operator; fused direction update + K.d stencil; fused r/u update + norms).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--size n] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size n] [--impl ours|reference] [--workload NAME]
+
+--workload (default elastic512 = the headline, BASELINE.json metric) selects the other BASELINE.json configs, each printed as one JSON
+line of the same shape: config2 (256^3 sphere, 6 unit load cases solved to 1e-10), config3 (J2 plasticity fibre image, load
+increments), config4 (Voronoi "polycrystal-like" image, the headline protocol on it), config5 (Neo-Hooke, mixed BCs, --method cg|fp).
 
 N > 1 (launched by torchrun, one rank per GPU): the grid grows with N (weak scaling, 512^3 voxels per GPU):
 N=2: 1024x512x512, N=4: 1024x1024x512, N=8: 1024^3 (BASELINE config 4's grid), decomposed into x-slabs like the reference.
@@ -79,19 +83,59 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_port_rate(n, iters):
-    """CPU restatement (oracle: NumPy/BLAS + scipy.fft on every host thread) timed on an n^3 sample of the same workload."""
+def host_memory_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return float(ln.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def cpu_port_run(dims, iters, warm=0, threads=0):
+    """The CPU arm: oracle/cpu/fans_cpu.cpp, a multithreaded C++ restatement of the reference's linear solve loop (std::thread over
+    x-slabs, own FFT; the reference itself needs MPI/FFTW/HDF5/Eigen and cannot be built in this image) on the SAME workload: two-phase
+    ellipsoid, LinearElasticIsotropic, HEX8, CG, exactly `iters` iterations (tol = 0).  Returns rate, iterations, loop seconds, threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import fans_oracle as fo
-    ms = fo.sphere_microstructure(n)
-    mats = [{"phases": [0, 1], "matmodel": "LinearElasticIsotropic", "material_properties": {"bulk_modulus": K_BULK, "shear_modulus": G_SHEAR}}]
-    sol = fo.OracleSolver(ms, [1.0, 1.0, 1.0], "mechanical", mats, "HEX8", "cg", "small",
-                          {"measure": "Linfinity", "type": "absolute", "tolerance": 0.0}, iters)
-    sol.set_gradient(G0)
-    t0 = time.perf_counter()
-    sol.solve()
-    dt = time.perf_counter() - t0
-    return 3.0 * n ** 3 * sol.iter / dt, sol.iter, dt
+    import fans_cpu
+    from fans_b200 import simple   # microstructure generator only (NumPy)
+    ms = simple.ellipsoid_microstructure(dims)
+    cpu = fans_cpu.two_phase_elastic(ms, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, threads)
+    if warm:
+        cpu.solve(G0, warm, 0.0)
+        cpu.zero_u()
+    r = cpu.solve(G0, iters, 0.0)
+    nthreads = cpu.threads
+    cpu.close()
+    dof = 3.0 * dims[0] * dims[1] * dims[2]
+    return dof * r["iters"] / r["loop_s"], r["iters"], r["loop_s"], nthreads, r["fft_s"]
+
+
+def cpu_grid(full_dims, budget_s, iters):
+    """largest power-of-two cube <= the workload's grid that the host can hold (about 185 B/voxel) and finish within budget_s, from a
+    measured 64^3 probe of this machine"""
+    probe = [64, 64, 64]
+    rate, _, _, _, _ = cpu_port_run(probe, 2)
+    n = min(full_dims)
+    mem = host_memory_gb()
+    while n > 64 and (185.0 * n ** 3 / 1e9 > 0.5 * mem or 3.0 * n ** 3 * iters / rate > budget_s):
+        n //= 2
+    return [n, n, n] if n < min(full_dims) else list(full_dims)
+
+
+def cpu_baseline_object(args):
+    dims = cpu_grid([args.size] * 3, 20.0, 3) if not args.cpu_size else [args.cpu_size] * 3
+    rate, it, dt, nthreads, fft = cpu_port_run(dims, 3)
+    return {"value": rate, "unit": "voxel-DOF/s", "cores": nthreads, "kind": "port",
+            "sample": "%d CG iterations of the same workload on a %dx%dx%d grid, %.1f s (%.0f %% FFT): multithreaded C++ restatement of the "
+                      "reference loop (oracle/cpu/fans_cpu.cpp, std::thread over x-slabs, own FFT), not the FANS binary"
+                      % (it, dims[0], dims[1], dims[2], dt, 100.0 * fft / dt)}
+
+
+# BASELINE.json `configs` (SURVEY.md 8d gives the concrete inputs); aliases map onto the canonical names
+WORKLOADS = {"elastic512": "elastic512", "config2": "config2", "elastic256x6": "config2", "config3": "config3", "j2_fibre": "config3",
+             "config4": "config4", "voronoi": "config4", "config5": "config5", "neohooke_mixed": "config5"}
 
 
 def workload_name(dims):
@@ -99,19 +143,21 @@ def workload_name(dims):
 
 
 def run_reference(args, dims):
-    n = args.ref_size
-    for _ in range(max(1, args.warmup // 3)):
-        cpu_port_rate(n, 1)
-    rate, it, dt = cpu_port_rate(n, max(args.steps, 1))
-    cores = os.cpu_count()
+    """`--impl reference`: the reference's CPU implementation of the path on every host thread.  The FANS binary cannot exist here
+    (MPI, FFTW, HDF5, Eigen absent), so this is the C++ restatement; a step is one CG iteration of the SAME workload, on the same
+    grid when the host can hold it and finish within a few minutes, else on the largest cube that does (stated in `config`)."""
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    g = [args.ref_size] * 3 if args.ref_size else cpu_grid(dims, 150.0, K + min(W, 3))
+    rate, it, dt, nthreads, fft = cpu_port_run(g, K, warm=min(W, 3))
+    sample = ("%d CG iterations on %dx%dx%d after %d warm-up iterations, %.1f s, %.0f %% of it inside convolution(); multithreaded C++ "
+              "restatement of the reference loop (oracle/cpu/fans_cpu.cpp), not the FANS binary (MPI/FFTW/HDF5/Eigen: unbuildable here)"
+              % (it, g[0], g[1], g[2], min(W, 3), dt, 100.0 * fft / dt))
     line = {"impl": "reference", "metric": "voxel_dof_updates_per_s", "value": rate, "unit": "voxel-DOF/s", "n_gpus": args.gpus,
             "steps": it, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(it, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(dims), "sample": "%d^3 sample of it" % n},
+            "config": {"workload": workload_name(dims), "grid": dims, "cpu_grid": g, "same_grid": list(g) == list(dims)},
             "cg_iterations_per_s": it / dt,
-            "cpu_baseline": {"value": rate, "unit": "voxel-DOF/s", "cores": cores, "kind": "port",
-                             "sample": "%d CG iterations on a %d^3 sample, NumPy/scipy.fft restatement of the reference (oracle/), "
-                                       "not the FANS binary (it needs MPI/FFTW/HDF5/Eigen: unbuildable here)" % (it, n)},
+            "cpu_baseline": {"value": rate, "unit": "voxel-DOF/s", "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "voxel-DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -133,14 +179,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--size", type=int, default=0, help="voxels per axis and GPU (default: the BASELINE size of the workload)")
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--ref-size", type=int, default=96)
-    ap.add_argument("--cpu-size", type=int, default=96)
+    ap.add_argument("--ref-size", type=int, default=0)
+    ap.add_argument("--cpu-size", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--grid", default="", help="nx,ny,nz: override the weak-scaling grid (experiments only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (experiments only)")
+    ap.add_argument("--workload", default="elastic512", choices=sorted(WORKLOADS))
+    ap.add_argument("--method", default="cg", help="config5: cg | fp")
+    ap.add_argument("--load-steps", type=int, default=3, help="config3 / config5: load increments to run")
+    ap.add_argument("--no-selfcheck", action="store_true")
+    ap.add_argument("--no-ncu", action="store_true", help="do not measure roofline.traffic live with ncu")
     args = ap.parse_args()
+    args.workload = WORKLOADS[args.workload]
+    if not args.size:
+        args.size = 256 if args.workload == "config2" else 512
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dims = grid_for(args.size, max(world, args.gpus) if args.impl == "reference" else world)
@@ -151,45 +205,97 @@ def main():
             run_reference(args, dims)
         return
 
-    import numpy as np
     import torch
-    from fans_b200 import simple, dist as fdist
+    from fans_b200 import dist as fdist
 
     comm = fdist.init()
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
-    n, K, W = args.size, args.steps, max(args.warmup, 3)
-    x0, n0 = fdist.slab(dims[0], world, rank)
-    ms = simple.ellipsoid_microstructure(dims, x0, n0)
-    ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", dev, gdims=dims, comm=comm if world > 1 else None)
-    ctx.set_gradient(G0)
+    env = Env(args, rank, world, dev, comm, torch, dims)
+    if args.workload in ("elastic512", "config4"):
+        line = run_linear_headline(env)
+    elif args.workload == "config2":
+        line = run_config2(env)
+    else:
+        line = run_nonlinear(env)
+    if world > 1 and not args.no_selfcheck:
+        sc = selfcheck_slabs(env)
+        if rank == 0:
+            line["selfcheck"] = sc
+    if rank == 0:
+        print(json.dumps(line))
+    comm.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
 
-    def max_over_ranks(v):
-        if world == 1:
+class Env:
+    """per-process state shared by the workloads"""
+
+    def __init__(self, args, rank, world, dev, comm, torch, dims):
+        self.args, self.rank, self.world, self.dev, self.comm, self.torch, self.dims = args, rank, world, dev, comm, torch, dims
+        from fans_b200 import dist as fdist
+        self.x0, self.n0 = fdist.slab(dims[0], world, rank)
+        self.nloc = float(self.n0) * dims[1] * dims[2]
+        self.nvox = float(dims[0]) * dims[1] * dims[2]
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.torch.distributed.barrier()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.torch.distributed.all_reduce(t, op=self.torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    def slab_comm(self):
+        return self.comm if self.world > 1 else None
+
+
+def base_line(env, value, t_loop, K, W, workload, extra_cfg=None):
+    cfg = {"workload": workload, "grid": env.dims, "voxels_per_gpu": env.nloc,
+           "decomposition": "x-slabs, %d plane(s) of %dx%d per GPU" % (env.n0, env.dims[1], env.dims[2]),
+           "l2": "fields (%.2f GB each per GPU) are far larger than the 126 MB L2; no flush needed" % (24.0 * env.nloc / 1e9),
+           "timing": "CUDA events on the library stream around the iteration loop (host polls of the error / line-search scalars "
+                     "included), max over ranks, barrier + synchronize on both sides"}
+    cfg.update(extra_cfg or {})
+    return {"metric": "voxel_dof_updates_per_s", "value": value, "unit": "voxel-DOF/s", "n_gpus": env.world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_loop / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "cg_iterations_per_s": K / t_loop}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# headline (BASELINE.json metric) and config 4: fixed number of linear-elastic CG iterations on the two-phase image
+# ------------------------------------------------------------------------------------------------------------------------------
+def run_linear_headline(env):
+    from fans_b200 import simple
+    args, dims, world, rank, dev = env.args, env.dims, env.world, env.rank, env.dev
+    K, W = args.steps, max(args.warmup, 3)
+    if args.workload == "config4":
+        ms = simple.voronoi_microstructure(dims, x0=env.x0, n0=env.n0)
+        wl = "linear-elastic polycrystal-like Voronoi image (512 seeds per 1024^3, phase = grain mod 2), CG, HEX8, %dx%dx%d" % tuple(dims)
+    else:
+        ms = simple.ellipsoid_microstructure(dims, env.x0, env.n0)
+        wl = workload_name(dims)
+    ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", dev, gdims=dims, comm=env.slab_comm())
+    ctx.set_gradient(G0)
     # warm-up: W iterations of a fresh solve (tol = 0 forces exactly n_it iterations)
     ctx.zero("u")
     ctx.solve("cg", W, 0.0, "Linfinity", "absolute")
     ctx.zero("u")
-    barrier()
+    env.barrier()
     l0 = ctx.launch_count()
     with ClockSampler(dev) as cs:
         res = ctx.solve("cg", K, 0.0, "Linfinity", "absolute")
-        barrier()
+        env.barrier()
     l1 = ctx.launch_count()
     assert res["iters"] == K, res
-    t_loop = max_over_ranks(res["loop_ms"]) * 1e-3   # CUDA events on the library stream around exactly K iterations
-    nvox = float(dims[0]) * dims[1] * dims[2]
-    dof = 3.0 * nvox
+    t_loop = env.max_over_ranks(res["loop_ms"]) * 1e-3   # CUDA events on the library stream around exactly K iterations
+    dof = 3.0 * env.nvox
     value = dof * K / t_loop
 
     # per-kernel device times (separate, untimed run so the event pairs do not perturb the number above)
@@ -198,8 +304,7 @@ def main():
     ctx.solve("cg", max(3, min(K, 5)), 0.0, "Linfinity", "absolute")
     prof = ctx.profile()
     ctx.set_profiling(False)
-    nloc = float(n0) * dims[1] * dims[2]
-    F = 8.0 * 3 * nloc
+    nloc = env.nloc
     alg = {k: v * nloc for k, v in ALG_BYTES_PER_VOXEL.items()}
     # the y passes carry the x<->y transposes over NVLink when world > 1: they are NVLink-bound there (nvlink_roofline below), the
     # HBM roofline object is then quoted for the dominant HBM-bound kernel
@@ -211,24 +316,56 @@ def main():
     achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
     iter_gbs = BYTES_PER_VOXEL_ITER_H3 * nloc * K / t_loop / 1e9   # per GPU
 
-    # e2e: the reference-facing call sequence with HOST buffers (pinned): microstructure + start field in, K iterations,
-    # homogenized stress + displacement field out; all copies inside the timed region, wall clock, max over ranks
     e2e_obj = None
     if args.no_e2e:
         sig = ctx.homogenized_stress()
     else:
-        e2e_obj, sig = e2e_leg(torch, ctx, ms, n0, dims, K, dof, world, barrier, max_over_ranks)
-    finish(args, rank, world, ctx, comm, torch, dims, n0, nloc, K, W, value, t_loop, iter_gbs, peak, which, dom, achieved, dom_ms, prof, cs,
-           e2e_obj, l1 - l0, sig)
+        e2e_obj, sig = e2e_leg(env, ctx, ms, K, dof)
+    sc1 = None
+    if world == 1 and not args.no_selfcheck:
+        sc1 = selfcheck_operator(env, ctx)
+    ctx.close()
+    if rank != 0:
+        return None
+    line = base_line(env, value, t_loop, K, W, wl)
+    traffic, tsrc = dram_traffic(dom, nloc, args)
+    line.update({"hbm_roofline_iteration": {"bytes_per_voxel_iter": BYTES_PER_VOXEL_ITER_H3, "achieved_gbs_per_gpu": iter_gbs, "peak_gbs": peak,
+                                            "frac": iter_gbs / peak, "peak_source": which},
+                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "traffic": traffic, "traffic_source": tsrc, "peak_source": which, "ms_per_launch": dom_ms,
+                              "algorithmic_bytes": ALG_BYTES_PER_VOXEL[dom] * nloc},
+                 "kernel_ms": {k: v[0] / v[1] for k, v in prof.items()},
+                 "clocks": cs.summary(), "e2e": e2e_obj, "gpu_launches": l1 - l0, "homogenized_stress": [float(x) for x in sig]})
+    if sc1 is not None:
+        line["selfcheck_1gpu"] = sc1
+    if world > 1:
+        # bytes each GPU sends (forward push) / receives (inverse pull) per transpose: its spectrum minus the block it keeps
+        kzp = (dims[2] // 2 + 1 + 7) // 8 * 8
+        tb = 16.0 * 3 * env.n0 * dims[1] * kzp * (world - 1) / world
+        km = line["kernel_ms"]
+        t_y = (km["fft_y_fwd"] + km["fft_y_inv"]) * 1e-3
+        line["nvlink_roofline"] = {"bound": "nvlink", "kernels": "fft_y_fwd + fft_y_inv (transposes fused into the y passes, peer stores / loads)",
+                                   "bytes_per_gpu_per_transpose": tb, "achieved": 2.0 * tb / t_y / 1e9, "peak": 770.0, "unit": "GB/s per direction",
+                                   "frac": 2.0 * tb / t_y / 1e9 / 770.0,
+                                   "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md); nominal NVLink 5: 900",
+                                   "ms_both_transposes": 1e3 * t_y,
+                                   "note": "kernel times from the profiling run (passes one after the other); in the timed loop the z passes "
+                                           "of the neighbouring component overlap them (component pipeline)"}
+    if not args.no_cpu and world == 1:
+        line["cpu_baseline"] = cpu_baseline_object(args)
+    return line
 
 
-def e2e_leg(torch, ctx, ms, n0, dims, K, dof, world, barrier, max_over_ranks):
-    u_host = torch.zeros((n0, dims[1], dims[2], 3), dtype=torch.float64, pin_memory=True).numpy()
+def e2e_leg(env, ctx, ms, K, dof):
+    """the reference-facing call sequence with HOST buffers (pinned): microstructure + start field in, K iterations, homogenized
+    stress + displacement field out; all copies inside the timed region, wall clock, max over ranks"""
+    torch, dims, world = env.torch, env.dims, env.world
+    u_host = torch.zeros((env.n0, dims[1], dims[2], 3), dtype=torch.float64, pin_memory=True).numpy()
     ms = torch.from_numpy(ms.view("int16")).pin_memory().numpy().view("uint16")   # every host buffer of the timed region is pinned
     ctx.upload("u", u_host)
     ctx.solve("cg", 1, 0.0, "Linfinity", "absolute")   # untimed: first-touch of the staging buffer
     u_host[...] = 0.0
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     ctx.set_microstructure(ms)               # H2D: phase image
     ctx.set_gradient(G0)
@@ -236,69 +373,251 @@ def e2e_leg(torch, ctx, ms, n0, dims, K, dof, world, barrier, max_over_ranks):
     r2 = ctx.solve("cg", K, 0.0, "Linfinity", "absolute")
     sig = ctx.homogenized_stress()           # D2H: n_str doubles
     ctx.download_into("u", u_host)           # D2H: fluctuation field
-    barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    env.barrier()
+    t_e2e = env.max_over_ranks(time.perf_counter() - t0)
     e2e = dof * r2["iters"] / t_e2e
     return {"value": e2e, "unit": "voxel-DOF/s", "h2d_bytes_per_step": world * (ms.nbytes + u_host.nbytes) / K,
             "d2h_bytes_per_step": world * (u_host.nbytes + sig.nbytes) / K,
             "what": "set_microstructure + upload u + K CG iterations + homogenized stress + download u, pinned host buffers, wall clock"}, sig
 
 
-def dram_traffic(kernel, nloc):
-    """per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of bench.py's workload,
-    committed under profiles/ as bytes per voxel of the capture (512^3); scaled to this run's voxels per GPU"""
+def selfcheck_operator(env, ctx):
+    """Full-size self-consistency of the linear operator on this GPU: K.d of a pseudo-random field through the 27-point stencil
+    kernel against the element-sweep form (FANS_LINEAR_SWEEP=1), and the dense-product sweep against the sum-factorised one for the
+    residual — two independent kernels per operator, compared at the bench size (the oracle parity tests stop at 128^3)."""
+    import numpy as np
+    torch = env.torch
+    n0, ny, nz = env.n0, env.dims[1], env.dims[2]
+    g = torch.Generator(device="cpu").manual_seed(7)
+    host = torch.empty((n0, ny, nz, 3), dtype=torch.float64, pin_memory=True)
+    host.normal_(generator=g)
+    host.mul_(1e-3)
+    ctx.upload("u", host.numpy())
+    out = {}
+    ctx.apply_linear("rnew", "u")
+    a = torch.from_numpy(ctx.download("rnew"))
+    os.environ["FANS_LINEAR_SWEEP"] = "1"
+    ctx.apply_linear("rnew", "u")
+    del os.environ["FANS_LINEAR_SWEEP"]
+    b = torch.from_numpy(ctx.download("rnew"))
+    out["Kd_stencil_vs_sweep_rel"] = float((a - b).abs().max() / b.abs().max())
+    del a, b
+    ctx.residual("r", "u")
+    a = torch.from_numpy(ctx.download("r"))
+    os.environ["FANS_SWEEP_DENSE"] = "1"
+    ctx.residual("r", "u")
+    del os.environ["FANS_SWEEP_DENSE"]
+    b = torch.from_numpy(ctx.download("r"))
+    out["residual_sumfact_vs_dense_rel"] = float((a - b).abs().max() / b.abs().max())
+    out["gate"] = 1e-12
+    out["ok"] = bool(max(out["Kd_stencil_vs_sweep_rel"], out["residual_sumfact_vs_dense_rel"]) < 1e-12)
+    out["grid"] = [n0, ny, nz]
+    ctx.zero("u")
+    return out
+
+
+def selfcheck_slabs(env):
+    """Multi-GPU parity inside the bench run (the driver's GPU test box has one GPU): a 64^3 two-phase sphere solved to 1e-10 on the
+    N-rank slab path (halo exchange, fused NVLink transposes, scalar all-reduces) and, on rank 0 alone, on a single GPU.
+    Gates: homogenized stress 1e-9, displacement field 1e-8 (relative, max norm), CG iterations +-1."""
+    import numpy as np
+    from fans_b200 import simple, dist as fdist
+    torch, world, rank, dev = env.torch, env.world, env.rank, env.dev
+    n = 64
+    dims = [n, n, n]
+    x0, n0 = fdist.slab(n, world, rank)
+    ms_full = simple.sphere_microstructure(n)
+    ctx = simple.linear_elastic_context(ms_full[x0:x0 + n0], [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", dev, gdims=dims, comm=env.comm)
+    ctx.set_gradient(G0)
+    res = ctx.solve("cg", 200, 1e-10, "Linfinity", "absolute")
+    sig = ctx.homogenized_stress()
+    u = torch.from_numpy(ctx.download("u")).cuda()
+    ctx.close()
+    parts = [torch.empty_like(u) for _ in range(world)]
+    torch.distributed.all_gather(parts, u)
+    out = None
+    if rank == 0:
+        u_slabs = torch.cat(parts, 0).cpu().numpy()
+        c1 = simple.linear_elastic_context(ms_full, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", dev)
+        c1.set_gradient(G0)
+        r1 = c1.solve("cg", 200, 1e-10, "Linfinity", "absolute")
+        s1 = c1.homogenized_stress()
+        u1 = c1.download("u")
+        c1.close()
+        out = {"case": "64^3 sphere, linear elastic CG to 1e-10: %d-rank slab path vs one GPU" % world,
+               "sigma_rel_err": float(np.abs(sig - s1).max() / np.abs(s1).max()),
+               "u_rel_err": float(np.abs(u_slabs - u1).max() / np.abs(u1).max()),
+               "iters_diff": int(res["iters"] - r1["iters"]), "iters": int(res["iters"]), "gates": [1e-9, 1e-8, 1]}
+        out["ok"] = bool(out["sigma_rel_err"] < 1e-9 and out["u_rel_err"] < 1e-8 and abs(out["iters_diff"]) <= 1)
+    torch.distributed.barrier()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# config 2: 256^3 sphere, six unit load cases solved to 1e-10 (the homogenized tangent of solver.h:739-778)
+# ------------------------------------------------------------------------------------------------------------------------------
+def run_config2(env):
+    import numpy as np
+    from fans_b200 import simple
+    args, dims, dev = env.args, env.dims, env.dev
+    ms = simple.ellipsoid_microstructure(dims, env.x0, env.n0)   # the sphere of SURVEY 8d config 2 on a cube
+    ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", dev, gdims=dims, comm=env.slab_comm())
+    ctx.set_gradient(G0)
+    ctx.solve("cg", 3, 0.0, "Linfinity", "absolute")   # warm-up
+    torch = env.torch
+    u_host = torch.zeros((env.n0, dims[1], dims[2], 3), dtype=torch.float64, pin_memory=True).numpy()
+    env.barrier()
+    l0 = ctx.launch_count()
+    iters, t_loop, t_solve, C = 0, 0.0, 0.0, np.zeros((6, 6))
+    t0 = time.perf_counter()
+    with ClockSampler(dev) as cs:
+        for i in range(6):   # a new Solver (u = 0) per load case, main.cpp:15-16
+            g = np.zeros(6)
+            g[i] = 1e-3
+            ctx.upload("u", u_host)          # H2D: zero start field
+            ctx.set_gradient(g)
+            r = ctx.solve("cg", 500, 1e-10, "Linfinity", "absolute")
+            C[:, i] = ctx.homogenized_stress() / 1e-3
+            iters += r["iters"]
+            t_loop += r["loop_ms"] * 1e-3
+            t_solve += r["elapsed_ms"] * 1e-3
+        env.barrier()
+    t_wall = env.max_over_ranks(time.perf_counter() - t0)
+    t_loop = env.max_over_ranks(t_loop)
+    l1 = ctx.launch_count()
+    ctx.close()
+    if env.rank != 0:
+        return None
+    dof = 3.0 * env.nvox
+    line = base_line(env, dof * iters / t_loop, t_loop, iters, 3,
+                     "config 2: linear-elastic two-phase sphere %dx%dx%d, CG to Linf 1e-10, 6 unit load cases 1e-3 e_i" % tuple(dims),
+                     {"load_cases": 6})
+    peaks, which = measured_peaks()
+    gbs = BYTES_PER_VOXEL_ITER_H3 * env.nloc * iters / t_loop / 1e9
+    line.update({"hbm_roofline_iteration": {"bytes_per_voxel_iter": BYTES_PER_VOXEL_ITER_H3, "achieved_gbs_per_gpu": gbs,
+                                            "peak_gbs": float(peaks["hbm_gbs"]), "frac": gbs / float(peaks["hbm_gbs"]), "peak_source": which},
+                 "e2e": {"value": dof * iters / t_wall, "unit": "voxel-DOF/s", "h2d_bytes_per_step": env.world * 6.0 * u_host.nbytes / iters,
+                         "d2h_bytes_per_step": 6.0 * 48 / iters, "what": "6 x (upload u, solve, homogenized stress), wall clock"},
+                 "solve_s_total": t_solve, "wall_s_total": t_wall, "clocks": cs.summary(), "gpu_launches": l1 - l0,
+                 "homogenized_tangent": [[float(x) for x in row] for row in 0.5 * (C + C.T)]})
+    return line
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# configs 3 and 5: nonlinear CG (secant line search) / fixed point with history variables or mixed BCs, load increments to 1e-10
+# ------------------------------------------------------------------------------------------------------------------------------
+def run_nonlinear(env):
+    import numpy as np
+    from fans_b200 import simple, mixedbc
+    args, dims, dev = env.args, env.dims, env.dev
+    n = dims[1]
+    steps = args.load_steps
+    sl = slice(env.x0, env.x0 + env.n0)
+    ctrl = None
+    if args.workload == "config3":
+        if dims[0] != dims[1]:
+            raise SystemExit("config3 uses a cubic grid: run it with --grid n,n,n for more than one GPU")
+        ms = simple.fiber_microstructure(n)[sl]
+        ctx = simple.j2_fiber_context(ms, [1.0, 1.0, 1.0], "HEX8", dev, gdims=dims, comm=env.slab_comm())
+        method, n_it = "cg", 500
+        loads = [[1e-3 * (t + 1), 0, 0, 0, 0, 0] for t in range(steps)]   # every 10th increment of the config's 1e-4 ramp
+        wl = ("config 3: J2ViscoPlastic_NonLinearIsotropicHardening matrix (test_J2Plasticity.json parameters) + elastic fibres along z "
+              "(64 discs, vf 0.4), %dx%dx%d, HEX8, CG + secant line search to Linf 1e-10, eps11 = 1e-3 .. %g" % (tuple(dims) + (1e-3 * steps,)))
+        hist_bytes = 1664.0   # SURVEY 8d: 13 doubles read + 13 written per Gauss point, 8 Gauss points
+    else:
+        ms = simple.ellipsoid_microstructure(dims, env.x0, env.n0)
+        ctx = simple.neohooke_context(ms, [1.0, 1.0, 1.0], K_BULK, G_SHEAR, "HEX8", dev, gdims=dims, comm=env.slab_comm())
+        method, n_it = args.method, 2000
+        lam = np.asarray(K_BULK) - 2.0 / 3.0 * np.asarray(G_SHEAR)
+        kref = np.mean([simple.spatial_tangent_at_identity(lam[i], G_SHEAR[i]) for i in range(2)], axis=0)
+        # test_MixedBCs_LargeStrain.json load case 1: F33 ramp with P11 = P22 = 0, all other F components held at the identity
+        mbc = mixedbc.MixedBC([1, 2, 3, 5, 6, 7, 8], [0, 4], [[0, 0, 0, 0, 0, 0, 1.0 + 0.1 * (t + 1)] for t in range(steps)],
+                              [[0.0, 0.0]] * steps, 9)
+        ctrl = mixedbc.MixedBCController(mbc, kref)
+        loads = [None] * steps
+        wl = ("config 5: CompressibleNeoHookean two-phase sphere %dx%dx%d, HEX8, mixed BCs (F33 = 1.1 .. %.1f, P11 = P22 = 0), %s to "
+              "Linf 1e-10" % (tuple(dims) + (1.0 + 0.1 * steps, method)))
+        hist_bytes = 0.0
+    env.barrier()   # no separate warm-up: every load step is a full solve of seconds; the first one carries the one-off costs
+    per_step, iters, evals, t_loop = [], 0, 0, 0.0
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    with ClockSampler(dev) as cs:
+        for t in range(steps):
+            if ctrl is not None:
+                ctrl.activate(ctx, t)
+            else:
+                ctx.set_gradient(loads[t])
+            if t == steps - 1:
+                ctx.set_profiling(True)
+            r = ctx.solve(method, n_it, 1e-10, "Linfinity", "absolute")
+            if t == steps - 1:
+                prof = ctx.profile()
+                ctx.set_profiling(False)
+            sig = ctx.homogenized_stress()
+            ms_loop = env.max_over_ranks(r["loop_ms"])
+            per_step.append({"iters": r["iters"], "residual_evals": r["n_residual_evals"], "loop_ms": ms_loop,
+                             "ms_per_iter": ms_loop / max(r["iters"], 1), "fft_ms": r["fft_ms"], "err_last": r["err_last"],
+                             "stress": [float(x) for x in sig], "gradient": [float(x) for x in ctx.get_gradient()]})
+            iters += r["iters"]
+            evals += r["n_residual_evals"]
+            t_loop += ms_loop * 1e-3
+            ctx.extrapolate_displacement()
+        env.barrier()
+    t_wall = env.max_over_ranks(time.perf_counter() - t0)
+    l1 = ctx.launch_count()
+    ctx.close()
+    if env.rank != 0:
+        return None
+    dof = 3.0 * env.nvox
+    line = base_line(env, dof * iters / t_loop, t_loop, iters, 0, wl, {"load_steps": steps, "method": method})
+    peaks, which = measured_peaks()
+    peak = float(peaks["hbm_gbs"])
+    km = {k: v[0] / v[1] for k, v in prof.items()}
+    # dominant kernel: the residual sweep.  Algorithmic bytes per evaluation: u in + r out (2F) + phase image (2N) + history of
+    # the history-bearing elements (config 3: the J2 matrix, 60 % of the voxels)
+    frac_hist = 0.6 if hist_bytes else 0.0
+    alg = (48.0 + 2.0 + hist_bytes * frac_hist) * env.nloc
+    ach = alg / (km["sweep_residual"] * 1e-3) / 1e9
+    line.update({"roofline": {"bound": "hbm", "kernel": "sweep_residual", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                              "traffic": None, "peak_source": which, "ms_per_launch": km["sweep_residual"], "algorithmic_bytes": alg,
+                              "note": "the sweep is FP64-pipe / latency bound (profiles/r2_ncu_sweep_*.txt), HBM is the stated roofline"},
+                 "residual_evals": evals, "kernel_ms": km, "kernel_calls_last_step": {k: v[1] for k, v in prof.items()},
+                 "load_step_results": per_step, "clocks": cs.summary(), "gpu_launches": l1 - l0,
+                 "e2e": {"value": dof * iters / t_wall, "unit": "voxel-DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8.0 * 9 * steps / max(iters, 1),
+                         "what": "wall clock over all load steps incl. mixed-BC activation, history commit, homogenized stress readback; "
+                                 "fields stay on the device between load steps like Solver::v_u in the reference"}})
+    return line
+
+
+def dram_traffic(kernel, nloc, args):
+    """per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel: measured live with one short ncu
+    pass of tools/kbench.py on the same grid when ncu is on PATH, else the table committed under profiles/ (bytes per voxel of an
+    `ncu --set full` capture of this workload at 512^3), scaled to this run's voxels per GPU"""
+    import shutil
+    kname = {"sweep_linear": "k_stencil_linear", "fft_x_gamma": "k_fft_xg", "cg_update": "k_cg_update", "fft_z_inv": "k_fft_zi",
+             "fft_z_fwd": "k_fft_zf", "fft_y_fwd": "k_fft_y", "fft_y_inv": "k_fft_y"}.get(kernel)
+    if kname and shutil.which("ncu") and not args.no_ncu and args.workload == "elastic512" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        try:
+            cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + kname,
+                   "--launch-skip", "3", "--launch-count", "1", "--csv", sys.executable, os.path.join(ROOT, "tools", "kbench.py"),
+                   "--size", str(args.size), "--steps", "1", "--no-profile"]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+            tot = 0.0
+            for ln in out.splitlines():
+                if "dram__bytes_" in ln:
+                    cells = [c.strip('"') for c in ln.split('","')]
+                    val, unit = float(cells[-1].replace(",", "")), cells[-2].lower()
+                    tot += val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            if tot > 0:
+                return tot, "ncu live (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        except Exception:
+            pass
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_per_voxel.json")))
-        return t["kernels"][kernel] * nloc
+        return t["kernels"][kernel] * nloc, "profiles/dram_traffic_per_voxel.json (ncu --set full capture) x voxels"
     except Exception:
-        return None
-
-
-def finish(args, rank, world, ctx, comm, torch, dims, n0, nloc, K, W, value, t_loop, iter_gbs, peak, which, dom, achieved, dom_ms, prof, cs,
-           e2e_obj, launches, sig):
-    if rank == 0:
-        line = {"metric": "voxel_dof_updates_per_s", "value": value, "unit": "voxel-DOF/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": 1e3 * t_loop / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": workload_name(dims), "grid": dims, "voxels_per_gpu": nloc,
-                           "decomposition": "x-slabs, %d plane(s) of %dx%d per GPU" % (n0, dims[1], dims[2]),
-                           "l2": "fields (3.2 GB each per GPU) are far larger than the 126 MB L2; no flush needed",
-                           "timing": "CUDA events on the library stream around exactly K iterations (one host poll of the error per "
-                                     "iteration included), max over ranks, barrier + synchronize on both sides"},
-                "cg_iterations_per_s": K / t_loop,
-                "hbm_roofline_iteration": {"bytes_per_voxel_iter": BYTES_PER_VOXEL_ITER_H3, "achieved_gbs_per_gpu": iter_gbs, "peak_gbs": peak,
-                                            "frac": iter_gbs / peak, "peak_source": which},
-                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": dram_traffic(dom, nloc), "peak_source": which, "ms_per_launch": dom_ms,
-                             "algorithmic_bytes": ALG_BYTES_PER_VOXEL[dom] * nloc},
-                "kernel_ms": {k: v[0] / v[1] for k, v in prof.items()},
-                "clocks": cs.summary(),
-                "e2e": e2e_obj,
-                "gpu_launches": launches,
-                "homogenized_stress": [float(x) for x in sig]}
-        if world > 1:
-            # bytes each GPU sends (forward push) / receives (inverse pull) per transpose: its spectrum minus the block it keeps
-            kzp = (dims[2] // 2 + 1 + 7) // 8 * 8
-            tb = 16.0 * 3 * n0 * dims[1] * kzp * (world - 1) / world
-            km = line["kernel_ms"]
-            t_y = (km["fft_y_fwd"] + km["fft_y_inv"]) * 1e-3
-            line["nvlink_roofline"] = {"bound": "nvlink", "kernels": "fft_y_fwd + fft_y_inv (transposes fused into the y passes, peer stores / loads)",
-                                       "bytes_per_gpu_per_transpose": tb, "achieved": 2.0 * tb / t_y / 1e9, "peak": 900.0, "unit": "GB/s per direction",
-                                       "frac": 2.0 * tb / t_y / 1e9 / 900.0, "peak_source": "NVLink 5 nominal, per direction per GPU",
-                                       "ms_both_transposes": 1e3 * t_y,
-                                       "note": "kernel times from the profiling run (passes one after the other); in the timed loop the z passes "
-                                               "of the neighbouring component overlap them (component pipeline)"}
-        if not args.no_cpu and world == 1:
-            rate, it, dt = cpu_port_rate(args.cpu_size, 6)
-            line["cpu_baseline"] = {"value": rate, "unit": "voxel-DOF/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "%d CG iterations on a %d^3 sample of the workload, NumPy/scipy.fft restatement (oracle/), %.1f s"
-                                              % (it, args.cpu_size, dt)}
-        print(json.dumps(line))
-    ctx.close()
-    comm.close()
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        return None, None
 
 
 if __name__ == "__main__":

@@ -73,24 +73,27 @@ __device__ __forceinline__ void inv_sym3(const double C[6] /*00,11,22,01,02,12*/
 }
 
 // History values of ONE Gauss point staged ahead of time in thread-private shared-memory slots (sweep.cu issues the cp.async of
-// Gauss point g+1 while g is evaluated): slot v < 13 = committed value of variable v (hist_t), slot 13 + (v - 6) = CURRENT value of
-// variable v in 6..12 (hist; J2Plasticity accumulates psi / psi_bar on every call).  s == nullptr: read global memory directly.
-#define FANS_HIST_STAGE_SLOTS 20
+// Gauss point g+1 while g is evaluated): slot v < 13 = committed value of variable v (hist_t).  s == nullptr: read global memory
+// directly.  The CURRENT values of psi / psi_bar (which J2Plasticity accumulates on every call) are never read: the increment goes
+// out as a fire-and-forget reduction, and only when the Gauss point yields.
+#define FANS_HIST_STAGE_SLOTS 13
 struct HistStage {
     const double *s;
     int stride;
     __device__ __forceinline__ double operator()(int slot) const { return s[slot * stride]; }
 };
 
-// One Gauss point.  e: strain-like input, s: stress-like output.
-template <int NSTR>
+// One Gauss point.  e: strain-like input, s: stress-like output.  LAW >= 0: the model is known at compile time (the caller has
+// dispatched on pd.model once per element, so the Gauss-point loop carries no model branches); LAW = -1: dispatch here.
+#define FANS_LAW_IS(m) ((LAW < 0) ? (pd.model == (m)) : (LAW == (m)))
+template <int NSTR, int LAW = -1>
 __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&e)[NSTR], double (&s)[NSTR], double *hist,
                                              const double *hist_t, int *pflag, size_t nloc, size_t nh, int ngp, int gp, size_t el,
                                              size_t hel, bool write_state, int *fault, const HistStage hs = HistStage{nullptr, 0})
 {
     // nloc / el address the dense per-element arrays (plastic_flag), nh / hel the compact history arrays
     const double *P = pd.params;
-    if (pd.model == FANS_MAT_LINEAR) {
+    if (FANS_LAW_IS(FANS_MAT_LINEAR)) {
         if (pd.lin_iso) {
             if (NSTR == 6) {
                 // LinearElasticIsotropic::get_sigma (LinearElastic.h:43-53): params = lambda, 2 mu
@@ -118,7 +121,7 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
         return;
     }
     if (NSTR == 6) {
-        if (pd.model == FANS_MAT_PSEUDOPLASTIC_LINEAR || pd.model == FANS_MAT_PSEUDOPLASTIC_NONLIN) {
+        if (FANS_LAW_IS(FANS_MAT_PSEUDOPLASTIC_LINEAR) || FANS_LAW_IS(FANS_MAT_PSEUDOPLASTIC_NONLIN)) {
             // PseudoPlastic.h:95-116 (linear hardening), :143-168 (power law)
             const double K = P[0], G = P[1], sy = P[2];
             const double treps = e[0] + e[1] + e[2];
@@ -135,7 +138,7 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             const double buf1 = K * treps;
             double buf2;
             bool elastic;
-            if (pd.model == FANS_MAT_PSEUDOPLASTIC_LINEAR) {
+            if (FANS_LAW_IS(FANS_MAT_PSEUDOPLASTIC_LINEAR)) {
                 const double Hh = P[3], eps_crit = P[4], E_s = P[5];
                 elastic = dn <= eps_crit;
                 buf2 = elastic ? 2.0 * G : (SQRT_TWO_THIRDS * sy + (2.0 / 3.0) * E_s * Hh * (dn - eps_crit)) / dn;
@@ -153,7 +156,7 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             if (write_state && pflag) pflag[(size_t)gp * nloc + el] = elastic ? pd.local_mat : pd.group_n_mat + pd.local_mat;
             return;
         }
-        if (pd.model == FANS_MAT_J2_LINEAR_ISO || pd.model == FANS_MAT_J2_NONLIN_ISO) {
+        if (FANS_LAW_IS(FANS_MAT_J2_LINEAR_ISO) || FANS_LAW_IS(FANS_MAT_J2_NONLIN_ISO)) {
             // J2Plasticity.h:65-108; history: plasticStrain(0..5), psi(6), psi_bar(7..12)
             const double K = P[0], G = P[1], sy = P[2], Kiso = P[3], Hk = P[4], eta = P[5], dt = P[6];
             double ept[6], pbt[6];
@@ -174,7 +177,7 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
 #pragma unroll
             for (int i = 0; i < 6; ++i) dev[i] = st[i] - (i < 3 ? mean : 0.0);
             double q_tr;
-            if (pd.model == FANS_MAT_J2_LINEAR_ISO) q_tr = -Kiso * psit;
+            if (FANS_LAW_IS(FANS_MAT_J2_LINEAR_ISO)) q_tr = -Kiso * psit;
             else q_tr = -Kiso * psit - (P[7] - sy) * (1.0 - exp(-P[8] * psit));
             double dmq[6], n2 = 0.0;
 #pragma unroll
@@ -191,7 +194,7 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
             double gam = 0.0;
             if (!(f_trial < 0)) {
                 const double den = 2 * G + (2.0 / 3.0) * (Kiso + Hk) + eta / dt;
-                if (pd.model == FANS_MAT_J2_LINEAR_ISO) {
+                if (FANS_LAW_IS(FANS_MAT_J2_LINEAR_ISO)) {
                     gam = f_trial / den;
                 } else {
                     // J2Plasticity.h:207-223: Newton loop on the SIGNED increment; "(2 / 3)" is integer 0 => dg = -den
@@ -213,16 +216,19 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
                 double *hb = hist + (size_t)gp * nh + hel;   // variable v of this Gauss point: hb[v * vs]
                 const size_t vs = (size_t)ngp * nh;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    hb[i * vs] = ept[i] + gam * nvec[i];
-                    // quirk (J2Plasticity.h:103-104): psi / psi_bar ACCUMULATE on every call
-                    hb[(7 + i) * vs] = (hs.s ? hs(14 + i) : hb[(7 + i) * vs]) - gam * nvec[i];
+                for (int i = 0; i < 6; ++i) hb[i * vs] = ept[i] + gam * nvec[i];
+                // quirk (J2Plasticity.h:103-104): psi += sqrt(2/3) gamma, psi_bar -= gamma n ACCUMULATE on every call (every residual
+                // evaluation of every iteration).  One thread owns the Gauss point, so a reduction (RED.ADD.F64, no load, nothing to
+                // wait for) is the same single addition; an elastic point (gamma = 0) adds nothing and touches nothing.
+                if (gam != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) atomicAdd(&hb[(7 + i) * vs], -(gam * nvec[i]));
+                    atomicAdd(&hb[6 * vs], gam * SQRT_TWO_THIRDS);
                 }
-                hb[6 * vs] = (hs.s ? hs(13) : hb[6 * vs]) + gam * SQRT_TWO_THIRDS;
             }
             return;
         }
-        if (pd.model == FANS_MAT_J2NEW_LINEAR_ISO) {
+        if (FANS_LAW_IS(FANS_MAT_J2NEW_LINEAR_ISO)) {
             // J2PlasticityNew.h:43-109; history: plasticStrain(0..5), q(6)
             const double K = P[0], G = P[1], sy0 = P[2], Kiso = P[3];
             double ep[6];
@@ -272,7 +278,7 @@ __device__ __forceinline__ void material_law(const PhaseDev &pd, const double (&
         C[4] = F[0][0] * F[0][2] + F[1][0] * F[1][2] + F[2][0] * F[2][2];
         C[5] = F[0][1] * F[0][2] + F[1][1] * F[1][2] + F[2][1] * F[2][2];
         double S[6];
-        if (pd.model == FANS_MAT_SVK) {
+        if (FANS_LAW_IS(FANS_MAT_SVK)) {
             // SaintVenantKirchhoff.h:33-38 : S = lambda tr(E) I + 2 mu E
             const double E0 = 0.5 * (C[0] - 1.0), E1 = 0.5 * (C[1] - 1.0), E2 = 0.5 * (C[2] - 1.0);
             const double ltr = lam * (E0 + E1 + E2);

@@ -14,6 +14,7 @@
 #include "internal.h"
 #include "materials.cuh"
 #include <cmath>
+#include <type_traits>
 
 #define TY 8
 #define TZ 32
@@ -37,6 +38,7 @@ struct SweepParams {
     double *out;             // nodal result
     const uint16_t *phidx;
     const PhaseDev *phases;
+    int n_phases;
     const double *Kglob;     // phase stiffness table in global memory (used when it does not fit __constant__)
     int n_k, k_const;
     double g0[9];
@@ -47,6 +49,7 @@ struct SweepParams {
     size_t nh;               // history-bearing elements (stride of the compact history arrays)
     int *pflag;
     double gm, gp, il[3];    // sum-factorised path: Gauss coordinates 0.5 -/+ sqrt(3)/6 and 1 / element length per axis
+    int stg2;                // k_sweep_sf: staging tile double-buffered (one barrier per plane)
     int hstage;              // 1: history of Gauss point g+1 is staged in shared memory (cp.async) while g is evaluated
     int *fault;
     // reductions
@@ -250,14 +253,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                 auto hist_issue = [&](int g, int buf) {
                     double *dst = hmine + (size_t)buf * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
                     const size_t vs = (size_t)p.ngp * p.nh, go = (size_t)g * p.nh + he;   // variable v of Gauss point g: [v * vs + go]
-                    const double *bt = p.hist_t + go, *bc = p.hist + go;
+                    const double *bt = p.hist_t + go;
 #pragma unroll
                     for (int v = 0; v < 13; ++v)
                         if (v < nT) cp_async8(dst + v * SWEEP_THREADS, bt + v * vs);
-                    if (st_j2) {
-#pragma unroll
-                        for (int v = 6; v < 13; ++v) cp_async8(dst + (13 + v - 6) * SWEEP_THREADS, bc + v * vs);
-                    }
                     cp_async_commit();
                 };
                 if (nT) hist_issue(0, 0);
@@ -408,34 +407,45 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
 // Node planes travel global -> shared with cp.async into a 3-slot ring, one plane ahead of the element plane being evaluated.
 // Tiling, halo-element recomputation and the fixed-order nodal assembly are those of k_sweep above.
 // ------------------------------------------------------------------------------------------------
-template <int H, int NSTR, int MODE>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_sf(const SweepParams p)
+// Tile of the sum-factorised kernel: 10 x 32 owned nodes + 43 halo elements = 363 of 384 threads.  Twelve warps are three per SM
+// sub-partition, i.e. the same 168-register budget as ten, and the 16 KB register file of every sub-partition is used.
+#define FY 10
+#define FZ 32
+#define FNTILE ((FY + 2) * (FZ + 2))
+#define FNELT ((FY + 1) * (FZ + 1))
+#define SF_THREADS 384
+#define SF_NPH 8   // phase descriptors kept in shared memory (more phases: read from global memory)
+
+template <int H, int NSTR, int MODE, bool BBAR>
+__global__ void __launch_bounds__(SF_THREADS, 1) k_sweep_sf(const SweepParams p)
 {
     extern __shared__ double smem[];
     constexpr int ND = 8 * H;
     constexpr int NR = (MODE == SW_STRAINSTRESS) ? NSTR : 1;
-    double *ring = smem;                   // [3][H][NTILE]
-    double *stg = smem + 3 * H * NTILE;    // [ND][NELT]
-    double *hstg = stg + ND * NELT;        // [2][FANS_HIST_STAGE_SLOTS][SWEEP_THREADS] (only if p.hstage)
+    double *ring = smem;                    // [3][H][FNTILE]
+    double *stg0 = smem + 3 * H * FNTILE;   // [nstg][ND][FNELT]: element forces of plane x live in buffer x & (nstg - 1)
+    const int nstg = p.stg2 ? 2 : 1;
+    double *hstg = stg0 + (MODE == SW_STRAINSTRESS ? 0 : nstg * ND * FNELT);   // [2][FANS_HIST_STAGE_SLOTS][SF_THREADS] (only if p.hstage)
     __shared__ double scratch[32 * NR];
+    __shared__ PhaseDev sph[SF_NPH];
 
     const int tid = threadIdx.x;
-    const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TY;
+    const int z0 = blockIdx.x * FZ, y0 = blockIdx.y * FY;
     const int xs = blockIdx.z * p.xchunk;
     const int xe = min(xs + p.xchunk, p.n0);
-    const bool own = tid < TY * TZ;
+    const bool own = tid < FY * FZ;
     int ely, elz;
     bool has_el = true;
     if (own) {
-        ely = tid / TZ;
-        elz = tid % TZ;
+        ely = tid / FZ;
+        elz = tid % FZ;
     } else {
-        const int hh = tid - TY * TZ;
-        if (hh < TZ + 1) {
+        const int hh = tid - FY * FZ;
+        if (hh < FZ + 1) {
             ely = -1;
             elz = hh - 1;
-        } else if (hh < TZ + 1 + TY) {
-            ely = hh - (TZ + 1);
+        } else if (hh < FZ + 1 + FY) {
+            ely = hh - (FZ + 1);
             elz = -1;
         } else {
             ely = 0;
@@ -445,8 +455,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_sf(const SweepParams
     }
     const int ey = wrapi(y0 + ely, p.ny), ez = wrapi(z0 + elz, p.nz);
     const bool own_valid = own && (y0 + ely < p.ny) && (z0 + elz < p.nz);
-    const int eidx = (ely + 1) * (TZ + 1) + (elz + 1);
-    const int n00 = (ely + 1) * (TZ + 2) + (elz + 1);
+    const int eidx = (ely + 1) * (FZ + 1) + (elz + 1);
+    const int n00 = (ely + 1) * (FZ + 2) + (elz + 1);
+    for (int i = tid; i < (int)(sizeof(PhaseDev) / sizeof(double)) * min(p.n_phases, SF_NPH); i += SF_THREADS)
+        reinterpret_cast<double *>(sph)[i] = reinterpret_cast<const double *>(p.phases)[i];
 
     double carry[H];
 #pragma unroll
@@ -460,261 +472,304 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep_sf(const SweepParams
         if (xp <= xe) {
             const int xg = wrapi(xp, p.n0);
             const bool hal = p.in_hi && xp >= p.n0;
-            for (int i = tid; i < NTILE; i += SWEEP_THREADS) {
-                const int ry = i / (TZ + 2), rz = i % (TZ + 2);
+            for (int i = tid; i < FNTILE; i += SF_THREADS) {
+                const int ry = i / (FZ + 2), rz = i % (FZ + 2);
                 const int y = wrapi(y0 - 1 + ry, p.ny), z = wrapi(z0 - 1 + rz, p.nz);
                 const size_t g = ((size_t)xg * p.ny + y) * p.nz + z;
 #pragma unroll
                 for (int c = 0; c < H; ++c)
-                    cp_async8(&ring[(slot * H + c) * NTILE + i],
+                    cp_async8(&ring[(slot * H + c) * FNTILE + i],
                               hal ? &p.in_hi[(size_t)c * p.ny * p.nz + (size_t)y * p.nz + z] : &p.in[c * p.nloc + g]);
             }
         }
         cp_async_commit();
     };
 
-    const double wm = p.gm, wp = p.gp;   // N_0(xi = m) = N_1(xi = p) = wp ; N_1(xi = m) = N_0(xi = p) = wm
-    const double ilx = p.il[0], ily = p.il[1], ilz = p.il[2];
+    // interpolation weights at the Gauss coordinates 0.5 -/+ sqrt(3)/6: N_0(m) = N_1(p) = wp, N_1(m) = N_0(p) = wm; the derivative
+    // factors 1 / l_e are folded into a second copy of the weights
+    const double wm = p.gm, wp = p.gp;
+    const double wmx = wm * p.il[0], wpx = wp * p.il[0], wmy = wm * p.il[1], wpy = wp * p.il[1], wmz = wm * p.il[2], wpz = wp * p.il[2];
+    // transposed direction: the quadrature weight v_e / n_gp (matmodel.h:199) rides on the same factors
+    const double vmx = wmx * p.vw, vpx = wpx * p.vw, vmy = wmy * p.vw, vpy = wpy * p.vw, vmz = wmz * p.vw, vpz = wpz * p.vw;
 
+    // nodal assembly of element plane xq (forces staged in buffer `stq`): node (ly,lz) is local node (bx,by,bz) of element
+    // (ly-by, lz-bz) of plane xq (bx = 0) / xq-1 (bx = 1, carried in registers from the previous call); fixed order
+    auto assemble = [&](int xq, const double *stq) {
+        if (!own) return;
+        double outv[H], nxt[H];
+#pragma unroll
+        for (int c = 0; c < H; ++c) outv[c] = carry[c], nxt[c] = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int by = b & 1, bz = b >> 1;
+            const int ee = eidx - by * (FZ + 1) - bz;
+            const int i0 = 2 * by + 4 * bz;
+#pragma unroll
+            for (int c = 0; c < H; ++c) {
+                outv[c] += stq[(H * i0 + c) * FNELT + ee];
+                nxt[c] += stq[(H * (i0 + 1) + c) * FNELT + ee];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < H; ++c) carry[c] = nxt[c];
+        if (own_valid && xq >= xs) {
+            const size_t g = ((size_t)xq * p.ny + ey) * p.nz + ez;
+#pragma unroll
+            for (int c = 0; c < H; ++c) p.out[c * p.nloc + g] = outv[c];
+        }
+    };
+
+    // One barrier per element plane when the staging tile is double-buffered (p.stg2): the barrier that publishes node plane x+1
+    // also publishes the element forces of plane x-1, whose assembly is deferred to the start of iteration x.
     int sa = 0, sb = 1, sc = 2;  // ring slots of node planes x, x+1, x+2
     issue_plane(xs - 1, sa);
     issue_plane(xs, sb);
     for (int x = xs - 1; x < xe; ++x) {
+        cp_async_wait_0();       // plane x+1 has landed (this thread's copies) ...
+        __syncthreads();         // ... and everybody else's; everybody has left element plane x-1: its forces are complete and
+                                 // the ring slot of node plane x-1 (sc) is free
         issue_plane(x + 2, sc);
-        cp_async_wait_1();       // planes x and x+1 have landed (this thread's copies) ...
-        __syncthreads();         // ... and everybody else's
+        double *stg = stg0 + (size_t)((x - (xs - 1)) & (nstg - 1)) * ND * FNELT;
+        if (MODE != SW_STRAINSTRESS && p.stg2 && x > xs - 1) assemble(x - 1, stg0 + (size_t)((x - 1 - (xs - 1)) & 1) * ND * FNELT);
         const bool skip_lo = p.in_hi && x < 0;
         const bool do_el = has_el && !skip_lo && (MODE != SW_STRAINSTRESS || (own_valid && x >= xs));
         if (skip_lo && has_el && MODE != SW_STRAINSTRESS) {
 #pragma unroll
-            for (int i = 0; i < ND; ++i) stg[i * NELT + eidx] = 0.0;
+            for (int i = 0; i < ND; ++i) stg[i * FNELT + eidx] = 0.0;
         }
         if (do_el) {
-            const double *rA = ring + (size_t)sa * H * NTILE + n00, *rB = ring + (size_t)sb * H * NTILE + n00;
-            // nodal value of component c at local node (bx, by, bz): plane bx, tile offset by*(TZ+2) + bz  (include/solver.h:333-340)
-#define UN(c, bx, by, bz) (((bx) ? rB : rA)[(c) * NTILE + (by) * (TZ + 2) + (bz)])
+            const double *rA = ring + (size_t)sa * H * FNTILE + n00, *rB = ring + (size_t)sb * H * FNTILE + n00;
+            // nodal value of component c at local node (bx, by, bz): plane bx, tile offset by*(FZ+2) + bz  (include/solver.h:333-340)
+#define UN(c, bx, by, bz) (((bx) ? rB : rA)[(c) * FNTILE + (by) * (FZ + 2) + (bz)])
             const int xg = wrapi(x, p.n0);
             const size_t e = ((size_t)xg * p.ny + ey) * p.nz + ez;
-            const PhaseDev &pd = p.phases[p.phidx[e]];
+            const int ph = p.phidx[e];
+            const PhaseDev &pd = (ph < SF_NPH) ? sph[ph] : p.phases[ph];
             const size_t he = (pd.has_hist && p.hidx) ? (size_t)p.hidx[e] : 0;
             const bool wr = own_valid && x >= xs;
 
-            // ---- z derivative at (gx, gy), the same for both gz: GZ[c][gx][gy]
-            double GZ[H][2][2];
+            // the whole element for ONE material law known at compile time: no model branch inside the Gauss-point loop
+            auto element = [&](auto law_tag) {
+                constexpr int LAW = decltype(law_tag)::value;
+                // ---- z derivative at (gx, gy), the same for both gz: GZ[c][gx][gy]
+                double GZ[H][2][2];
 #pragma unroll
-            for (int c = 0; c < H; ++c) {
-                const double d00 = UN(c, 0, 0, 1) - UN(c, 0, 0, 0), d01 = UN(c, 0, 1, 1) - UN(c, 0, 1, 0);
-                const double d10 = UN(c, 1, 0, 1) - UN(c, 1, 0, 0), d11 = UN(c, 1, 1, 1) - UN(c, 1, 1, 0);
-                const double e00 = (wp * d00 + wm * d10) * ilz, e01 = (wp * d01 + wm * d11) * ilz;   // gx = 0, by = 0 / 1
-                const double e10 = (wm * d00 + wp * d10) * ilz, e11 = (wm * d01 + wp * d11) * ilz;   // gx = 1
-                GZ[c][0][0] = wp * e00 + wm * e01;
-                GZ[c][0][1] = wm * e00 + wp * e01;
-                GZ[c][1][0] = wp * e10 + wm * e11;
-                GZ[c][1][1] = wm * e10 + wp * e11;
-            }
-            // B-bar: centre value of the volumetric row (include/matmodel.h:113-140), as in k_sweep
-            double mc = 0.0, Qsum = 0.0;
-            if (p.bbar && NSTR > 3) {
-                double t = 0.0;
+                for (int c = 0; c < H; ++c) {
+                    const double d00 = UN(c, 0, 0, 1) - UN(c, 0, 0, 0), d01 = UN(c, 0, 1, 1) - UN(c, 0, 1, 0);
+                    const double d10 = UN(c, 1, 0, 1) - UN(c, 1, 0, 0), d11 = UN(c, 1, 1, 1) - UN(c, 1, 1, 0);
+                    const double e00 = wpz * d00 + wmz * d10, e01 = wpz * d01 + wmz * d11;   // gx = 0, by = 0 / 1
+                    const double e10 = wmz * d00 + wpz * d10, e11 = wmz * d01 + wpz * d11;   // gx = 1
+                    GZ[c][0][0] = wp * e00 + wm * e01;
+                    GZ[c][0][1] = wm * e00 + wp * e01;
+                    GZ[c][1][0] = wp * e10 + wm * e11;
+                    GZ[c][1][1] = wm * e10 + wp * e11;
+                }
+                // B-bar: centre value of the volumetric row (include/matmodel.h:113-140), as in k_sweep
+                double mc = 0.0, Qsum = 0.0;
+                if (BBAR && NSTR > 3) {
+                    double t = 0.0;
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const int bx = a & 1, by = (a >> 1) & 1, bz = (a >> 2) & 1;
-                    if (NSTR == 6) {
-                        t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
-                        t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN((H > 1 ? 1 : 0), bx, by, bz), t);
-                        t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN((H > 2 ? 2 : 0), bx, by, bz), t);
-                    } else {
-                        t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
-                        t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN(0, bx, by, bz), t);
-                        t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN(0, bx, by, bz), t);
+                    for (int a = 0; a < 8; ++a) {
+                        const int bx = a & 1, by = (a >> 1) & 1, bz = (a >> 2) & 1;
+                        if (NSTR == 6) {
+                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
+                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN((H > 1 ? 1 : 0), bx, by, bz), t);
+                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN((H > 2 ? 2 : 0), bx, by, bz), t);
+                        } else {
+                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
+                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN(0, bx, by, bz), t);
+                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN(0, bx, by, bz), t);
+                        }
                     }
+                    mc = t * (1.0 / 3.0);
                 }
-                mc = t * (1.0 / 3.0);
-            }
-            // history staging (see k_sweep): the values of Gauss point g+1 travel global -> shared while g is evaluated
-            const bool st_j2 = (pd.model == FANS_MAT_J2_LINEAR_ISO || pd.model == FANS_MAT_J2_NONLIN_ISO);
-            const int nT = (p.hstage && NSTR == 6) ? (st_j2 ? 13 : (pd.model == FANS_MAT_J2NEW_LINEAR_ISO ? 7 : 0)) : 0;
-            double *hmine = hstg + tid;
-            auto hist_issue = [&](int g, int buf) {
-                double *dst = hmine + (size_t)buf * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
-                const size_t vs = (size_t)8 * p.nh, go = (size_t)g * p.nh + he;
-                const double *bt = p.hist_t + go, *bc = p.hist + go;
+                // history staging (see k_sweep): the values of Gauss point g+1 travel global -> shared while g is evaluated
+                constexpr bool st_j2 = (LAW == FANS_MAT_J2_LINEAR_ISO || LAW == FANS_MAT_J2_NONLIN_ISO);
+                constexpr int nTc = (NSTR == 6) ? (st_j2 ? 13 : (LAW == FANS_MAT_J2NEW_LINEAR_ISO ? 7 : 0)) : 0;
+                const int nT = p.hstage ? nTc : 0;
+                double *hmine = hstg + tid;
+                auto hist_issue = [&](int g, int buf) {
+                    double *dst = hmine + (size_t)buf * FANS_HIST_STAGE_SLOTS * SF_THREADS;
+                    const size_t vs = (size_t)8 * p.nh, go = (size_t)g * p.nh + he;
+                    const double *bt = p.hist_t + go;
 #pragma unroll
-                for (int v = 0; v < 13; ++v)
-                    if (v < nT) cp_async8(dst + v * SWEEP_THREADS, bt + v * vs);
-                if (st_j2) {
-#pragma unroll
-                    for (int v = 6; v < 13; ++v) cp_async8(dst + (13 + v - 6) * SWEEP_THREADS, bc + v * vs);
-                }
-                cp_async_commit();
-            };
-            if (nT) hist_issue(0, 0);
+                    for (int v = 0; v < nTc; ++v) cp_async8(dst + v * SF_THREADS, bt + v * vs);
+                    cp_async_commit();
+                };
+                if (nT) hist_issue(0, 0);
 
-            double TZs[H][2][2];   // sum over gz of T[c][z] at (gx, gy)
-            double Q0[H][2][2], Q1[H][2][2];   // nodal x/y forces of the two halves before the z interpolation: [c][bx][by]
-            double esum[NSTR], ssum[NSTR];
+                double TZs[H][2][2];   // sum over gz of T[c][z] at (gx, gy)
+                double esum[NSTR], ssum[NSTR];
 #pragma unroll
-            for (int i = 0; i < NSTR; ++i) esum[i] = 0.0, ssum[i] = 0.0;
+                for (int i = 0; i < NSTR; ++i) esum[i] = 0.0, ssum[i] = 0.0;
 #pragma unroll
-            for (int c = 0; c < H; ++c)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) TZs[c][i >> 1][i & 1] = 0.0, Q0[c][i >> 1][i & 1] = 0.0, Q1[c][i >> 1][i & 1] = 0.0;
+                for (int c = 0; c < H; ++c) TZs[c][0][0] = TZs[c][0][1] = TZs[c][1][0] = TZs[c][1][1] = 0.0;
 
 #pragma unroll 1
-            for (int gzi = 0; gzi < 2; ++gzi) {
-                const double wz0 = gzi ? wm : wp, wz1 = gzi ? wp : wm;   // N_0(gz), N_1(gz)
-                double GX[H][2], GY[H][2];   // d/dx at gy, d/dy at gx (this gz)
-#pragma unroll
-                for (int c = 0; c < H; ++c) {
-                    const double a00 = wz0 * UN(c, 0, 0, 0) + wz1 * UN(c, 0, 0, 1), a01 = wz0 * UN(c, 0, 1, 0) + wz1 * UN(c, 0, 1, 1);
-                    const double a10 = wz0 * UN(c, 1, 0, 0) + wz1 * UN(c, 1, 0, 1), a11 = wz0 * UN(c, 1, 1, 0) + wz1 * UN(c, 1, 1, 1);
-                    const double dx0 = (a10 - a00) * ilx, dx1 = (a11 - a01) * ilx;   // by = 0 / 1
-                    const double dy0 = (a01 - a00) * ily, dy1 = (a11 - a10) * ily;   // bx = 0 / 1
-                    GX[c][0] = wp * dx0 + wm * dx1;
-                    GX[c][1] = wm * dx0 + wp * dx1;
-                    GY[c][0] = wp * dy0 + wm * dy1;
-                    GY[c][1] = wm * dy0 + wp * dy1;
-                }
-                double TX[H][2], TY_[H][2];   // sums over gx of T[c][x] at gy ; over gy of T[c][y] at gx
-#pragma unroll
-                for (int c = 0; c < H; ++c) TX[c][0] = TX[c][1] = TY_[c][0] = TY_[c][1] = 0.0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int gx = k & 1, gy = k >> 1;
-                    const int g = 4 * gzi + k;   // Gauss point number gx + 2 gy + 4 gz (include/matmodel.h:109-111)
-                    HistStage hs{nullptr, SWEEP_THREADS};
-                    if (nT) {
-                        if (g + 1 < 8) {
-                            hist_issue(g + 1, (g + 1) & 1);
-                            cp_async_wait_1();
-                        } else {
-                            cp_async_wait_0();
-                        }
-                        hs.s = hmine + (size_t)(g & 1) * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
-                    }
-                    double Hm[H][3];
-#pragma unroll
-                    for (int c = 0; c < H; ++c) Hm[c][0] = GX[c][gy], Hm[c][1] = GY[c][gx], Hm[c][2] = GZ[c][gx][gy];
-                    double eps[NSTR], sig[NSTR];
-                    strain_from_grad<H, NSTR>(Hm, eps);
-                    if (p.bbar && NSTR > 3) {
-                        const double m = (eps[0] + eps[1] + eps[2]) * (1.0 / 3.0);
-                        eps[0] += mc - m;
-                        eps[1] += mc - m;
-                        eps[2] += mc - m;
-                    }
-#pragma unroll
-                    for (int i = 0; i < NSTR; ++i) eps[i] += p.g0[i];
-                    material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.nh, 8, g, e, he, wr, p.fault, hs);
-                    if (MODE == SW_STRAINSTRESS) {
-#pragma unroll
-                        for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
-                    } else {
-                        if (p.bbar && NSTR > 3) {
-                            const double qv = (sig[0] + sig[1] + sig[2]) * (1.0 / 3.0);
-                            sig[0] -= qv;
-                            sig[1] -= qv;
-                            sig[2] -= qv;
-                            Qsum += qv;
-                        }
-                        double Tm[H][3];
-                        stress_tensor<H, NSTR>(sig, Tm);
-#pragma unroll
-                        for (int c = 0; c < H; ++c) {
-                            TX[c][gy] += Tm[c][0];
-                            TY_[c][gx] += Tm[c][1];
-                            TZs[c][gx][gy] += Tm[c][2];
-                        }
-                    }
-                }
-                if (MODE != SW_STRAINSTRESS) {
-                    // transpose of the x / y interpolations of this half: Q[c][bx][by] = -/+ ilx RX[c][by] -/+ ily RY[c][bx]
+                for (int gzi = 0; gzi < 2; ++gzi) {
+                    const double wz0 = gzi ? wm : wp, wz1 = gzi ? wp : wm;   // N_0(gz), N_1(gz)
+                    double GX[H][2], GY[H][2];   // d/dx at gy, d/dy at gx (this gz)
 #pragma unroll
                     for (int c = 0; c < H; ++c) {
-                        const double rx0 = (wp * TX[c][0] + wm * TX[c][1]) * ilx, rx1 = (wm * TX[c][0] + wp * TX[c][1]) * ilx;     // by = 0 / 1
-                        const double ry0 = (wp * TY_[c][0] + wm * TY_[c][1]) * ily, ry1 = (wm * TY_[c][0] + wp * TY_[c][1]) * ily; // bx = 0 / 1
-                        Q0[c][0][0] = Q1[c][0][0], Q0[c][0][1] = Q1[c][0][1], Q0[c][1][0] = Q1[c][1][0], Q0[c][1][1] = Q1[c][1][1];
-                        Q1[c][0][0] = -rx0 - ry0;
-                        Q1[c][0][1] = -rx1 + ry0;
-                        Q1[c][1][0] = rx0 - ry1;
-                        Q1[c][1][1] = rx1 + ry1;
+                        const double a00 = wz0 * UN(c, 0, 0, 0) + wz1 * UN(c, 0, 0, 1), a01 = wz0 * UN(c, 0, 1, 0) + wz1 * UN(c, 0, 1, 1);
+                        const double a10 = wz0 * UN(c, 1, 0, 0) + wz1 * UN(c, 1, 0, 1), a11 = wz0 * UN(c, 1, 1, 0) + wz1 * UN(c, 1, 1, 1);
+                        const double dx0 = a10 - a00, dx1 = a11 - a01;   // by = 0 / 1
+                        const double dy0 = a01 - a00, dy1 = a11 - a10;   // bx = 0 / 1
+                        GX[c][0] = wpx * dx0 + wmx * dx1;
+                        GX[c][1] = wmx * dx0 + wpx * dx1;
+                        GY[c][0] = wpy * dy0 + wmy * dy1;
+                        GY[c][1] = wmy * dy0 + wpy * dy1;
                     }
-                }
-            }
-            if (MODE == SW_RESIDUAL) {
-                // z part: RZ[c][bx][by] = ilz sum_gx,gy N_bx(gx) N_by(gy) TZs ; node (bx,by,bz): N_bz(gz0) Q0 + N_bz(gz1) Q1 -/+ RZ
-                double res[ND];
+                    double TX[H][2], TY_[H][2];   // sums over gx of T[c][x] at gy ; over gy of T[c][y] at gx
 #pragma unroll
-                for (int c = 0; c < H; ++c) {
-                    const double f00 = (wp * TZs[c][0][0] + wm * TZs[c][1][0]) * ilz, f01 = (wp * TZs[c][0][1] + wm * TZs[c][1][1]) * ilz;  // bx = 0, gy = 0 / 1
-                    const double f10 = (wm * TZs[c][0][0] + wp * TZs[c][1][0]) * ilz, f11 = (wm * TZs[c][0][1] + wp * TZs[c][1][1]) * ilz;  // bx = 1
-                    const double rz[2][2] = {{wp * f00 + wm * f01, wm * f00 + wp * f01}, {wp * f10 + wm * f11, wm * f10 + wp * f11}};
+                    for (int c = 0; c < H; ++c) TX[c][0] = TX[c][1] = TY_[c][0] = TY_[c][1] = 0.0;
 #pragma unroll
-                    for (int bx = 0; bx < 2; ++bx)
-#pragma unroll
-                        for (int by = 0; by < 2; ++by) {
-                            res[H * (bx + 2 * by) + c] = wp * Q0[c][bx][by] + wm * Q1[c][bx][by] - rz[bx][by];
-                            res[H * (bx + 2 * by + 4) + c] = wm * Q0[c][bx][by] + wp * Q1[c][bx][by] + rz[bx][by];
+                    for (int k = 0; k < 4; ++k) {
+                        const int gx = k & 1, gy = k >> 1;
+                        const int g = 4 * gzi + k;   // Gauss point number gx + 2 gy + 4 gz (include/matmodel.h:109-111)
+                        HistStage hs{nullptr, SF_THREADS};
+                        if (nT) {
+                            if (g + 1 < 8) {
+                                hist_issue(g + 1, (g + 1) & 1);
+                                cp_async_wait_1();
+                            } else {
+                                cp_async_wait_0();
+                            }
+                            hs.s = hmine + (size_t)(g & 1) * FANS_HIST_STAGE_SLOTS * SF_THREADS;
                         }
-                }
-                if (p.bbar && NSTR > 3) {
-                    double sq[NSTR];
+                        double Hm[H][3];
 #pragma unroll
-                    for (int i = 0; i < NSTR; ++i) sq[i] = (i < 3) ? Qsum : 0.0;
-                    double Tm[H][3];
-                    stress_tensor<H, NSTR>(sq, Tm);
-                    const double *bc = c_bg + 8 * 24;
+                        for (int c = 0; c < H; ++c) Hm[c][0] = GX[c][gy], Hm[c][1] = GY[c][gx], Hm[c][2] = GZ[c][gx][gy];
+                        double eps[NSTR], sig[NSTR];
+                        strain_from_grad<H, NSTR>(Hm, eps);
+                        if (BBAR && NSTR > 3) {
+                            const double m = (eps[0] + eps[1] + eps[2]) * (1.0 / 3.0);
+                            eps[0] += mc - m;
+                            eps[1] += mc - m;
+                            eps[2] += mc - m;
+                        }
 #pragma unroll
-                    for (int a = 0; a < 8; ++a)
+                        for (int i = 0; i < NSTR; ++i) eps[i] += p.g0[i];
+                        material_law<NSTR, LAW>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.nh, 8, g, e, he, wr, p.fault, hs);
+                        if (MODE == SW_STRAINSTRESS) {
+#pragma unroll
+                            for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
+                        } else {
+                            if (BBAR && NSTR > 3) {
+                                const double qv = (sig[0] + sig[1] + sig[2]) * (1.0 / 3.0);
+                                sig[0] -= qv;
+                                sig[1] -= qv;
+                                sig[2] -= qv;
+                                Qsum += qv;
+                            }
+                            double Tm[H][3];
+                            stress_tensor<H, NSTR>(sig, Tm);
+#pragma unroll
+                            for (int c = 0; c < H; ++c) {
+                                TX[c][gy] += Tm[c][0];
+                                TY_[c][gx] += Tm[c][1];
+                                TZs[c][gx][gy] += Tm[c][2];
+                            }
+                        }
+                    }
+                    if (MODE != SW_STRAINSTRESS) {
+                        // transpose of the x / y interpolations of this half: Q[c][bx][by] = -/+ RX[c][by] -/+ RY[c][bx], then the z
+                        // interpolation N_bz(gz) Q to the two node layers.  The first half parks its result in the element's own
+                        // column of the staging tile (thread-private until the barrier), the second half adds to it.
 #pragma unroll
                         for (int c = 0; c < H; ++c) {
-                            double s = res[H * a + c];
+                            const double rx0 = vpx * TX[c][0] + vmx * TX[c][1], rx1 = vmx * TX[c][0] + vpx * TX[c][1];       // by = 0 / 1
+                            const double ry0 = vpy * TY_[c][0] + vmy * TY_[c][1], ry1 = vmy * TY_[c][0] + vpy * TY_[c][1];   // bx = 0 / 1
+                            const double q[2][2] = {{-rx0 - ry0, -rx1 + ry0}, {rx0 - ry1, rx1 + ry1}};
 #pragma unroll
-                            for (int j = 0; j < 3; ++j) s = fma(bc[j * 8 + a], Tm[c][j], s);
-                            res[H * a + c] = s;
+                            for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+                                for (int by = 0; by < 2; ++by) {
+                                    double *s0 = &stg[(H * (bx + 2 * by) + c) * FNELT + eidx], *s1 = &stg[(H * (bx + 2 * by + 4) + c) * FNELT + eidx];
+                                    if (gzi == 0) {
+                                        *s0 = wz0 * q[bx][by];
+                                        *s1 = wz1 * q[bx][by];
+                                    } else {
+                                        *s0 = fma(wz0, q[bx][by], *s0);
+                                        *s1 = fma(wz1, q[bx][by], *s1);
+                                    }
+                                }
                         }
+                    }
                 }
+                if (MODE == SW_RESIDUAL) {
+                    // z part: RZ[c][bx][by] = sum_gx,gy N_bx(gx) N_by(gy) TZs / l_z ; node layer bz = 0 gets -RZ, bz = 1 +RZ
 #pragma unroll
-                for (int i = 0; i < ND; ++i) stg[i * NELT + eidx] = res[i] * p.vw;
-            } else if (wr) {  // SW_STRAINSTRESS: element averages of the owned elements
+                    for (int c = 0; c < H; ++c) {
+                        const double f00 = vpz * TZs[c][0][0] + vmz * TZs[c][1][0], f01 = vpz * TZs[c][0][1] + vmz * TZs[c][1][1];  // bx = 0, gy = 0 / 1
+                        const double f10 = vmz * TZs[c][0][0] + vpz * TZs[c][1][0], f11 = vmz * TZs[c][0][1] + vpz * TZs[c][1][1];  // bx = 1
+                        const double rz[2][2] = {{wp * f00 + wm * f01, wm * f00 + wp * f01}, {wp * f10 + wm * f11, wm * f10 + wp * f11}};
 #pragma unroll
-                for (int i = 0; i < NSTR; ++i) {
-                    const double ev = esum[i] * 0.125, sv = ssum[i] * 0.125;
-                    if (p.eps_out) p.eps_out[i * p.nloc + e] = ev;
-                    if (p.sig_out) p.sig_out[i * p.nloc + e] = sv;
-                    racc[i] += sv;
+                        for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+                            for (int by = 0; by < 2; ++by) {
+                                double *s0 = &stg[(H * (bx + 2 * by) + c) * FNELT + eidx], *s1 = &stg[(H * (bx + 2 * by + 4) + c) * FNELT + eidx];
+                                *s0 -= rz[bx][by];
+                                *s1 += rz[bx][by];
+                            }
+                    }
+                    if (BBAR && NSTR > 3) {
+                        double sq[NSTR];
+#pragma unroll
+                        for (int i = 0; i < NSTR; ++i) sq[i] = (i < 3) ? Qsum : 0.0;
+                        double Tm[H][3];
+                        stress_tensor<H, NSTR>(sq, Tm);
+                        const double *bc = c_bg + 8 * 24;
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+#pragma unroll
+                            for (int c = 0; c < H; ++c) {
+                                double sacc = 0.0;
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) sacc = fma(bc[j * 8 + a], Tm[c][j], sacc);
+                                stg[(H * a + c) * FNELT + eidx] += sacc * p.vw;
+                            }
+                    }
+                } else if (wr) {  // SW_STRAINSTRESS: element averages of the owned elements
+#pragma unroll
+                    for (int i = 0; i < NSTR; ++i) {
+                        const double ev = esum[i] * 0.125, sv = ssum[i] * 0.125;
+                        if (p.eps_out) p.eps_out[i * p.nloc + e] = ev;
+                        if (p.sig_out) p.sig_out[i * p.nloc + e] = sv;
+                        racc[i] += sv;
+                    }
                 }
+            };
+#ifdef SF_ONLY_LAW
+            if constexpr (NSTR == 6 || NSTR == 9) { element(std::integral_constant<int, SF_ONLY_LAW>{}); } else
+#endif
+            if constexpr (NSTR == 6) {
+                switch (pd.model) {
+                case FANS_MAT_LINEAR: element(std::integral_constant<int, FANS_MAT_LINEAR>{}); break;
+                case FANS_MAT_PSEUDOPLASTIC_LINEAR: element(std::integral_constant<int, FANS_MAT_PSEUDOPLASTIC_LINEAR>{}); break;
+                case FANS_MAT_PSEUDOPLASTIC_NONLIN: element(std::integral_constant<int, FANS_MAT_PSEUDOPLASTIC_NONLIN>{}); break;
+                case FANS_MAT_J2_LINEAR_ISO: element(std::integral_constant<int, FANS_MAT_J2_LINEAR_ISO>{}); break;
+                case FANS_MAT_J2_NONLIN_ISO: element(std::integral_constant<int, FANS_MAT_J2_NONLIN_ISO>{}); break;
+                default: element(std::integral_constant<int, FANS_MAT_J2NEW_LINEAR_ISO>{}); break;
+                }
+            } else if constexpr (NSTR == 9) {
+                if (pd.model == FANS_MAT_SVK) element(std::integral_constant<int, FANS_MAT_SVK>{});
+                else element(std::integral_constant<int, FANS_MAT_NEOHOOKE>{});
+            } else {
+                element(std::integral_constant<int, FANS_MAT_LINEAR>{});
             }
 #undef UN
         }
-        __syncthreads();
-        if (MODE != SW_STRAINSTRESS) {
-            if (own) {
-                double outv[H], nxt[H];
-#pragma unroll
-                for (int c = 0; c < H; ++c) outv[c] = carry[c], nxt[c] = 0.0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int by = b & 1, bz = b >> 1;
-                    const int ee = eidx - by * (TZ + 1) - bz;
-                    const int i0 = 2 * by + 4 * bz;
-#pragma unroll
-                    for (int c = 0; c < H; ++c) {
-                        outv[c] += stg[(H * i0 + c) * NELT + ee];
-                        nxt[c] += stg[(H * (i0 + 1) + c) * NELT + ee];
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < H; ++c) carry[c] = nxt[c];
-                if (own_valid && x >= xs) {
-                    const size_t g = ((size_t)x * p.ny + ey) * p.nz + ez;
-#pragma unroll
-                    for (int c = 0; c < H; ++c) p.out[c * p.nloc + g] = outv[c];
-                }
-            }
+        if (MODE != SW_STRAINSTRESS && !p.stg2) {   // single staging buffer: assemble right away, second barrier per plane
+            __syncthreads();
+            assemble(x, stg);
         }
         const int t = sa;
         sa = sb, sb = sc, sc = t;
+    }
+    if (MODE != SW_STRAINSTRESS && p.stg2) {
+        __syncthreads();
+        assemble(xe - 1, stg0 + (size_t)((xe - 1 - (xs - 1)) & 1) * ND * FNELT);
     }
     cp_async_wait_0();
     if (MODE != SW_STRAINSTRESS && p.out_hi && xe == p.n0 && own_valid) {
@@ -751,8 +806,13 @@ static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t s
     prof_begin(ctx, MODE == SW_LINEAR ? PC_SWEEP_LINEAR : (MODE == SW_RESIDUAL ? PC_SWEEP_RESIDUAL : PC_SWEEP_STRAINSTRESS));
     if constexpr (MODE != SW_LINEAR) {
         if (sf) {  // 8-point elements: sum-factorised gradient / divergence
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_sf<H, NSTR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_sweep_sf<H, NSTR, MODE><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
+            if (p.bbar) {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_sf<H, NSTR, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_sweep_sf<H, NSTR, MODE, true><<<grid, SF_THREADS, smem, ctx->st>>>(p);
+            } else {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_sf<H, NSTR, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_sweep_sf<H, NSTR, MODE, false><<<grid, SF_THREADS, smem, ctx->st>>>(p);
+            }
             prof_end(ctx);
             ctx->launches++;
             CUDA_TRY(ctx, cudaGetLastError());
@@ -802,6 +862,7 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.out = out;
     p.phidx = ctx->phidx;
     p.phases = ctx->d_phase;
+    p.n_phases = ctx->n_phases;
     p.Kglob = ctx->d_K;
     p.n_k = ctx->n_k;
     p.k_const = ctx->k_in_const;
@@ -825,15 +886,21 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.eps_out = eps_out;
     p.sig_out = sig_out;
     // x chunking: enough CTAs to fill 148 SMs a few times over, at most ~6% redundant plane loads
-    const int gy = (ctx->ny + TY - 1) / TY, gz = (ctx->nz + TZ - 1) / TZ;
+    // the 8-point elements take the sum-factorised kernel (FANS_SWEEP_DENSE=1: the dense B products of k_sweep, for A/B runs)
+    const bool sf = mode != SW_LINEAR && ctx->ngp == 8 && !(getenv("FANS_SWEEP_DENSE") && atoi(getenv("FANS_SWEEP_DENSE")) != 0);
+    const int ty = sf ? FY : TY, tz = sf ? FZ : TZ;
+    const int gy = (ctx->ny + ty - 1) / ty, gz = (ctx->nz + tz - 1) / tz;
     int xchunk = ctx->n0;
     while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < 4L * FANS_SMS) xchunk = (xchunk + 1) / 2;
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
     p.hstage = (ctx->any_history && mode != SW_LINEAR && !(getenv("FANS_HIST_STAGE") && atoi(getenv("FANS_HIST_STAGE")) == 0)) ? 1 : 0;
-    // the 8-point elements take the sum-factorised kernel (FANS_SWEEP_DENSE=1: the dense B products of k_sweep, for A/B runs)
-    const bool sf = mode != SW_LINEAR && ctx->ngp == 8 && !(getenv("FANS_SWEEP_DENSE") && atoi(getenv("FANS_SWEEP_DENSE")) != 0);
-    const size_t smem = sizeof(double) * ((sf ? 3 : 2) * ctx->h * NTILE + 8 * ctx->h * NELT + (p.hstage ? 2 * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS : 0));
+    // sum-factorised kernel: double-buffered staging tile (one barrier per plane) whenever it fits beside the history staging
+    const size_t sf_base = sizeof(double) * (3 * ctx->h * FNTILE + (p.hstage ? 2 * FANS_HIST_STAGE_SLOTS * SF_THREADS : 0));
+    const size_t sf_stg = (mode == SW_STRAINSTRESS) ? 0 : sizeof(double) * 8 * ctx->h * FNELT;
+    p.stg2 = (sf && sf_base + 2 * sf_stg <= 200 * 1024 && !(getenv("FANS_SWEEP_STG1") && atoi(getenv("FANS_SWEEP_STG1")))) ? 1 : 0;
+    const size_t smem = sf ? sf_base + (p.stg2 ? 2 : 1) * sf_stg
+                           : sizeof(double) * (2 * ctx->h * NTILE + 8 * ctx->h * NELT + (p.hstage ? 2 * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS : 0));
     int rc = FANS_ERR_ARG;
 #define SW_DISPATCH(H_, N_)                                                                           \
     do {                                                                                              \

@@ -16,6 +16,7 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--tag", default="")
 ap.add_argument("--fe", default="HEX8")
 ap.add_argument("--ms", default="ellipsoid", help="ellipsoid | homogeneous | layers | voronoi")
+ap.add_argument("--no-profile", action="store_true", help="only the timed solve (used under ncu by bench.py)")
 args = ap.parse_args()
 n = args.size
 dims = [n, n, n]
@@ -34,6 +35,10 @@ ctx.solve("cg", 3, 0.0, "Linfinity", "absolute")
 ctx.zero("u")
 res = ctx.solve("cg", args.steps, 0.0, "Linfinity", "absolute")
 loop = res["loop_ms"] / args.steps
+if args.no_profile:
+    print(json.dumps({"tag": args.tag, "ms_per_iter": round(loop, 4)}))
+    ctx.close()
+    sys.exit(0)
 ctx.zero("u")
 ctx.set_profiling(True)
 ctx.solve("cg", args.steps, 0.0, "Linfinity", "absolute")
