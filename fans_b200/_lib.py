@@ -57,7 +57,7 @@ EXPORTS = [
     "fans_set_reference_stiffness", "fans_set_gradient", "fans_get_gradient", "fans_set_mixed_bc", "fans_update_mixed_bc",
     "fans_field_upload", "fans_field_download", "fans_field_zero", "fans_field_copy", "fans_residual", "fans_apply_linear",
     "fans_convolution", "fans_dot", "fans_axpy", "fans_norm", "fans_solve", "fans_homogenized_stress", "fans_commit_history",
-    "fans_extrapolate_displacement", "fans_get_field", "fans_strain_stress", "fans_launch_count", "fans_set_profiling", "fans_get_profile", "fans_comm_unique_id", "fans_comm_create",
+    "fans_extrapolate_displacement", "fans_get_field", "fans_strain_stress", "fans_strain_stress_gp", "fans_launch_count", "fans_set_profiling", "fans_get_profile", "fans_comm_unique_id", "fans_comm_create",
     "fans_comm_destroy",
 ]
 
@@ -107,6 +107,7 @@ def load():
     lib.fans_extrapolate_displacement.argtypes = [P]
     lib.fans_get_field.argtypes = [P, C.c_char_p, C.c_void_p, C.c_size_t]
     lib.fans_strain_stress.argtypes = [P, dp, dp]
+    lib.fans_strain_stress_gp.argtypes = [P, dp, dp, dp, dp]
     lib.fans_set_profiling.argtypes = [P, C.c_int32]
     lib.fans_get_profile.argtypes = [P, C.c_int32, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_int64)]
     lib.fans_comm_unique_id.argtypes = [C.c_void_p]
@@ -299,10 +300,21 @@ class Context:
         self._ck(self.lib.fans_strain_stress(self.ptr, _dptr(e), _dptr(s)))
         return e, s
 
+    def strain_stress_gp(self):
+        """(strain, stress, strain_gp, stress_gp) from ONE sweep: element averages and all Gauss-point values [x][y][z][n_gp][n_str]"""
+        e = np.empty(self.dims + (self.n_str,))
+        s = np.empty(self.dims + (self.n_str,))
+        eg = np.empty(self.dims + (self.n_gp, self.n_str))
+        sg = np.empty(self.dims + (self.n_gp, self.n_str))
+        self._ck(self.lib.fans_strain_stress_gp(self.ptr, _dptr(e), _dptr(s), _dptr(eg), _dptr(sg)))
+        return e, s, eg, sg
+
     def get_field(self, name):
         nx, ny, nz = self.dims
         if name in ("strain", "stress"):
             out = np.empty((nx, ny, nz, self.n_str))
+        elif name in ("strain_gp", "stress_gp"):
+            out = np.empty((nx, ny, nz, self.n_gp, self.n_str))
         elif name == "plastic_flag":
             out = np.empty((nx, ny, nz), dtype=np.float32)
         elif name in ("plastic_strain", "kinematic_hardening_variable"):

@@ -345,8 +345,8 @@ static int create_rest(fans_ctx *ctx)
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_red, 0, sizeof(double) * S_COUNT, ctx->st));
     CUDA_TRY(ctx, cudaMallocHost(&ctx->h_red, sizeof(double) * S_COUNT));
     CUDA_TRY(ctx, cudaMallocHost(&ctx->h_stage, sizeof(double) * 4));
-    CUDA_TRY(ctx, cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), ctx->st));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));   // [0] grid-reduce ticket, [1] scratch word (phase-id maximum)
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket, 0, 2 * sizeof(unsigned int), ctx->st));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_flag, sizeof(int)));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->st));
     FANS_CHECK(ensure_fields(ctx, {FANS_FIELD_U, FANS_FIELD_R, FANS_FIELD_U_PREV}));
@@ -397,19 +397,35 @@ extern "C" void fans_destroy(fans_ctx *ctx)
 // ------------------------------------------------------------------------------------------------
 // problem data
 // ------------------------------------------------------------------------------------------------
+// largest phase id of the image (validated against the material table, MaterialManager.h:232-235), found on the device: the host
+// never walks the 134 M voxels of a 512^3 slab
+__global__ void k_u16_max(const uint16_t *__restrict__ a, size_t n, unsigned int *out)
+{
+    unsigned int m = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = max(m, (unsigned int)a[i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 extern "C" int fans_set_microstructure(fans_ctx *ctx, const uint16_t *ms)
 {
     if (!ctx || !ms) return FANS_ERR_ARG;
     cudaSetDevice(ctx->device);
-    uint16_t mx = 0;
-    for (size_t i = 0; i < ctx->nloc; ++i) mx = std::max(mx, ms[i]);
+    if (!ctx->phidx) CUDA_TRY(ctx, cudaMalloc(&ctx->phidx, sizeof(uint16_t) * ctx->nloc));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->phidx, ms, sizeof(uint16_t) * ctx->nloc, cudaMemcpyHostToDevice, ctx->st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket + 1, 0, sizeof(unsigned int), ctx->st));
+    k_u16_max<<<FANS_SMS * 8, 256, 0, ctx->st>>>(ctx->phidx, ctx->nloc, ctx->d_ticket + 1);
+    ctx->launches++;
+    unsigned int mx32 = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&mx32, ctx->d_ticket + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    const uint16_t mx = (uint16_t)mx32;
     ctx->ms_max = mx;
     if (ctx->materials_ready && (int)mx >= ctx->n_phases) {
+        ctx->ms_ready = false;
         fans_set_error(ctx, FANS_ERR_MATERIAL, "MaterialManager: Phase " + std::to_string(mx) + " not assigned");
         return FANS_ERR_MATERIAL;
     }
-    if (!ctx->phidx) CUDA_TRY(ctx, cudaMalloc(&ctx->phidx, sizeof(uint16_t) * ctx->nloc));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->phidx, ms, sizeof(uint16_t) * ctx->nloc, cudaMemcpyHostToDevice, ctx->st));
     if (ctx->P > 1) {  // phases of element plane -1 (the previous rank's last plane) for the gather-form stencil
         const size_t plane = (size_t)ctx->ny * ctx->nz;
         FANS_CHECK(comm_halo(ctx, nullptr, nullptr, ctx->phidx + (size_t)(ctx->n0 - 1) * plane, ctx->ms_lo, sizeof(uint16_t) * plane));
@@ -871,36 +887,53 @@ extern "C" int fans_extrapolate_displacement(fans_ctx *ctx)
 // ------------------------------------------------------------------------------------------------
 // postprocess data sources
 // ------------------------------------------------------------------------------------------------
-extern "C" int fans_strain_stress(fans_ctx *ctx, double *strain_host, double *stress_host)
+// ONE getStrainStress sweep (Solver::postprocess, solver.h:497-545): element averages [x][y][z][n_str] and / or all Gauss-point values
+// [x][y][z][n_gp][n_str]; any pointer may be NULL.  The material law runs once per Gauss point, history side effects included.
+extern "C" int fans_strain_stress_gp(fans_ctx *ctx, double *strain_host, double *stress_host, double *strain_gp_host, double *stress_gp_host)
 {
     if (!ctx) return FANS_ERR_ARG;
     cudaSetDevice(ctx->device);
     const size_t N = ctx->nloc;
-    const int ns = ctx->nstr;
+    const int ns = ctx->nstr, ngp = ctx->ngp;
     FANS_CHECK(ensure_field(ctx, FANS_FIELD_U));
-    double *de = nullptr, *ds = nullptr;
-    if (strain_host) CUDA_TRY(ctx, cudaMalloc(&de, sizeof(double) * ns * N));
-    if (stress_host && cudaMalloc(&ds, sizeof(double) * ns * N) != cudaSuccess) {
-        cudaFree(de);
-        fans_set_error(ctx, FANS_ERR_CUDA, "fans_strain_stress: out of device memory");
-        return FANS_ERR_CUDA;
-    }
-    int rc = sweep_run(ctx, SWEEP_STRAINSTRESS, ctx->field[FANS_FIELD_U], nullptr, nullptr, nullptr, nullptr, nullptr, de, ds);
+    double *host[4] = {strain_host, stress_host, strain_gp_host, stress_gp_host};
+    double *dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    const size_t cnt[4] = {(size_t)ns * N, (size_t)ns * N, (size_t)ns * ngp * N, (size_t)ns * ngp * N};
+    auto release = [&]() {
+        for (double *d : dev)
+            if (d) cudaFree(d);
+    };
+    for (int k = 0; k < 4; ++k)
+        if (host[k] && cudaMalloc(&dev[k], sizeof(double) * cnt[k]) != cudaSuccess) {
+            release();
+            fans_set_error(ctx, FANS_ERR_CUDA, "fans_strain_stress: out of device memory");
+            return FANS_ERR_CUDA;
+        }
+    int rc = sweep_run(ctx, SWEEP_STRAINSTRESS, ctx->field[FANS_FIELD_U], nullptr, nullptr, nullptr, nullptr, nullptr, dev[0], dev[1], dev[2], dev[3]);
     if (rc == FANS_OK) {
-        std::vector<double> tmp((size_t)ns * N);
-        for (int pass = 0; pass < 2; ++pass) {
-            double *src = pass == 0 ? de : ds, *o = pass == 0 ? strain_host : stress_host;
-            if (!o) continue;
-            cudaMemcpyAsync(tmp.data(), src, sizeof(double) * ns * N, cudaMemcpyDeviceToHost, ctx->st);
+        std::vector<double> tmp;
+        for (int k = 0; k < 4; ++k) {
+            if (!host[k]) continue;
+            tmp.resize(cnt[k]);
+            cudaMemcpyAsync(tmp.data(), dev[k], sizeof(double) * cnt[k], cudaMemcpyDeviceToHost, ctx->st);
             cudaStreamSynchronize(ctx->st);
+            const size_t per = cnt[k] / N;   // device order [n_str][ngp][element] -> host [element][ngp][n_str]
+            const int g_n = (int)(per / ns);
             for (int i = 0; i < ns; ++i)
-                for (size_t v = 0; v < N; ++v) o[v * ns + i] = tmp[i * N + v];
+                for (int g = 0; g < g_n; ++g) {
+                    const double *src = tmp.data() + ((size_t)i * g_n + g) * N;
+                    for (size_t v = 0; v < N; ++v) host[k][(v * g_n + g) * ns + i] = src[v];
+                }
         }
         rc = check_fault(ctx);
     }
-    cudaFree(de);
-    cudaFree(ds);
+    release();
     return rc;
+}
+
+extern "C" int fans_strain_stress(fans_ctx *ctx, double *strain_host, double *stress_host)
+{
+    return fans_strain_stress_gp(ctx, strain_host, stress_host, nullptr, nullptr);
 }
 
 extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t bytes)
@@ -919,6 +952,11 @@ extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t
     if (n == "strain" || n == "stress") {
         if (!need(sizeof(double) * ctx->nstr * N)) return FANS_ERR_ARG;
         return n == "strain" ? fans_strain_stress(ctx, (double *)dst, nullptr) : fans_strain_stress(ctx, nullptr, (double *)dst);
+    }
+    if (n == "strain_gp" || n == "stress_gp") {
+        if (!need(sizeof(double) * ctx->nstr * ctx->ngp * N)) return FANS_ERR_ARG;
+        return n == "strain_gp" ? fans_strain_stress_gp(ctx, nullptr, nullptr, (double *)dst, nullptr)
+                                : fans_strain_stress_gp(ctx, nullptr, nullptr, nullptr, (double *)dst);
     }
     if (n == "plastic_flag") {
         if (!ctx->pflag) {

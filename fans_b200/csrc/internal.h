@@ -32,7 +32,7 @@ int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const in
 enum { SWEEP_LINEAR = 0, SWEEP_RESIDUAL = 1, SWEEP_STRAINSTRESS = 2 };
 uint64_t sweep_new_stamp();
 int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const double *s_in, double *d_new,
-              const double *beta_dev, double *red_out, double *eps_out, double *sig_out);
+              const double *beta_dev, double *red_out, double *eps_out, double *sig_out, double *eps_gp = nullptr, double *sig_gp = nullptr);
 
 // api.cu: (re)builds the compact history index + arrays when microstructure or materials changed since the last build
 int history_prepare(fans_ctx *ctx);

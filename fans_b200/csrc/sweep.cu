@@ -58,6 +58,7 @@ struct SweepParams {
     double *red_out;         // SW_LINEAR: <in_new, out>;  SW_STRAINSTRESS: sum of element stress (n_str values)
     // strain/stress output (optional)
     double *eps_out, *sig_out;   // [n_str][nloc] element averages
+    double *eps_gp, *sig_gp;     // [n_str][ngp][nloc] every Gauss point (strain_gp / stress_gp, solver.h:534-542), optional
     // slab decomposition (world_size > 1), scatter form across the slab boundary like the reference (solver.h:244-269):
     const double *in_hi;         // node plane n0 of the input (= plane 0 of the next rank), [H][ny*nz], final values
     double *out_hi;              // contributions of this rank's last element plane to node plane n0 (sent to the next rank)
@@ -296,7 +297,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                     material_law<NSTR>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.nh, p.ngp, g, e, he, wr, p.fault, hs);
                     if (MODE == SW_STRAINSTRESS) {
 #pragma unroll
-                        for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
+                        for (int i = 0; i < NSTR; ++i) {
+                            esum[i] += eps[i], ssum[i] += sig[i];
+                            if (wr && p.eps_gp) p.eps_gp[((size_t)i * p.ngp + g) * p.nloc + e] = eps[i];
+                            if (wr && p.sig_gp) p.sig_gp[((size_t)i * p.ngp + g) * p.nloc + e] = sig[i];
+                        }
                     } else {
                         if (p.bbar && NSTR > 3) {
                             const double qv = (sig[0] + sig[1] + sig[2]) * (1.0 / 3.0);
@@ -653,7 +658,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_sweep_sf(const SweepParams p)
                         material_law<NSTR, LAW>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.nh, 8, g, e, he, wr, p.fault, hs);
                         if (MODE == SW_STRAINSTRESS) {
 #pragma unroll
-                            for (int i = 0; i < NSTR; ++i) esum[i] += eps[i], ssum[i] += sig[i];
+                            for (int i = 0; i < NSTR; ++i) {
+                                esum[i] += eps[i], ssum[i] += sig[i];
+                                if (wr && p.eps_gp) p.eps_gp[((size_t)i * 8 + g) * p.nloc + e] = eps[i];
+                                if (wr && p.sig_gp) p.sig_gp[((size_t)i * 8 + g) * p.nloc + e] = sig[i];
+                            }
                         } else {
                             if (BBAR && NSTR > 3) {
                                 const double qv = (sig[0] + sig[1] + sig[2]) * (1.0 / 3.0);
@@ -834,7 +843,7 @@ static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t s
 
 // mode: SW_*; in/out device SoA fields. s_in/d_new/beta only for the fused CG direction update.
 int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const double *s_in, double *d_new,
-              const double *beta_dev, double *red_out, double *eps_out, double *sig_out)
+              const double *beta_dev, double *red_out, double *eps_out, double *sig_out, double *eps_gp, double *sig_gp)
 {
     if (!ctx->ms_ready || !ctx->materials_ready) {
         fans_set_error(ctx, FANS_ERR_STATE, "microstructure and materials must be set before an element sweep");
@@ -885,6 +894,8 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.red_out = red_out;
     p.eps_out = eps_out;
     p.sig_out = sig_out;
+    p.eps_gp = eps_gp;
+    p.sig_gp = sig_gp;
     // x chunking: enough CTAs to fill 148 SMs a few times over, at most ~6% redundant plane loads
     // the 8-point elements take the sum-factorised kernel (FANS_SWEEP_DENSE=1: the dense B products of k_sweep, for A/B runs)
     const bool sf = mode != SW_LINEAR && ctx->ngp == 8 && !(getenv("FANS_SWEEP_DENSE") && atoi(getenv("FANS_SWEEP_DENSE")) != 0);

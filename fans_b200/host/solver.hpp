@@ -167,15 +167,32 @@ class Solver {
         auto want = [&](const std::string &n) { return std::find(results.begin(), results.end(), n) != results.end(); };
         const size_t N = (size_t)local_n0 * n_y * n_z;
         push_gradient();
-        std::vector<double> strain(N * n_str), stress(N * n_str);
-        check(fans_get_field(ctx, "strain", strain.data(), strain.size() * sizeof(double)));
-        check(fans_get_field(ctx, "stress", stress.data(), stress.size() * sizeof(double)));
-        // averages (solver.h:540-575)
+        // what was asked for (solver.h:459-481): ONE getStrainStress sweep, and only when something needs it — the sweep calls the
+        // material law, and J2Plasticity's psi / psi_bar accumulate on every call (J2Plasticity.h:103-104)
         const int n_mat = reader.n_mat;
+        const bool need_stress = want("stress"), need_strain = want("strain"), need_stress_gp = want("stress_gp"), need_strain_gp = want("strain_gp");
+        const bool need_global_avg = want("stress_average") || want("strain_average");
+        auto want_phase = [&](const char *base, int m) {   // the reference filters on the full name; the bare key asks for every phase
+            return want(base) || want(std::string(base) + "_phase" + std::to_string(m));
+        };
+        bool need_phase_avg = false;
+        for (int m = 0; m < n_mat; ++m) need_phase_avg = need_phase_avg || want_phase("phase_stress_average", m) || want_phase("phase_strain_average", m);
+        const bool need_compute = need_stress || need_stress_gp || need_strain || need_strain_gp || need_global_avg || need_phase_avg;
+        const size_t n_gp = reader.FE_type == "HEX8R" ? 1 : 8;  // matmodel.h:104-155
+        std::vector<double> strain, stress, strain_gp, stress_gp;
+        if (need_compute) {
+            strain.resize(N * n_str), stress.resize(N * n_str);
+            if (need_strain_gp) strain_gp.resize(N * n_gp * n_str);
+            if (need_stress_gp) stress_gp.resize(N * n_gp * n_str);
+            check(fans_strain_stress_gp(ctx, strain.data(), stress.data(), need_strain_gp ? strain_gp.data() : nullptr,
+                                        need_stress_gp ? stress_gp.data() : nullptr));
+        }
+        warn_unknown_results(results, n_mat);
+        // averages (solver.h:540-575)
         std::vector<double> sa(n_str, 0.0), ea(n_str, 0.0);
         std::vector<std::vector<double>> psa(n_mat, std::vector<double>(n_str, 0.0)), pea(n_mat, std::vector<double>(n_str, 0.0));
         std::vector<long> cnt(n_mat, 0);
-        for (size_t e = 0; e < N; ++e) {
+        for (size_t e = 0; e < (need_compute ? N : 0); ++e) {
             const int ph = reader.ms[e];
             for (int c = 0; c < n_str; ++c) {
                 sa[c] += stress[e * n_str + c];
@@ -239,16 +256,23 @@ class Solver {
         if (want("stress_average")) sink.write("stress_average", load_idx, time_idx, "f64", vdim, sa.data(), false);
         if (want("strain_average")) sink.write("strain_average", load_idx, time_idx, "f64", vdim, ea.data(), false);
         for (int m = 0; m < n_mat; ++m) {
-            if (want("phase_stress_average")) sink.write("phase_stress_average_phase" + std::to_string(m), load_idx, time_idx, "f64", vdim, psa[m].data(), false);
-            if (want("phase_strain_average")) sink.write("phase_strain_average_phase" + std::to_string(m), load_idx, time_idx, "f64", vdim, pea[m].data(), false);
+            if (want_phase("phase_stress_average", m)) sink.write("phase_stress_average_phase" + std::to_string(m), load_idx, time_idx, "f64", vdim, psa[m].data(), false);
+            if (want_phase("phase_strain_average", m)) sink.write("phase_strain_average_phase" + std::to_string(m), load_idx, time_idx, "f64", vdim, pea[m].data(), false);
         }
         if (want("absolute_error")) sink.write("absolute_error", load_idx, time_idx, "f64", {iter + 1}, err_all.data(), false);
         if (want("microstructure")) sink.write("microstructure", load_idx, time_idx, "u16", gd(1), reader.ms.data(), true);
         if (want("displacement_fluctuation")) sink.write("displacement_fluctuation", load_idx, time_idx, "f64", gd(howmany), u.data(), true);
         if (want("displacement")) sink.write("displacement", load_idx, time_idx, "f64", gd(howmany), ut.data(), true);
         if (want("residual")) sink.write("residual", load_idx, time_idx, "f64", gd(howmany), r.data(), true);
-        if (want("strain")) sink.write("strain", load_idx, time_idx, "f64", gd(n_str), strain.data(), true);
-        if (want("stress")) sink.write("stress", load_idx, time_idx, "f64", gd(n_str), stress.data(), true);
+        if (need_strain) sink.write("strain", load_idx, time_idx, "f64", gd(n_str), strain.data(), true);
+        if (need_stress) sink.write("stress", load_idx, time_idx, "f64", gd(n_str), stress.data(), true);
+        {   // every Gauss point, extra dims {n_gp, n_str} (solver.h:677-680)
+            std::vector<size_t> d = g;
+            d.push_back(n_gp);
+            d.push_back((size_t)n_str);
+            if (need_strain_gp) sink.write("strain_gp", load_idx, time_idx, "f64", d, strain_gp.data(), true);
+            if (need_stress_gp) sink.write("stress_gp", load_idx, time_idx, "f64", d, stress_gp.data(), true);
+        }
         // model postprocess (PseudoPlastic.h:55-63, J2Plasticity.h:245-322, J2PlasticityNew.h)
         auto try_field = [&](const char *nm, const char *dt, size_t extra, size_t esz) {
             if (!want(nm)) return;
@@ -284,6 +308,26 @@ class Solver {
     }
 
     std::vector<double> stress_average, strain_average;
+
+    // result names this front end does not produce are reported once instead of being dropped silently
+    void warn_unknown_results(const std::vector<std::string> &results, int n_mat)
+    {
+        if (warned_results || world_rank != 0) return;
+        warned_results = true;
+        static const char *known[] = {"stress", "strain", "stress_gp", "strain_gp", "stress_average", "strain_average", "phase_stress_average",
+                                      "phase_strain_average", "absolute_error", "microstructure", "displacement_fluctuation", "displacement",
+                                      "residual", "mpi_rank", "plastic_flag", "plastic_strain", "isotropic_hardening_variable",
+                                      "kinematic_hardening_variable", "plastic_strain_gp", "isotropic_hardening_variable_gp",
+                                      "kinematic_hardening_variable_gp", "homogenized_tangent"};
+        for (const std::string &r : results) {
+            bool ok = false;
+            for (const char *k : known) ok = ok || r == k;
+            for (int m = 0; m < n_mat && !ok; ++m)
+                ok = r == "phase_stress_average_phase" + std::to_string(m) || r == "phase_strain_average_phase" + std::to_string(m);
+            if (!ok) fprintf(stderr, "# WARNING: result '%s' is not produced by the GPU front end and is skipped\n", r.c_str());
+        }
+    }
+    bool warned_results = false;
 
   protected:
     MixedBC mbc_local;

@@ -171,6 +171,9 @@ int fans_get_field(fans_ctx *ctx, const char *name, void *host_dst, size_t bytes
  * each double [x][y][z][n_str]; either pointer may be NULL.  Like the reference's sweep it calls the material law once per
  * Gauss point, with the same side effects on the history variables (J2Plasticity.h:103-104). */
 int fans_strain_stress(fans_ctx *ctx, double *strain_host, double *stress_host);
+/* The same single sweep with the Gauss-point outputs of Solver::postprocess (solver.h:534-542, 677-680: "strain_gp" / "stress_gp",
+ * double [x][y][z][n_gp][n_str]) next to the element averages; any pointer may be NULL. */
+int fans_strain_stress_gp(fans_ctx *ctx, double *strain_host, double *stress_host, double *strain_gp_host, double *stress_gp_host);
 
 /* per-kernel-class device timing (CUDA events on the library's stream). cls = 0.. until *name is "" */
 int fans_set_profiling(fans_ctx *ctx, int32_t on);  /* resets the accumulators */

@@ -45,7 +45,8 @@ def compare(cfg, ms, check_hist=()):
         res["stress_average"] = ctx.homogenized_stress()
         res["u"] = ctx.download("u")
         res["post"] = {}
-        res["post"]["strain"], res["post"]["stress"] = ctx.strain_stress()  # one sweep, like Solver::postprocess
+        # ONE sweep like Solver::postprocess (solver.h:497-545): element averages and every Gauss point (strain_gp / stress_gp)
+        res["post"]["strain"], res["post"]["stress"], res["post"]["strain_gp"], res["post"]["stress_gp"] = ctx.strain_stress_gp()
         res["post"].update({k: ctx.get_field(k) for k in check_hist})
 
     ro, sol = fo.run_load_cases(ms, cfg, on_step=o_step)
