@@ -58,7 +58,7 @@ EXPORTS = [
     "fans_field_upload", "fans_field_download", "fans_field_zero", "fans_field_copy", "fans_residual", "fans_apply_linear",
     "fans_convolution", "fans_dot", "fans_axpy", "fans_norm", "fans_solve", "fans_homogenized_stress", "fans_commit_history",
     "fans_extrapolate_displacement", "fans_get_field", "fans_strain_stress", "fans_strain_stress_gp", "fans_launch_count", "fans_set_profiling", "fans_get_profile", "fans_comm_unique_id", "fans_comm_create",
-    "fans_comm_destroy",
+    "fans_comm_destroy", "fans_allreduce_sum",
 ]
 
 _lib = None
@@ -113,6 +113,7 @@ def load():
     lib.fans_comm_unique_id.argtypes = [C.c_void_p]
     lib.fans_comm_create.argtypes = [C.POINTER(P), C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
     lib.fans_comm_destroy.argtypes = [P]
+    lib.fans_allreduce_sum.argtypes = [P, dp, C.c_int32]
     lib.fans_launch_count.argtypes = [P]
     lib.fans_launch_count.restype = C.c_int64
     _lib = lib

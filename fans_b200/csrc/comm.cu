@@ -124,6 +124,25 @@ int comm_allreduce(fans_ctx *ctx, const double *in, double *out, int n, bool is_
     return FANS_OK;
 }
 
+// MPI_Allreduce(MPI_IN_PLACE, ..., MPI_SUM) of a small HOST vector over the slabs: the averages of Solver::postprocess
+// (include/solver.h:556-571).  A C++ host without MPI needs nothing but this library to run P ranks.
+extern "C" int fans_allreduce_sum(fans_ctx *ctx, double *host_inout, int32_t n)
+{
+    if (!ctx || !host_inout || n < 0) return FANS_ERR_ARG;
+    if (ctx->P == 1 || n == 0) return FANS_OK;
+    cudaSetDevice(ctx->device);
+    double *d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(double) * n));
+    int rc = FANS_OK;
+    if (cudaMemcpyAsync(d, host_inout, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st) != cudaSuccess) rc = FANS_ERR_CUDA;
+    if (rc == FANS_OK) rc = comm_allreduce(ctx, d, d, n, false);
+    if (rc == FANS_OK && cudaMemcpyAsync(host_inout, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) rc = FANS_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->st) != cudaSuccess) rc = FANS_ERR_CUDA;
+    cudaFree(d);
+    if (rc == FANS_ERR_CUDA) fans_set_error(ctx, rc, "fans_allreduce_sum: CUDA error");
+    return rc;
+}
+
 // ring exchange of one plane in each direction:
 //   to_prev (may be null) is sent to rank-1 and arrives there as from_next;  to_next -> rank+1 arrives as from_prev.
 int comm_halo(fans_ctx *ctx, const void *to_prev, void *from_next, const void *to_next, void *from_prev, size_t bytes)

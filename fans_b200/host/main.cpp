@@ -6,7 +6,13 @@
 // following the reference's HDF5 group layout (include/reader.h:331-351).
 //     FANS_gpu --describe input.json [ms.u16 nx ny nz]   prints what the host derives from the input (no GPU needed).
 //     FANS_gpu <input.json> results.h5 ...                writes the reference's HDF5 results layout instead (h5write.hpp).
+// Several ranks (reference: mpiexec -n P, src/main.cpp:60-61; here one process per GPU, no MPI needed): start P copies with
+// RANK / WORLD_SIZE / LOCAL_RANK in the environment (torchrun's names; OMPI_COMM_WORLD_* and FANS_* are accepted too) and a shared
+// FANS_COMM_FILE path — rank 0 drops the 128-byte NCCL id there, the others pick it up (tools/fans_mprun.py does exactly that).
+// Every rank owns n_x/P x-planes; rank r > 0 writes its field slabs to results_dir/rank<r>/ (results.rank<r>.h5), small data come
+// from rank 0 only.
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstring>
@@ -112,6 +118,68 @@ static int h5_selftest(const char *file)
     return 0;
 }
 
+// ---- slab world: rank / size from the environment, NCCL id through a file (the role MPI_Init + MPI_Bcast play in the reference) ----
+static int env_int(std::initializer_list<const char *> names, int dflt)
+{
+    for (const char *n : names)
+        if (const char *v = getenv(n)) return atoi(v);
+    return dflt;
+}
+
+static void slab_world(Reader &reader)
+{
+    reader.world_size = env_int({"FANS_WORLD_SIZE", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE"}, 1);
+    reader.world_rank = env_int({"FANS_RANK", "RANK", "OMPI_COMM_WORLD_RANK"}, 0);
+    reader.device = env_int({"FANS_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, -1);
+    if (reader.world_size <= 1) {
+        reader.world_size = 1, reader.world_rank = 0;
+        return;
+    }
+    const char *f = getenv("FANS_COMM_FILE");
+    if (!f) throw std::runtime_error("WORLD_SIZE > 1 needs FANS_COMM_FILE (a path all ranks share) for the NCCL id rendezvous");
+    const std::string file = f;
+    unsigned char id[128];
+    if (reader.world_rank == 0) {
+        if (fans_comm_unique_id(id) != FANS_OK) throw std::runtime_error(std::string("fans_comm_unique_id: ") + fans_last_error(nullptr));
+        const std::string tmp = file + ".tmp";
+        {
+            std::ofstream o(tmp, std::ios::binary);
+            o.write((const char *)id, 128);
+        }
+        if (rename(tmp.c_str(), file.c_str()) != 0) throw std::runtime_error("cannot publish " + file);
+    } else {
+        bool ok = false;
+        for (int i = 0; i < 6000 && !ok; ++i) {   // up to 60 s
+            std::ifstream in(file, std::ios::binary);
+            if (in && in.read((char *)id, 128) && in.gcount() == 128) ok = true;
+            else usleep(10000);
+        }
+        if (!ok) throw std::runtime_error("timed out waiting for the NCCL id in " + file);
+    }
+    if (fans_comm_create(&reader.comm, reader.world_size, reader.world_rank, id, reader.device) != FANS_OK)
+        throw std::runtime_error(std::string("fans_comm_create: ") + fans_last_error(nullptr));
+    if (reader.world_rank == 0) unlink(file.c_str());   // everybody holds the communicator once CommInitRank has returned
+}
+
+// field slabs of rank r > 0 go next to rank 0's; small data (averages, error history, tangent) are identical on every rank
+struct RankSink : ResultsSink {
+    ResultsSink &inner;
+    int rank;
+    RankSink(ResultsSink &s, int r) : inner(s), rank(r) {}
+    void write(const std::string &name, int load_idx, int time_idx, const std::string &dtype, const std::vector<size_t> &dims, const void *data,
+               bool is_field) override
+    {
+        if (is_field || rank == 0) inner.write(name, load_idx, time_idx, dtype, dims, data, is_field);
+    }
+};
+
+static std::string rank_path(const std::string &out, int rank, bool h5)
+{
+    if (rank == 0) return out;
+    if (h5) return out.substr(0, out.size() - 3) + ".rank" + std::to_string(rank) + ".h5";
+    return out + "/rank" + std::to_string(rank);
+}
+
 static void load_raw_ms(Reader &reader, const char *file, int nx, int ny, int nz)
 {
     std::ifstream in(file, std::ios::binary);
@@ -161,8 +229,9 @@ static void runSolver(Reader &reader, ResultsSink &sink)
         MaterialManager *matmanager = createMaterialManager(reader);
         Solver *solver = createSolver(reader, matmanager);  // a fresh Solver (u = 0) per load case, like the reference
         for (size_t time_step_idx = 0; time_step_idx < reader.load_cases[load_path_idx].n_steps; ++time_step_idx) {
-            printf("\n║ ▶ Load case %zu/%zu: Time step %zu/%zu\n", load_path_idx + 1, reader.load_cases.size(), time_step_idx + 1,
-                   reader.load_cases[load_path_idx].n_steps);
+            if (reader.world_rank == 0)
+                printf("\n║ ▶ Load case %zu/%zu: Time step %zu/%zu\n", load_path_idx + 1, reader.load_cases.size(), time_step_idx + 1,
+                       reader.load_cases[load_path_idx].n_steps);
             if (reader.load_cases[load_path_idx].mixed) {
                 solver->enableMixedBC(reader.load_cases[load_path_idx].mbc, time_step_idx);
             } else {
@@ -171,7 +240,7 @@ static void runSolver(Reader &reader, ResultsSink &sink)
             }
             solver->solve();
             solver->postprocess(sink, (int)load_path_idx, (int)time_step_idx);
-            printf("# iterations %zu\n", solver->iter);
+            if (reader.world_rank == 0) printf("# iterations %zu\n", solver->iter);
             if (reader.extrapolate_displacement) solver->extrapolateDisplacement();
         }
         delete solver;
@@ -195,18 +264,24 @@ int main(int argc, char **argv)
             return 10;
         }
         Reader reader;
+        slab_world(reader);
         reader.ReadInputFile(argv[1]);
         if (argc == 7) load_raw_ms(reader, argv[3], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]));
         else reader.ReadMS(reader.howmany());
         const std::string out = argv[2];
-        if (out.size() > 3 && out.compare(out.size() - 3, 3, ".h5") == 0) {  // HDF5 results file like the reference's
-            H5Sink sink(out, reader.dataset_name);
-            runSolver(reader, sink);
+        const bool h5 = out.size() > 3 && out.compare(out.size() - 3, 3, ".h5") == 0;
+        const std::string mine = rank_path(out, reader.world_rank, h5);
+        if (h5) {  // HDF5 results file like the reference's
+            H5Sink sink(mine, reader.dataset_name);
+            RankSink rs(sink, reader.world_rank);
+            runSolver(reader, rs);
             sink.w.close();
         } else {  // directory of raw arrays + index.jsonl
-            DirSink sink(out, reader.dataset_name);
-            runSolver(reader, sink);
+            DirSink sink(mine, reader.dataset_name);
+            RankSink rs(sink, reader.world_rank);
+            runSolver(reader, rs);
         }
+        if (reader.comm) fans_comm_destroy(reader.comm);
         return 0;
     } catch (const std::exception &e) {
         fprintf(stderr, "ERROR: %s\n", e.what());

@@ -41,6 +41,8 @@ class Reader {
 
     int world_rank = 0, world_size = 1;
     int local_n0 = 0, local_0_start = 0, local_n1 = 0, local_1_start = 0;
+    void *comm = nullptr;   // slab communicator (fans_comm_create) when world_size > 1, see main.cpp
+    int device = -1;        // CUDA device of this rank (-1: current)
 
     int howmany() const { return problemType == "thermal" ? 1 : 3; }
     int n_str() const { return problemType == "thermal" ? 3 : (strain_type == "large" ? 9 : 6); }
@@ -202,9 +204,8 @@ class Reader {
     {
         if (L.size() != 3) throw std::runtime_error("microstructure.L must have 3 entries");
         l_e = {L[0] / dims[0], L[1] / dims[1], L[2] / dims[2]};
-        // slab sizes of a single rank (src/reader.cpp:311-331); multi-rank contexts are set up by the launcher
-        local_n0 = dims[0], local_0_start = 0, local_n1 = dims[1], local_1_start = 0;
         if (dims[0] / 4 < world_size) throw std::runtime_error("[ERROR] Number of processes * 4 must be <= n_x");
+        if (dims[0] % world_size || dims[1] % world_size) throw std::runtime_error("n_x and n_y must be divisible by the number of ranks");
         // ComputeVolumeFractions (src/reader.cpp:13-61)
         uint16_t mx = 0, mn = 65535;
         for (uint16_t v : ms) mx = std::max(mx, v), mn = std::min(mn, v);
@@ -212,6 +213,15 @@ class Reader {
         volume_fractions.assign(n_mat, 0.0);
         for (uint16_t v : ms) volume_fractions[v - mn] += 1.0;
         for (double &v : volume_fractions) v /= (double)ms.size();
+        // slab of this rank (src/reader.cpp:311-331: fftw_mpi_local_size_many_transposed hands out n_x/P x-planes and n_y/P y-rows);
+        // every rank has read the whole image, the volume fractions above are global like the reference's (reader.cpp:40-57)
+        local_n0 = dims[0] / world_size, local_0_start = world_rank * local_n0;
+        local_n1 = dims[1] / world_size, local_1_start = world_rank * local_n1;
+        if (world_size > 1) {
+            const size_t plane = (size_t)dims[1] * dims[2];
+            std::vector<uint16_t> slab(ms.begin() + (size_t)local_0_start * plane, ms.begin() + (size_t)(local_0_start + local_n0) * plane);
+            ms.swap(slab);
+        }
     }
 };
 

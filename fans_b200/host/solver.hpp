@@ -59,7 +59,8 @@ class Solver {
         cfg.world_rank = world_rank;
         cfg.local_n0 = (int)local_n0, cfg.local_0_start = (int)local_0_start;
         cfg.local_n1 = (int)local_n1, cfg.local_1_start = (int)local_1_start;
-        cfg.device = -1;
+        cfg.device = rd.device;
+        cfg.nccl_comm = rd.comm;   // one rank per GPU, rank order = slab order (main.cpp: slab_world)
         if (fans_create(&ctx, &cfg) != FANS_OK) throw std::runtime_error(std::string("fans_create: ") + fans_last_error(nullptr));
         const auto descs = matmanager->phase_descs();
         check(fans_set_materials(ctx, (int)descs.size(), descs.data()));
@@ -200,6 +201,25 @@ class Solver {
                 if (ph < n_mat) psa[ph][c] += stress[e * n_str + c], pea[ph][c] += strain[e * n_str + c];
             }
             if (ph < n_mat) cnt[ph]++;
+        }
+        if (world_size > 1 && need_compute) {   // the MPI_Allreduce calls of solver.h:556-571, packed into one
+            std::vector<double> pack;
+            pack.insert(pack.end(), sa.begin(), sa.end());
+            pack.insert(pack.end(), ea.begin(), ea.end());
+            for (int m = 0; m < n_mat; ++m) {
+                pack.insert(pack.end(), psa[m].begin(), psa[m].end());
+                pack.insert(pack.end(), pea[m].begin(), pea[m].end());
+                pack.push_back((double)cnt[m]);
+            }
+            check(fans_allreduce_sum(ctx, pack.data(), (int)pack.size()));
+            size_t k = 0;
+            for (int c = 0; c < n_str; ++c) sa[c] = pack[k++];
+            for (int c = 0; c < n_str; ++c) ea[c] = pack[k++];
+            for (int m = 0; m < n_mat; ++m) {
+                for (int c = 0; c < n_str; ++c) psa[m][c] = pack[k++];
+                for (int c = 0; c < n_str; ++c) pea[m][c] = pack[k++];
+                cnt[m] = (long)(pack[k++] + 0.5);
+            }
         }
         const double Ntot = (double)n_x * n_y * n_z;
         for (int c = 0; c < n_str; ++c) sa[c] /= Ntot, ea[c] /= Ntot;

@@ -129,6 +129,9 @@ int  fans_version(void);
 int fans_comm_unique_id(void *id128 /* out: 128 bytes */);
 int fans_comm_create(void **comm, int32_t n_ranks, int32_t rank, const void *id128, int32_t device /* -1: current */);
 int fans_comm_destroy(void *comm);
+/* MPI_Allreduce(MPI_IN_PLACE, host_inout, n, MPI_DOUBLE, MPI_SUM) over the slabs of ctx's communicator: what Solver::postprocess does
+ * with its averages (include/solver.h:556-571).  No-op for world_size == 1. */
+int fans_allreduce_sum(fans_ctx *ctx, double *host_inout, int32_t n);
 
 /* ---- problem data ---- */
 int fans_set_microstructure(fans_ctx *ctx, const uint16_t *ms);                               /* Solver::ms solver.h:34,121 */

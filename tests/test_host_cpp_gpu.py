@@ -86,3 +86,69 @@ def test_cli_hdf5_results(tmp_path):
     assert np.allclose(stress.reshape(-1, 6).mean(0), w[pre + "/stress_average"][0], rtol=1e-5, atol=1e-8)
     msr, _ = w[pre + "/microstructure"]
     assert np.array_equal(msr[..., 0], np.transpose(gu.sphere32(), (2, 1, 0)))
+
+
+def j2_cfg(steps):
+    cfg = gu.reference_input("J2Plasticity")
+    cfg["macroscale_loading"] = [[[0.002 * (t + 1), -0.001 * (t + 1), -0.001 * (t + 1), 0.0005 * (t + 1), 0, 0] for t in range(steps)]]
+    cfg["results"] = ["stress_average", "strain_average", "absolute_error", "stress", "strain", "plastic_strain", "isotropic_hardening_variable"]
+    return cfg
+
+
+def test_cli_j2_multistep_matches_oracle(tmp_path):
+    """J2 plasticity over several time steps through FANS_gpu, results requested like a user would (stress AND strain fields): the
+    postprocess sweep must run exactly once per time step — J2Plasticity accumulates psi / psi_bar on every get_sigma call
+    (J2Plasticity.h:103-104), so a second sweep would change every later step."""
+    import fans_oracle as fo
+    steps = 3
+    cfg = j2_cfg(steps)
+    load, _ = run_cli(tmp_path, cfg)
+    out = []
+
+    def o_step(sol, lc, t, res):
+        res["post"] = sol.postprocess()   # one getStrainStress sweep per step, like Solver::postprocess
+
+    ro, _ = fo.run_load_cases(gu.sphere32(), cfg, on_step=o_step)
+    for t in range(steps):
+        sa = load("stress_average", 0, t)
+        assert rel_err(sa, ro[0][t]["post"]["stress_average"]) < 1e-9, t
+        assert abs(len(load("absolute_error", 0, t)) - 1 - ro[0][t]["iters"]) <= 1
+        assert rel_err(load("stress", 0, t), np.asarray(ro[0][t]["post"]["stress"]).reshape(32, 32, 32, 6)) < 1e-8, t
+        assert rel_err(load("isotropic_hardening_variable", 0, t),
+                       np.asarray(ro[0][t]["post"]["isotropic_hardening_variable"]).reshape(32, 32, 32)) < 1e-8, t
+
+
+def test_cli_two_ranks(tmp_path):
+    """FANS_gpu on 2 ranks (one per GPU, NCCL id through FANS_COMM_FILE, no MPI): same averages and iteration counts as one rank,
+    the field slabs of the two ranks concatenate to the single-rank field.  Reference: mpiexec -n 2 FANS (src/main.cpp:60-61)."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = j2_cfg(2)
+    exe = cpp_host.build()
+    ms = tmp_path / "ms.u16"
+    gu.sphere32().tofile(ms)
+    inp = tmp_path / "in.json"
+    inp.write_text(json.dumps(cfg))
+    one, two = tmp_path / "one", tmp_path / "two"
+    r = subprocess.run([exe, str(inp), str(one), str(ms), "32", "32", "32"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fans_mprun.py"), "-n", "2", "--", exe, str(inp), str(two), str(ms), "32", "32", "32"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+    def loader(d):
+        index = [json.loads(l) for l in open(os.path.join(d, "index.jsonl"))]
+
+        def load(name, t):
+            e = [i for i in index if i["name"] == name and i["time_step"] == t][0]
+            return np.fromfile(str(d) + e["path"], dtype=np.float64).reshape(e["dims"])
+        return load
+    l1, l2a, l2b = loader(one), loader(two), loader(two / "rank1")
+    for t in range(2):
+        assert rel_err(l2a("stress_average", t), l1("stress_average", t)) < 1e-9
+        assert abs(len(l2a("absolute_error", t)) - len(l1("absolute_error", t))) <= 1
+        both = np.concatenate([l2a("stress", t), l2b("stress", t)], axis=0)
+        assert both.shape == (32, 32, 32, 6) and rel_err(both, l1("stress", t)) < 1e-8

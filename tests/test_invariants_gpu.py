@@ -77,7 +77,21 @@ def test_j2_return_map_invariants(kind):
         q = q - (sinf - SY) * (1.0 - np.exp(-delta * psi))
     f = np.linalg.norm(dev(sig) + (2.0 / 3.0) * Hk * pb, axis=-1) - S23 * (SY - q)
     scale = S23 * SY
-    assert np.abs(f[plastic] - eta * gam[plastic] / dt).max() < (1e-8 if kind == "j2_nonlin" else 1e-12) * scale   # Newton stops at 1e-10 in gamma
+    if kind == "j2_lin":
+        assert np.abs(f[plastic] - eta * gam[plastic] / dt).max() < 1e-12 * scale
+    else:
+        # The reference's Newton loop (J2Plasticity.h:207-223) runs on the SIGNED increment with the slope -den (its "(2 / 3)" is
+        # integer 0): the first step overshoots, the second comes back and, being negative, ends the loop.  The consistency condition
+        # therefore holds to the square of the contraction factor c = sqrt(2/3) (s_inf - s_y) delta sqrt(2/3) / den, not to round-off ...
+        den = 2.0 * G0 + (2.0 / 3.0) * (Kiso + Hk) + eta / dt
+        c = (2.0 / 3.0) * (sinf - SY) * delta / den
+        f_trial = 2.0 * G0 * np.linalg.norm(dev(eps), axis=-1) - S23 * SY      # virgin state: q = qbar = 0
+        assert np.abs(f[plastic] - eta * gam[plastic] / dt).max() < 2.0 * c * c * f_trial[plastic].max()
+        # ... and gamma is exactly that two-step iterate
+        sd = S23 * (sinf - SY)
+        g1 = f_trial / den
+        g2 = g1 + (f_trial - g1 * den - sd * (1.0 - np.exp(-delta * S23 * g1))) / den
+        assert np.abs(gam[plastic] - g2[plastic]).max() < 1e-12 * gam.max()
     assert f[~plastic].max() <= 1e-14                                               # elastic points are inside the yield surface
     ctx.close()
 
