@@ -250,6 +250,22 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // named barriers (ids 1..15; 0 is __syncthreads): producer/consumer hand-over of ring slots without stalling the whole CTA
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+// warp-specialised register budget (setmaxnreg, sm_90a+): the kernel is launched with 80 registers per thread (2 CTAs x 384 threads);
+// the producer warpgroup hands 40 of them back, the two consumer warpgroups take 16 more each — the consumer step (18 accumulators,
+// 12 staged inputs, 3 homogeneity flags) no longer spills to local memory in the march
+#ifndef STENCIL_SETMAXNREG
+#define STENCIL_SETMAXNREG 1
+#endif
+#ifndef STENCIL_PROD_REGS
+#define STENCIL_PROD_REGS 40
+#endif
+#ifndef STENCIL_CONS_REGS
+#define STENCIL_CONS_REGS 96
+#endif
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N)); }
 #define BAR_FULL 1    // +slot: plane (and the element plane after it) is in the ring
 #define BAR_EMPTY 5   // +slot: the consumers are done with the plane that lived in the slot
 #define BAR_CONS 9    // consumer-only barrier (interface queue)
@@ -283,6 +299,7 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
 
     if (wy >= GY) {
         // =================================== producer warpgroup ===================================
+        if (STENCIL_SETMAXNREG && STENCIL_MINB == 2) reg_dealloc<STENCIL_PROD_REGS>();
         const int lane = tid - G_CONS;  // producer thread index 0..G_PROD-1
         const double beta = p.s ? *p.beta : 0.0;
         int goff[G_NLP], roff[G_NLP], moff[G_NLM];
@@ -374,6 +391,7 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
         }
     } else {
         // =================================== consumer warps ===================================
+        if (STENCIL_SETMAXNREG && STENCIL_MINB == 2) reg_alloc<STENCIL_CONS_REGS>();
         const int ry = wy + 1, rzA = 2 * lane + 2;  // tile coordinates of node A (column = z - z0 + 2); node B = rzA + 1
         const int rzM = 2 * lane + 1;               // column of node A in the phase-image tile (z - z0 + 1)
         const int yA = y0 + wy, zA = z0 + 2 * lane;

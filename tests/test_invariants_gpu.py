@@ -12,6 +12,7 @@ from fans_b200 import simple
 pytestmark = pytest.mark.gpu
 
 K0, G0, SY = 62.5, 28.8462, 0.1
+LOAD = [0.002, -0.0005, -0.0004, 0.0006, 0.0, 0.0003]   # ||dev|| = 2.1e-3
 S23 = np.sqrt(2.0 / 3.0)
 
 
@@ -53,7 +54,7 @@ def test_j2_return_map_invariants(kind):
         name = "J2ViscoPlastic_NonLinearIsotropicHardening"
         props.update(saturation_stress=[sinf], saturation_exponent=[delta])
     ctx = one_phase_ctx({"phases": [0], "matmodel": name, "material_properties": props})
-    ctx.set_gradient([0.002, -0.0005, -0.0004, 0.0006, 0.0, 0.0003])   # partly beyond yield: sigma_dev ~ 2 G e ~ 0.1
+    ctx.set_gradient(list(0.67 * np.array(LOAD)))   # ||dev eps|| ~ 1.4e-3 = the elastic limit sqrt(2/3) sigma_y / (2 G): both branches occur
     ctx.upload("u", smooth_u(ctx.dims, 2e-4))
     _, _, eps, sig = ctx.strain_stress_gp()      # one law call per Gauss point, history written
     ctx.commit_history()
@@ -103,7 +104,7 @@ def test_j2new_return_map_invariants():
     ctx = one_phase_ctx({"phases": [0], "matmodel": "J2PlasticityNew_LinearIsotropicHardening",
                          "material_properties": {"bulk_modulus": [K0], "shear_modulus": [G0], "yield_stress": [SY],
                                                  "isotropic_hardening_parameter": [Kiso]}})
-    ctx.set_gradient([0.002, -0.0005, -0.0004, 0.0006, 0.0, 0.0003])
+    ctx.set_gradient(list(0.67 * np.array(LOAD)))
     ctx.upload("u", smooth_u(ctx.dims, 2e-4, 1))
     _, _, eps, sig = ctx.strain_stress_gp()
     ctx.commit_history()
@@ -131,8 +132,9 @@ def test_pseudoplastic_hardening_curve(kind):
         mat = {"phases": [0], "matmodel": "PseudoPlasticNonLinearHardening",
                "material_properties": {"bulk_modulus": [K0], "shear_modulus": [G0], "yield_stress": [SY], "hardening_exponent": [0.2], "eps_0": [0.01]}}
     ctx = one_phase_ctx(mat)
-    ctx.set_gradient([0.002, -0.0005, -0.0004, 0.0006, 0.0, 0.0003])
-    ctx.upload("u", smooth_u(ctx.dims, 2e-4, 2))
+    sc = 0.67 if kind == "lin" else 0.35     # the power law leaves the elastic branch at eps_eq = 6.7e-4 already
+    ctx.set_gradient(list(sc * np.array(LOAD)))
+    ctx.upload("u", smooth_u(ctx.dims, 2e-4 * sc, 2))
     _, _, eps, sig = ctx.strain_stress_gp()
     e, s = dev(eps), dev(sig)
     ne, nsig = np.linalg.norm(e, axis=-1), np.linalg.norm(s, axis=-1)
