@@ -93,6 +93,7 @@ struct fans_ctx {
     double *d_K = nullptr;      // phase stiffness table [n_k][(8h)^2]
     double *d_C = nullptr;      // phase tangent table   [n_k][n_str^2]
     std::vector<double> K_host; // host copy of the phase stiffness table
+    std::vector<double> S_host; // 27-point block stencils of the phases [q][delta][i][j] (stencil.cu), passed as a kernel parameter
     uint16_t ms_max = 0;
     int n_k = 0;
     bool k_in_const = false;

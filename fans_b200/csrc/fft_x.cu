@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
 // Gamma_hat block to its own frequencies (no cross-thread traffic, no barrier) and runs the three inverse transforms.  A third of
 // the threads and of the registers of k_fft_xg per tile, so TWO independent CTAs fit on an SM and one CTA's butterflies overlap the
 // other's loads, stores and shared-memory exchanges.
-template <int N, int T>
+// PF: the strided rows of the NEXT component (and, during the inverse transforms, of the next tile's first component) travel
+// global -> shared with cp.async straight into that component's tile, which is idle until its own forward transform starts — the
+// load latency that one CTA per SM cannot hide with other warps disappears behind the butterflies, at no register cost.
+template <int N, int T, bool PF>
 __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 * 1024) ? 2 : 1)
     k_fft_xg_seq(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,
                  int nWork, PeerTable peers)
@@ -126,15 +129,37 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 
     constexpr size_t NT = (size_t)N * T;
     const int tc = threadIdx.x, t = tc % T, jt = tc / T;
     const TileIdxX<T> idx{t};
+    auto tile_off = [&](int w) { return (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t; };
+    auto prefetch = [&](int w, int c) {   // rows of component c of tile w -> this thread's slots of tile c; one commit group
+        const double2 *base = spec + (size_t)c * g.cStride + tile_off(w);
+        double2 *dst = sm + c * NT + tc;
+#pragma unroll
+        for (int e = 0; e < E; ++e) cp_async16(dst + e * NTC, base + spec_row_x(g, rp_row<N, 0>(jt, e)));
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (PF && (int)blockIdx.x < nWork) prefetch(blockIdx.x, 0);
     for (int w = blockIdx.x; w < nWork; w += gridDim.x) {
-        const size_t off = (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t;
+        const size_t off = tile_off(w);
         double2 a[1][E];
 #pragma unroll 1
         for (int c = 0; c < H; ++c) {
             double2 *X = sm + c * NT;
-            const double2 *base = spec + (size_t)c * g.cStride + off;
+            if (PF) {
+                // tile c+1 is idle (its last use, the previous tile's inverse transform, lies behind barriers every thread has passed)
+                if (c + 1 < H) {
+                    prefetch(w, c + 1);
+                    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                }
 #pragma unroll
-            for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_x(g, rp_row<N, 0>(jt, e))];
+                for (int e = 0; e < E; ++e) a[0][e] = X[e * NTC + tc];
+                if (NST > 1) __syncthreads();  // everybody holds its rows before the first exchange overwrites the slots
+            } else {
+                const double2 *base = spec + (size_t)c * g.cStride + off;
+#pragma unroll
+                for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_x(g, rp_row<N, 0>(jt, e))];
+            }
             rp_forward<N, 1>(a, jt, X, 0, idx, tw, 1);
             if (NST > 1) __syncthreads();  // everybody is done reading the last exchange of this component
 #pragma unroll
@@ -170,6 +195,12 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 
 #pragma unroll
                 for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
             }
+            // component 1 is through its inverse transform => every thread has left tile 0: the next tile's first component may land
+            if (PF && c == 1 && NST > 1 && w + (int)gridDim.x < nWork) prefetch(w + gridDim.x, 0);
+        }
+        if (PF && NST <= 1 && w + (int)gridDim.x < nWork) {  // single-stage transforms have no barriers to lean on
+            __syncthreads();
+            prefetch(w + gridDim.x, 0);
         }
     }
 }
@@ -182,15 +213,20 @@ static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const
     const size_t smem = 3 * sizeof(double2) * N * T;
     static int resident = 0;
     if (!resident) {
-        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg_seq<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fft_xg_seq<N, T>, NTHR, smem));
+        if (smem > 48 * 1024) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg_seq<N, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_xg_seq<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fft_xg_seq<N, T, true>, NTHR, smem));
         if (resident < 1) resident = 1;
     }
     const int nWork = ctx->n1 * nTiles;
     int grid = FANS_SMS * resident;
     if (const char *env = getenv("FANS_XG_GRID")) grid = atoi(env);
     if (grid > nWork) grid = nWork;
-    k_fft_xg_seq<N, T><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
+    const char *pf = getenv("FANS_XG_PF");   // 0: plain loads at the start of every component (A/B runs)
+    if (pf && atoi(pf) == 0) k_fft_xg_seq<N, T, false><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
+    else k_fft_xg_seq<N, T, true><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
     return FANS_OK;
 }
 

@@ -34,7 +34,17 @@
 #define STENCIL_MIXED_TABLE 0   // 1: warps cut by an interface take per-lane coefficients from the table in global memory (measured slower)
 #endif
 
-__constant__ double c_S[STENCIL_MAXQ * 27 * 9];   // [q][delta][i][j]
+// The 27-point block stencils travel as a KERNEL PARAMETER (__grid_constant__): parameter space is constant bank 0, whose entries
+// the FP64 pipe takes as direct operands (DFMA R, R, c[0x0][imm], R) — a user __constant__ array costs one LDCU per coefficient
+// and step (10 % of the kernel's instructions, profiles/r2g_ncu_stencil.txt).  It also keeps the table per launch, not per process.
+#ifndef STENCIL_COEF_PARAM
+#define STENCIL_COEF_PARAM 1
+#endif
+template <int H, int NQ>
+struct StencilCoef {
+    double S[NQ * 27 * H * H];   // [q][delta][i][j]
+};
+__constant__ double c_S[STENCIL_MAXQ * 27 * 9];   // the same table for the STENCIL_COEF_PARAM = 0 build (A/B runs)
 __constant__ double c_KQ[STENCIL_MAXQ * 576];      // [q][row][col]  (8h x 8h, h <= 3)
 
 struct StencilParams {
@@ -68,11 +78,11 @@ __device__ __forceinline__ int gwrap(int v, int n)
 // every component) to the node pair of output plane o = P - (DXI-1), phase Q (compile time => constant-bank operands).
 // Each plane row is read from shared memory once and feeds the accumulators of the three output planes it touches.
 template <int H, int Q, bool ISO, int DXI, int DY>
-__device__ __forceinline__ void stencil_row(const double (&v)[H][4], double (&accA)[H], double (&accB)[H])
+__device__ __forceinline__ void stencil_row(const double *__restrict__ Sall, const double (&v)[H][4], double (&accA)[H], double (&accB)[H])
 {
 #pragma unroll
     for (int dz = 0; dz < 3; ++dz) {
-        const double *S = c_S + ((Q * 27 + (DXI * 9 + DY * 3 + dz)) * H * H);
+        const double *S = Sall + ((Q * 27 + (DXI * 9 + DY * 3 + dz)) * H * H);
 #pragma unroll
         for (int i = 0; i < H; ++i)
 #pragma unroll
@@ -109,12 +119,12 @@ __device__ __forceinline__ void stencil_row_table(const double *__restrict__ Sq,
     }
 }
 template <int H, int NQ, bool ISO, int DXI, int DY>
-__device__ __forceinline__ void stencil_row_dispatch(int ph, const double (&v)[H][4], double (&accA)[H], double (&accB)[H])
+__device__ __forceinline__ void stencil_row_dispatch(const double *__restrict__ S, int ph, const double (&v)[H][4], double (&accA)[H], double (&accB)[H])
 {
-    if (NQ > 0 && ph == 0) stencil_row<H, 0, ISO, DXI, DY>(v, accA, accB);
-    else if (NQ > 1 && ph == 1) stencil_row<H, (NQ > 1 ? 1 : 0), ISO, DXI, DY>(v, accA, accB);
-    else if (NQ > 2 && ph == 2) stencil_row<H, (NQ > 2 ? 2 : 0), ISO, DXI, DY>(v, accA, accB);
-    else if (NQ > 3 && ph == 3) stencil_row<H, (NQ > 3 ? 3 : 0), ISO, DXI, DY>(v, accA, accB);
+    if (NQ > 0 && ph == 0) stencil_row<H, 0, ISO, DXI, DY>(S, v, accA, accB);
+    else if (NQ > 1 && ph == 1) stencil_row<H, (NQ > 1 ? 1 : 0), ISO, DXI, DY>(S, v, accA, accB);
+    else if (NQ > 2 && ph == 2) stencil_row<H, (NQ > 2 ? 2 : 0), ISO, DXI, DY>(S, v, accA, accB);
+    else if (NQ > 3 && ph == 3) stencil_row<H, (NQ > 3 ? 3 : 0), ISO, DXI, DY>(S, v, accA, accB);
 }
 
 // exact element form for ONE node at tile position (ry, rz) of plane k; element E = (ox,oy,oz) below the node
@@ -281,8 +291,9 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 // neighbourhood) are queued and evaluated in the exact element form.  Hand-over through named barriers per ring slot, so
 // neither side ever waits for the other unless it is genuinely ahead.
 template <int H, int NQ, bool ISO>
-__global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p)
+__global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p, const __grid_constant__ StencilCoef<H, NQ> coef)
 {
+    const double *__restrict__ Sc = STENCIL_COEF_PARAM ? coef.S : c_S;
     extern __shared__ __align__(16) double smem[];
     double *ring = smem;                                   // [4][H][GTILE]   combined direction planes
     double2 *stg = reinterpret_cast<double2 *>(smem + 4 * H * GTILE);  // [2][H][G_STG] raw d_old / s pairs in flight
@@ -441,15 +452,15 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
         }                                                                                                       \
         if (hph[0] >= 0) {                                                                                      \
             if (STENCIL_MIXED_TABLE && (mixed & 1)) stencil_row_table<H, ISO, 2, DY>(p.Stab + hph[0] * (27 * H * H), v, acc[0][0], acc[0][1]); \
-            else stencil_row_dispatch<H, NQ, ISO, 2, DY>(hph[0], v, acc[0][0], acc[0][1]);                       \
+            else stencil_row_dispatch<H, NQ, ISO, 2, DY>(Sc, hph[0], v, acc[0][0], acc[0][1]);                       \
         }                                                                                                       \
         if (hph[1] >= 0) {                                                                                      \
             if (STENCIL_MIXED_TABLE && (mixed & 2)) stencil_row_table<H, ISO, 1, DY>(p.Stab + hph[1] * (27 * H * H), v, acc[1][0], acc[1][1]); \
-            else stencil_row_dispatch<H, NQ, ISO, 1, DY>(hph[1], v, acc[1][0], acc[1][1]);                       \
+            else stencil_row_dispatch<H, NQ, ISO, 1, DY>(Sc, hph[1], v, acc[1][0], acc[1][1]);                       \
         }                                                                                                       \
         if (hph[2] >= 0) {                                                                                      \
             if (STENCIL_MIXED_TABLE && (mixed & 4)) stencil_row_table<H, ISO, 0, DY>(p.Stab + hph[2] * (27 * H * H), v, acc[2][0], acc[2][1]); \
-            else stencil_row_dispatch<H, NQ, ISO, 0, DY>(hph[2], v, acc[2][0], acc[2][1]);                       \
+            else stencil_row_dispatch<H, NQ, ISO, 0, DY>(Sc, hph[2], v, acc[2][0], acc[2][1]);                       \
         }                                                                                                       \
     }
                 ST_ROW(0)
@@ -526,14 +537,16 @@ void stencil_from_element_matrix(int h, const double *K, double *S /* [27][h][h]
 bool stencil_supported(const fans_ctx *ctx) { return ctx->all_linear && ctx->n_k >= 1 && ctx->n_k <= STENCIL_MAXQ && ctx->n_k == ctx->n_phases; }
 
 template <int H, int NQ>
-static int launch_stencil(fans_ctx *ctx, const StencilParams &p, dim3 grid, size_t smem, bool iso)
+static int launch_stencil(fans_ctx *ctx, const StencilParams &p, dim3 grid, size_t smem, bool iso, const std::vector<double> &S)
 {
+    StencilCoef<H, NQ> coef;
+    for (size_t i = 0; i < sizeof(coef.S) / sizeof(double); ++i) coef.S[i] = i < S.size() ? S[i] : 0.0;
     if (iso && H == 3) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ, (H == 3)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stencil_linear<H, NQ, (H == 3)><<<grid, G_THREADS, smem, ctx->st>>>(p);
+        k_stencil_linear<H, NQ, (H == 3)><<<grid, G_THREADS, smem, ctx->st>>>(p, coef);
     } else {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stencil_linear<H, NQ, false><<<grid, G_THREADS, smem, ctx->st>>>(p);
+        k_stencil_linear<H, NQ, false><<<grid, G_THREADS, smem, ctx->st>>>(p, coef);
     }
     return FANS_OK;
 }
@@ -562,7 +575,8 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
 {
     const int h = ctx->h, nd = 8 * h;
     if (g_stencil_stamp != ctx->const_stamp) {
-        std::vector<double> S((size_t)ctx->n_k * 27 * h * h);
+        std::vector<double> &S = ctx->S_host;
+        S.assign((size_t)ctx->n_k * 27 * h * h, 0.0);
         for (int q = 0; q < ctx->n_k; ++q) stencil_from_element_matrix(h, ctx->K_host.data() + (size_t)q * nd * nd, S.data() + (size_t)q * 27 * h * h);
         // synchronous copies: the host vector dies at scope exit
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
@@ -599,7 +613,7 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     prof_begin(ctx, PC_SWEEP_LINEAR);
     int rc = FANS_ERR_ARG;
 #define ST_CASE(H_, Q_) \
-    if (h == H_ && ctx->n_k == Q_) rc = launch_stencil<H_, Q_>(ctx, p, grid, smem, g_stencil_iso);
+    if (h == H_ && ctx->n_k == Q_) rc = launch_stencil<H_, Q_>(ctx, p, grid, smem, g_stencil_iso, ctx->S_host);
     ST_CASE(1, 1) ST_CASE(1, 2) ST_CASE(1, 3) ST_CASE(1, 4) ST_CASE(3, 1) ST_CASE(3, 2) ST_CASE(3, 3) ST_CASE(3, 4)
 #undef ST_CASE
     prof_end(ctx);
