@@ -230,4 +230,41 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *scratch, do
         }
     }
 }
+
+// scalar form of grid_reduce<1, 1>: the same deterministic two-level sum without an array argument (an array handed over by
+// reference pins the caller's accumulator to a local-memory slot for its whole lifetime)
+__device__ __forceinline__ void grid_reduce_sum1(double v, double *scratch, double *part, unsigned int *ticket, double *out)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    if (wid == 0) v = warp_sum(lane < nw ? scratch[lane] : 0.0);
+    __shared__ bool is_last1;
+    const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (threadIdx.x == 0) {
+        part[bid] = v;
+        __threadfence();
+        is_last1 = (atomicAdd(ticket, 1u) == nb - 1);
+    }
+    __syncthreads();
+    if (is_last1) {
+        __threadfence();
+        double a = 0.0;
+        for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) a += __ldcg(&part[b]);   // fixed order: thread t sums blocks t, t + blockDim, ...
+        a = warp_sum(a);
+        __syncthreads();
+        if (lane == 0) scratch[wid] = a;
+        __syncthreads();
+        if (wid == 0) {
+            a = warp_sum(lane < nw ? scratch[lane] : 0.0);
+            if (lane == 0) {
+                *out = a;
+                *ticket = 0u;
+            }
+        }
+    }
+}
 #endif

@@ -188,7 +188,7 @@ struct IfaceArgs {
     size_t nloc;
     int ny, nz, y0, z0, k;
 };
-template <int H>
+template <int H, int NCONS>
 __device__ __noinline__ double interface_phase(const IfaceArgs a, int tid)
 {
     constexpr int ND = 8 * H;
@@ -198,7 +198,7 @@ __device__ __noinline__ double interface_phase(const IfaceArgs a, int tid)
     for (int w = 0; w < GY; ++w) pre[w + 1] = pre[w] + a.qcnt[w];
     const int nitems = 16 * pre[GY];  // pair x 2 nodes x 8 elements
     double dot = 0.0;
-    for (int n0 = 0; n0 < nitems; n0 += G_CONS) {
+    for (int n0 = 0; n0 < nitems; n0 += NCONS) {
         const int n = n0 + tid;
         const bool on = n < nitems;
         double acc[H];
@@ -266,6 +266,9 @@ __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("ba
 #ifndef STENCIL_SETMAXNREG
 #define STENCIL_SETMAXNREG 1
 #endif
+#ifndef STENCIL_DEFER_IFACE
+#define STENCIL_DEFER_IFACE 1   // 0: consumer-only barrier + interface phase at the end of every step (A/B builds)
+#endif
 #ifndef STENCIL_PROD_REGS
 #define STENCIL_PROD_REGS 40
 #endif
@@ -283,6 +286,103 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 #define G_NLP ((GPAIRS + G_PROD - 1) / G_PROD)   // pair items per producer thread and component
 #define G_NLM ((GETILE + G_PROD - 1) / G_PROD)   // phase-image items per producer thread
 #define G_STG (G_NLP * G_PROD)                   // staging pairs per component
+
+// Producer warpgroup of the stencil kernels (`lane` = producer thread index 0..G_PROD-1, GT = threads of the CTA = barrier count):
+// raw s / d_old pairs of plane Q+1 travel global -> staging with cp.async while plane Q is combined (d = s + beta d_old) into ring
+// slot Q&3, d_new is stored and the phase-image ring refilled.
+template <int H, int GT>
+__device__ __forceinline__ void stencil_producer(const StencilParams &p, double *ring, double2 *stg, uint16_t *mring, int lane, int y0, int z0,
+                                                 int xs, int xe, size_t plane_sz)
+{
+    const double beta = p.s ? *p.beta : 0.0;
+    int goff[G_NLP], roff[G_NLP], moff[G_NLM];
+    unsigned mine_mask = 0;
+#pragma unroll
+    for (int j = 0; j < G_NLP; ++j) {
+        const int i = lane + j * G_PROD;
+        goff[j] = -1, roff[j] = 0;
+        if (i < GPAIRS) {
+            const int r = i / (GPZ / 2), q = i % (GPZ / 2);
+            goff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 2 + 2 * q, p.nz);
+            roff[j] = r * GPZ + 2 * q;
+            if (r >= 1 && r <= GY && q >= 1 && q <= GZ / 2 && (y0 - 1 + r) < p.ny && (z0 - 2 + 2 * q) < p.nz) mine_mask |= 1u << j;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G_NLM; ++j) {
+        const int i = lane + j * G_PROD;
+        moff[j] = -1;
+        if (i < GETILE) {
+            const int r = i / (GZ + 1), c = i % (GZ + 1);
+            moff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 1 + c, p.nz);
+        }
+    }
+    auto issue = [&](int xp) {
+        const bool lo = (p.halo_lo && xp < 0), hi = (p.halo_hi && xp >= p.n0);
+        const double *hal = lo ? p.halo_lo : (hi ? p.halo_hi : nullptr);
+        const size_t gbase = (xp < 0 ? (size_t)(xp + p.n0) : (xp >= p.n0 ? (size_t)(xp - p.n0) : (size_t)xp)) * plane_sz;
+        const double *srcd = hal ? hal : p.d_old + gbase;
+        const size_t cs = hal ? plane_sz : p.nloc;
+#pragma unroll
+        for (int cc = 0; cc < H; ++cc)
+#pragma unroll
+            for (int j = 0; j < G_NLP; ++j)
+                if (goff[j] >= 0) cp_async16(stg + cc * G_STG + lane + j * G_PROD, srcd + cc * cs + goff[j]);
+        if (p.s && !hal) {
+#pragma unroll
+            for (int cc = 0; cc < H; ++cc)
+#pragma unroll
+                for (int j = 0; j < G_NLP; ++j)
+                    if (goff[j] >= 0) cp_async16(stg + (H + cc) * G_STG + lane + j * G_PROD, p.s + cc * p.nloc + gbase + goff[j]);
+        }
+    };
+    auto combine = [&](int xp, bool owned) {
+        const bool hal = (p.halo_lo && xp < 0) || (p.halo_hi && xp >= p.n0);
+        const bool upd = p.s && !hal;
+        const size_t gbase = (xp < 0 ? (size_t)(xp + p.n0) : (xp >= p.n0 ? (size_t)(xp - p.n0) : (size_t)xp)) * plane_sz;
+        double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
+#pragma unroll
+        for (int cc = 0; cc < H; ++cc)
+#pragma unroll
+            for (int j = 0; j < G_NLP; ++j)
+                if (goff[j] >= 0) {
+                    double2 v = stg[cc * G_STG + lane + j * G_PROD];
+                    if (upd) {
+                        const double2 sv = stg[(H + cc) * G_STG + lane + j * G_PROD];
+                        v.x = sv.x + beta * v.x, v.y = sv.y + beta * v.y;
+                        if (owned && ((mine_mask >> j) & 1u)) *reinterpret_cast<double2 *>(p.d_new + cc * p.nloc + gbase + goff[j]) = v;
+                    }
+                    *reinterpret_cast<double2 *>(pl + cc * GTILE + roff[j]) = v;
+                }
+    };
+    uint16_t msr[G_NLM];
+    auto ms_fetch = [&](int xp) {
+        const uint16_t *src = (p.ms_lo && xp < 0) ? p.ms_lo : p.phidx + (size_t)gwrap(xp, p.n0) * plane_sz;
+#pragma unroll
+        for (int j = 0; j < G_NLM; ++j) msr[j] = (moff[j] >= 0) ? __ldg(src + moff[j]) : (uint16_t)0;
+    };
+    auto ms_put = [&](int xp) {
+        uint16_t *mp = mring + ((xp + 8) & 7) * GETILE;
+#pragma unroll
+        for (int j = 0; j < G_NLM; ++j)
+            if (moff[j] >= 0) mp[lane + j * G_PROD] = msr[j];
+    };
+    issue(xs - 1);
+    ms_fetch(xs - 1);
+    ms_put(xs - 1);
+    ms_fetch(xs);
+    for (int Q = xs - 1; Q <= xe; ++Q) {
+        cp_async_wait_all();
+        if (Q >= xs + 3) bar_sync(BAR_EMPTY + (Q & 3), GT);  // consumers have left plane Q-4
+        combine(Q, Q >= xs && Q < xe);
+        ms_put(Q + 1);
+        bar_arrive(BAR_FULL + (Q & 3), GT);
+        if (Q + 1 <= xe) {
+            issue(Q + 1);   // lands while the consumers work on plane Q
+            ms_fetch(Q + 2);
+        }
+    }
+}
 
 // Warp-specialised march along x.  Producer warpgroup (warps 8..11): raw s / d_old pairs of plane Q+1 travel global -> staging with
 // cp.async while it combines plane Q (d = s + beta d_old) into ring slot Q&3, stores d_new and refills the phase-image ring.
@@ -306,103 +406,17 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
     const int z0 = blockIdx.x * GZ, y0 = blockIdx.y * GY;
     const int xs = blockIdx.z * p.xchunk, xe = min(xs + p.xchunk, p.n0);
     const size_t plane_sz = (size_t)p.ny * p.nz;
-    double racc[1] = {0.0};
+    double dot_final = 0.0;   // <d_new, K d_new> of this thread; the running sum lives inside the consumer branch only (a value that
+                              // is live across the producer branch would have to fit the producers' 40-register budget and gets spilled)
 
     if (wy >= GY) {
         // =================================== producer warpgroup ===================================
         if (STENCIL_SETMAXNREG && STENCIL_MINB == 2) reg_dealloc<STENCIL_PROD_REGS>();
-        const int lane = tid - G_CONS;  // producer thread index 0..G_PROD-1
-        const double beta = p.s ? *p.beta : 0.0;
-        int goff[G_NLP], roff[G_NLP], moff[G_NLM];
-        unsigned mine_mask = 0;
-#pragma unroll
-        for (int j = 0; j < G_NLP; ++j) {
-            const int i = lane + j * G_PROD;
-            goff[j] = -1, roff[j] = 0;
-            if (i < GPAIRS) {
-                const int r = i / (GPZ / 2), q = i % (GPZ / 2);
-                goff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 2 + 2 * q, p.nz);
-                roff[j] = r * GPZ + 2 * q;
-                if (r >= 1 && r <= GY && q >= 1 && q <= GZ / 2 && (y0 - 1 + r) < p.ny && (z0 - 2 + 2 * q) < p.nz) mine_mask |= 1u << j;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < G_NLM; ++j) {
-            const int i = lane + j * G_PROD;
-            moff[j] = -1;
-            if (i < GETILE) {
-                const int r = i / (GZ + 1), c = i % (GZ + 1);
-                moff[j] = gwrap(y0 - 1 + r, p.ny) * p.nz + gwrap(z0 - 1 + c, p.nz);
-            }
-        }
-        auto issue = [&](int xp) {
-            const bool lo = (p.halo_lo && xp < 0), hi = (p.halo_hi && xp >= p.n0);
-            const double *hal = lo ? p.halo_lo : (hi ? p.halo_hi : nullptr);
-            const size_t gbase = (xp < 0 ? (size_t)(xp + p.n0) : (xp >= p.n0 ? (size_t)(xp - p.n0) : (size_t)xp)) * plane_sz;
-            const double *srcd = hal ? hal : p.d_old + gbase;
-            const size_t cs = hal ? plane_sz : p.nloc;
-#pragma unroll
-            for (int cc = 0; cc < H; ++cc)
-#pragma unroll
-                for (int j = 0; j < G_NLP; ++j)
-                    if (goff[j] >= 0) cp_async16(stg + cc * G_STG + lane + j * G_PROD, srcd + cc * cs + goff[j]);
-            if (p.s && !hal) {
-#pragma unroll
-                for (int cc = 0; cc < H; ++cc)
-#pragma unroll
-                    for (int j = 0; j < G_NLP; ++j)
-                        if (goff[j] >= 0) cp_async16(stg + (H + cc) * G_STG + lane + j * G_PROD, p.s + cc * p.nloc + gbase + goff[j]);
-            }
-        };
-        auto combine = [&](int xp, bool owned) {
-            const bool hal = (p.halo_lo && xp < 0) || (p.halo_hi && xp >= p.n0);
-            const bool upd = p.s && !hal;
-            const size_t gbase = (xp < 0 ? (size_t)(xp + p.n0) : (xp >= p.n0 ? (size_t)(xp - p.n0) : (size_t)xp)) * plane_sz;
-            double *pl = ring + (size_t)((xp + 4) & 3) * H * GTILE;
-#pragma unroll
-            for (int cc = 0; cc < H; ++cc)
-#pragma unroll
-                for (int j = 0; j < G_NLP; ++j)
-                    if (goff[j] >= 0) {
-                        double2 v = stg[cc * G_STG + lane + j * G_PROD];
-                        if (upd) {
-                            const double2 sv = stg[(H + cc) * G_STG + lane + j * G_PROD];
-                            v.x = sv.x + beta * v.x, v.y = sv.y + beta * v.y;
-                            if (owned && ((mine_mask >> j) & 1u)) *reinterpret_cast<double2 *>(p.d_new + cc * p.nloc + gbase + goff[j]) = v;
-                        }
-                        *reinterpret_cast<double2 *>(pl + cc * GTILE + roff[j]) = v;
-                    }
-        };
-        uint16_t msr[G_NLM];
-        auto ms_fetch = [&](int xp) {
-            const uint16_t *src = (p.ms_lo && xp < 0) ? p.ms_lo : p.phidx + (size_t)gwrap(xp, p.n0) * plane_sz;
-#pragma unroll
-            for (int j = 0; j < G_NLM; ++j) msr[j] = (moff[j] >= 0) ? __ldg(src + moff[j]) : (uint16_t)0;
-        };
-        auto ms_put = [&](int xp) {
-            uint16_t *mp = mring + ((xp + 8) & 7) * GETILE;
-#pragma unroll
-            for (int j = 0; j < G_NLM; ++j)
-                if (moff[j] >= 0) mp[lane + j * G_PROD] = msr[j];
-        };
-        issue(xs - 1);
-        ms_fetch(xs - 1);
-        ms_put(xs - 1);
-        ms_fetch(xs);
-        for (int Q = xs - 1; Q <= xe; ++Q) {
-            cp_async_wait_all();
-            if (Q >= xs + 3) bar_sync(BAR_EMPTY + (Q & 3), G_THREADS);  // consumers have left plane Q-4
-            combine(Q, Q >= xs && Q < xe);
-            ms_put(Q + 1);
-            bar_arrive(BAR_FULL + (Q & 3), G_THREADS);
-            if (Q + 1 <= xe) {
-                issue(Q + 1);   // lands while the consumers work on plane Q
-                ms_fetch(Q + 2);
-            }
-        }
+        stencil_producer<H, G_THREADS>(p, ring, stg, mring, tid - G_CONS, y0, z0, xs, xe, plane_sz);
     } else {
         // =================================== consumer warps ===================================
         if (STENCIL_SETMAXNREG && STENCIL_MINB == 2) reg_alloc<STENCIL_CONS_REGS>();
+        double dotacc = 0.0;
         const int ry = wy + 1, rzA = 2 * lane + 2;  // tile coordinates of node A (column = z - z0 + 2); node B = rzA + 1
         const int rzM = 2 * lane + 1;               // column of node A in the phase-image tile (z - z0 + 1)
         const int yA = y0 + wy, zA = z0 + 2 * lane;
@@ -414,8 +428,26 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
         for (int j = 0; j < 3; ++j)
 #pragma unroll
             for (int c = 0; c < H; ++c) acc[j][0][c] = 0.0, acc[j][1][c] = 0.0;
+        // interface nodes of plane k (queued in buffer par): exact element form over planes k-1..k+1
+        auto run_interface = [&](int k, int par) -> double {
+            int any = 0;
+#pragma unroll
+            for (int w = 0; w < GY; ++w) any |= qcnt[par][w];
+            if (!any) return 0.0;
+            IfaceArgs ia;
+            ia.ring = ring, ia.Ktab = p.Ktab, ia.mring = mring, ia.qlist = qlist[par], ia.qcnt = qcnt[par], ia.out = p.out;
+            ia.nloc = p.nloc, ia.ny = p.ny, ia.nz = p.nz, ia.y0 = y0, ia.z0 = z0, ia.k = k;
+            return interface_phase<H, G_CONS>(ia, tid);
+        };
         for (int P = xs - 1; P <= xe; ++P) {
             bar_sync(BAR_FULL + (P & 3), G_THREADS);  // plane P and element plane P+1 are in the rings
+#if STENCIL_DEFER_IFACE
+            // The hand-over barrier above is also the consumers' own barrier: everybody has finished step P-1, so the interface queue
+            // of plane P-2 (filled during step P-1) is complete.  Its nodes are evaluated now, over the planes P-3..P-1 that are still
+            // in the ring; only then does the slot of plane P-3 go back to the producer.  No consumer-only barrier is left in the march.
+            if (P - 2 >= xs) dotacc += run_interface(P - 2, (P - 1) & 1);
+            if (P - 1 >= xs + 1 && P + 1 <= xe) bar_arrive(BAR_EMPTY + ((P + 1) & 3), G_THREADS);
+#endif
             // ---- phase 1
             const int o2 = P + 1;  // newest output plane: classify its node pair from the 12 elements around it (planes o2-1, o2)
             hph[2] = -1;
@@ -479,7 +511,7 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
                 for (int c = 0; c < H; ++c) {
                     *reinterpret_cast<double2 *>(p.out + c * p.nloc + g) = make_double2(acc[0][0][c], acc[0][1][c]);
                     const double2 cv = *reinterpret_cast<const double2 *>(ctr + c * GTILE);
-                    racc[0] += acc[0][0][c] * cv.x + acc[0][1][c] * cv.y;
+                    dotacc += acc[0][0][c] * cv.x + acc[0][1][c] * cv.y;
                 }
             }
             if (qmask) {
@@ -494,24 +526,20 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
                 acc[2][0][c] = 0.0, acc[2][1][c] = 0.0;
             }
             hph[0] = hph[1], hph[1] = hph[2];
+#if !STENCIL_DEFER_IFACE
             bar_sync(BAR_CONS, G_CONS);
-            // ---- phase 2: the queued interface nodes of plane k (exact element form over planes k-1..k+1)
-            {
-                int any = 0;
-#pragma unroll
-                for (int w = 0; w < GY; ++w) any |= qcnt[par][w];
-                if (any) {
-                    IfaceArgs ia;
-                    ia.ring = ring, ia.Ktab = p.Ktab, ia.mring = mring, ia.qlist = qlist[par], ia.qcnt = qcnt[par], ia.out = p.out;
-                    ia.nloc = p.nloc, ia.ny = p.ny, ia.nz = p.nz, ia.y0 = y0, ia.z0 = z0, ia.k = k;
-                    racc[0] += interface_phase<H>(ia, tid);
-                }
-            }
+            dotacc += run_interface(k, par);
             // plane P-2 is not needed any more: its slot may take plane P+2
             if (P >= xs + 1 && P + 2 <= xe) bar_arrive(BAR_EMPTY + ((P + 2) & 3), G_THREADS);
+#endif
         }
+#if STENCIL_DEFER_IFACE
+        bar_sync(BAR_CONS, G_CONS);          // the queue of the last plane is complete
+        dotacc += run_interface(xe - 1, xe & 1);
+#endif
+        dot_final = dotacc;
     }
-    if (p.red_out) grid_reduce<1, 1>(racc, scratch, p.part, p.ticket, p.red_out);
+    if (p.red_out) grid_reduce_sum1(dot_final, scratch, p.part, p.ticket, p.red_out);
 }
 
 // ------------------------------------------------------------------------------------------------
