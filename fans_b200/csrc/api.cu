@@ -199,7 +199,8 @@ static int ensure_field(fans_ctx *ctx, int f)
         return FANS_ERR_ARG;
     }
     if (!ctx->field[f]) {
-        const size_t bytes = sizeof(double) * ctx->h * ctx->nloc;
+        // one extra (always zero) value: the double2 vector passes of vecops.cu round an odd h*nloc up (grids with odd dimensions)
+        const size_t bytes = sizeof(double) * ((size_t)ctx->h * ctx->nloc + 1);
         CUDA_TRY(ctx, cudaMalloc(&ctx->field[f], bytes));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->field[f], 0, bytes, ctx->st));
     }
@@ -209,7 +210,7 @@ static int ensure_field(fans_ctx *ctx, int f)
 int ensure_dalt(fans_ctx *ctx)
 {
     if (!ctx->d_alt) {
-        const size_t bytes = sizeof(double) * ctx->h * ctx->nloc;
+        const size_t bytes = sizeof(double) * ((size_t)ctx->h * ctx->nloc + 1);
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_alt, bytes));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_alt, 0, bytes, ctx->st));
     }
@@ -257,13 +258,18 @@ extern "C" int fans_create(fans_ctx **out, const fans_config *cfg)
         return fail(FANS_ERR_ARG, "(howmany, n_str) must be (1,3), (3,6) or (3,9)");
     if (ctx->fe < FANS_FE_HEX8 || ctx->fe > FANS_FE_BBAR)
         return fail(FANS_ERR_ARG, "Unknown FE_type. Supported types: HEX8, HEX8R, BBAR");
+    bool pow2 = true;
     for (int d = 0; d < 3; ++d) {
         const int n = cfg->dims[d];
-        if (n < 4 || (n & (n - 1)) != 0 || n > 2048)
-            return fail(FANS_ERR_ARG, "grid dimensions must be powers of two in [4, 2048] (got " + std::to_string(n) + ")");
+        if (n < 4 || n > 2048) return fail(FANS_ERR_ARG, "grid dimensions must lie in [4, 2048] (got " + std::to_string(n) + ")");
+        if ((n & (n - 1)) != 0) pow2 = false;
     }
+    // any size is accepted like the reference's FFTW plans (src/reader.cpp:300-305): sizes that are not powers of two take the
+    // Bluestein passes of fft_any.cu (single GPU); the slab decomposition with its fused transposes exists for 2^k grids only
+    ctx->any_fft = !pow2;
+    if (ctx->any_fft && ctx->P > 1) return fail(FANS_ERR_ARG, "world_size > 1 needs power-of-two grid dimensions (the fused NVLink transposes are radix-2^k)");
     // slab sizes as fftw_mpi_local_size_many_transposed hands them out for these grids (src/reader.cpp:311-331)
-    if ((ctx->P & (ctx->P - 1)) != 0 || ctx->nx % ctx->P != 0 || ctx->ny % ctx->P != 0)
+    if (ctx->P > 1 && ((ctx->P & (ctx->P - 1)) != 0 || ctx->nx % ctx->P != 0 || ctx->ny % ctx->P != 0))
         return fail(FANS_ERR_ARG, "world_size must be a power of two dividing n_x and n_y");
     if (ctx->rank < 0 || ctx->rank >= ctx->P) return fail(FANS_ERR_ARG, "world_rank out of range");
     if (ctx->n0 != ctx->nx / ctx->P || ctx->x0 != ctx->rank * ctx->n0 || ctx->n1 != ctx->ny / ctx->P || ctx->y1 != ctx->rank * ctx->n1)
@@ -310,12 +316,23 @@ static int create_rest(fans_ctx *ctx)
 
     ctx->kzc = ctx->nz / 2 + 1;
     ctx->kzp = (ctx->kzc + 7) / 8 * 8;
-    ctx->gT = fft_x_tile_width(ctx->nx, ctx->h);
+    ctx->gT = ctx->any_fft ? 4 : fft_x_tile_width(ctx->nx, ctx->h);
+    ctx->gE = ctx->any_fft ? 1 : (ctx->nx < 8 ? ctx->nx : 8);
     ctx->yT = 8;  // 128-byte rows: 512^3: 1.04 ms vs 1.39 ms with T=4; n_y = 1024 over NVLink (2 GPUs): 2.35 / 2.51 ms vs 3.69 / 3.00 ms
     if (const char *e = getenv("FANS_YT")) ctx->yT = (atoi(e) == 4) ? 4 : 8;
-    FANS_CHECK(fft_plan_init(ctx, ctx->planx, ctx->nx, ctx->nx));
-    FANS_CHECK(fft_plan_init(ctx, ctx->plany, ctx->ny, ctx->ny));
-    FANS_CHECK(fft_plan_init(ctx, ctx->planz, ctx->nz / 2, ctx->nz));
+    if (ctx->any_fft) {
+        FANS_CHECK(any_plan_init(ctx, ctx->anyx, ctx->nx));
+        FANS_CHECK(any_plan_init(ctx, ctx->anyy, ctx->ny));
+        FANS_CHECK(any_plan_init(ctx, ctx->anyz, ctx->nz));
+        ctx->planx.pos_host.resize(ctx->nx);   // natural frequency order along x and y
+        ctx->plany.pos_host.resize(ctx->ny);
+        for (int f = 0; f < ctx->nx; ++f) ctx->planx.pos_host[f] = f;
+        for (int f = 0; f < ctx->ny; ++f) ctx->plany.pos_host[f] = f;
+    } else {
+        FANS_CHECK(fft_plan_init(ctx, ctx->planx, ctx->nx, ctx->nx));
+        FANS_CHECK(fft_plan_init(ctx, ctx->plany, ctx->ny, ctx->ny));
+        FANS_CHECK(fft_plan_init(ctx, ctx->planz, ctx->nz / 2, ctx->nz));
+    }
     if (const char *env = getenv("FANS_XPAD")) ctx->xpad = atoi(env);
     const size_t spec_elems = (size_t)ctx->P * ctx->h * ctx->n0 * ((size_t)ctx->n1 * ctx->kzp + ctx->xpad);
     CUDA_TRY(ctx, cudaMalloc(&ctx->spec, sizeof(double2) * spec_elems));
@@ -370,7 +387,7 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     for (int f = 0; f < FANS_N_FIELDS; ++f)
         if (ctx->field[f]) cudaFree(ctx->field[f]);
     void *ptrs[] = {ctx->specB, ctx->ms_lo, ctx->halo_send_lo, ctx->halo_send_hi, ctx->halo_lo, ctx->halo_hi, ctx->d_alt, ctx->stage_io, ctx->ms, ctx->phidx, ctx->spec, ctx->gamma, ctx->d_phase, ctx->d_K, ctx->phase_lut,
-                    ctx->hist, ctx->hist_t, ctx->hidx, ctx->pflag, ctx->d_part, ctx->d_red, ctx->d_ticket, ctx->d_flag, ctx->d_C};
+                    ctx->hist, ctx->hist_t, ctx->hidx, ctx->pflag, ctx->d_Stab, ctx->d_part, ctx->d_red, ctx->d_ticket, ctx->d_flag, ctx->d_C};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
@@ -378,6 +395,9 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     fft_plan_free(ctx->planx);
     fft_plan_free(ctx->plany);
     fft_plan_free(ctx->planz);
+    any_plan_free(ctx->anyx);
+    any_plan_free(ctx->anyy);
+    any_plan_free(ctx->anyz);
     prof_resolve(ctx);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     for (auto &pr : ctx->conv_pending) cudaEventDestroy(pr.first), cudaEventDestroy(pr.second);
@@ -1021,7 +1041,7 @@ extern "C" int fans_get_field(fans_ctx *ctx, const char *name, void *dst, size_t
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
         double *o = (double *)dst;  // natural order [ky][kx][kz][NG]
         const size_t NT = (size_t)ctx->nx * T;
-        const int E = ctx->nx < 8 ? ctx->nx : 8, TPC = ctx->nx / E;
+        const int E = ctx->gE, TPC = ctx->nx / E;
         for (int ky = 0; ky < ctx->ny; ++ky) {
             const int py = ctx->plany.pos_host[ky];
             if (py < ctx->y1 || py >= ctx->y1 + ctx->n1) continue;

@@ -38,6 +38,14 @@ struct FftPlan {
     std::vector<int> pos_host;
 };
 
+// Bluestein plan of one axis for grids that are not powers of two (fft_any.cu)
+struct AnyPlan {
+    int n = 0, M = 0, logM = 0;   // transform length, power-of-two convolution length >= 2n-1
+    double2 *w = nullptr;         // device: chirp exp(-i pi k^2 / n), k < n
+    double2 *Bhat = nullptr;      // device: FFT_M of the wrapped conjugate chirp / M, bit-reversed order
+    double2 *tw = nullptr;        // device: exp(-2 pi i j / M), j < M/2
+};
+
 struct PhaseDev {  // device copy of one fans_phase_desc (params trimmed)
     int    model, local_mat, group_n_mat, k_index;  // k_index: slot of the phase stiffness in the K table (linear) or -1
     const double *tangent;                          // linear phases: device pointer to C (n_str x n_str, row-major)
@@ -84,6 +92,9 @@ struct fans_ctx {
     int gT = 4;                // kz tile width of the fused x pass
     int yT = 8;                // kz tile width of the y passes
     FftPlan planx, plany, planz;  // planz: half-length complex plan of the r2c/c2r transform (N = nz/2)
+    bool any_fft = false;         // some dimension is not a power of two: Bluestein passes of fft_any.cu, natural frequency order
+    AnyPlan anyx, anyy, anyz;
+    int gE = 8;                   // rows of the x transform a thread of the fused x pass holds (Gamma layout, gamma.cu); 1 for any_fft
     bool gamma_ready = false;
 
     // materials
@@ -94,6 +105,9 @@ struct fans_ctx {
     double *d_C = nullptr;      // phase tangent table   [n_k][n_str^2]
     std::vector<double> K_host; // host copy of the phase stiffness table
     std::vector<double> S_host; // 27-point block stencils of the phases [q][delta][i][j] (stencil.cu), passed as a kernel parameter
+    double *d_Stab = nullptr;   // the same table on the device (more than STENCIL_MAXQ phases, warps cut by an interface)
+    bool stencil_iso = false;   // every phase has the isotropic sparsity pattern (stencil.cu: stencil_iso_pattern)
+    uint64_t stencil_stamp = 0; // const_stamp the stencil tables were built for
     uint16_t ms_max = 0;
     int n_k = 0;
     bool k_in_const = false;

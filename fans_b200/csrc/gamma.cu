@@ -132,10 +132,10 @@ int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const in
     const double invN = 1.0 / ((double)ctx->nx * (double)ctx->ny * (double)ctx->nz);
     if (ctx->h == 1)
         k_build_gamma<1><<<(unsigned)nb, nthr, 0, ctx->st>>>(ctx->gamma, Ker0_dev, frqx, frqy, ctx->nx, ctx->ny, ctx->nz, ctx->n1, ctx->y1,
-                                                           ctx->kzc, T, nTiles, invN, ctx->nx < 8 ? ctx->nx : 8);
+                                                           ctx->kzc, T, nTiles, invN, ctx->gE);
     else
         k_build_gamma<3><<<(unsigned)nb, nthr, 0, ctx->st>>>(ctx->gamma, Ker0_dev, frqx, frqy, ctx->nx, ctx->ny, ctx->nz, ctx->n1, ctx->y1,
-                                                           ctx->kzc, T, nTiles, invN, ctx->nx < 8 ? ctx->nx : 8);
+                                                           ctx->kzc, T, nTiles, invN, ctx->gE);
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());

@@ -25,6 +25,11 @@ int  fft_x_tile_width(int nx, int h);
 struct SpecGeom;
 SpecGeom spec_geom_A(const fans_ctx *ctx);
 
+// fft_any.cu: grids that are not powers of two
+int  any_plan_init(fans_ctx *ctx, AnyPlan &p, int n);
+void any_plan_free(AnyPlan &p);
+int  conv_run_any(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out);
+
 // gamma.cu
 int gamma_build(fans_ctx *ctx, const double *Ker0_dev, const int *frqx, const int *frqy);
 

@@ -130,6 +130,7 @@ int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const d
         decltype(conv_event) &mk;
         ~ConvTimer() { c->conv_pending.emplace_back(a, mk()); }
     } conv_timer{ctx, ev_a, conv_event};
+    if (ctx->any_fft) return conv_run_any(ctx, in, out, scale, dotw, red_out);
     if (ctx->pipe && !ctx->prof) return conv_run_pipelined(ctx, in, out, scale, dotw, red_out);
     FANS_CHECK(fft_pass_z_fwd(ctx, in));
     FANS_CHECK(fft_pass_y(ctx, false));

@@ -34,18 +34,14 @@
 #define STENCIL_MIXED_TABLE 0   // 1: warps cut by an interface take per-lane coefficients from the table in global memory (measured slower)
 #endif
 
-// The 27-point block stencils travel as a KERNEL PARAMETER (__grid_constant__): parameter space is constant bank 0, whose entries
-// the FP64 pipe takes as direct operands (DFMA R, R, c[0x0][imm], R) — a user __constant__ array costs one LDCU per coefficient
-// and step (10 % of the kernel's instructions, profiles/r2g_ncu_stencil.txt).  It also keeps the table per launch, not per process.
-#ifndef STENCIL_COEF_PARAM
-#define STENCIL_COEF_PARAM 1
-#endif
+// The 27-point block stencils of up to STENCIL_MAXQ phases travel as a KERNEL PARAMETER (__grid_constant__, constant bank 0): no
+// process-global __constant__ table, nothing shared between contexts.  More phases (a polycrystal with one triclinic tensor per
+// grain, LinearElastic.h:77-159) take the NQ = 0 instantiation, which reads the coefficients of a lane's phase from the per-context
+// table in global memory (L1-resident; the lanes of a warp mostly share the address).
 template <int H, int NQ>
 struct StencilCoef {
-    double S[NQ * 27 * H * H];   // [q][delta][i][j]
+    double S[(NQ > 0 ? NQ : 1) * 27 * H * H];   // [q][delta][i][j]
 };
-__constant__ double c_S[STENCIL_MAXQ * 27 * 9];   // the same table for the STENCIL_COEF_PARAM = 0 build (A/B runs)
-__constant__ double c_KQ[STENCIL_MAXQ * 576];      // [q][row][col]  (8h x 8h, h <= 3)
 
 struct StencilParams {
     int n0, ny, nz;
@@ -125,54 +121,6 @@ __device__ __forceinline__ void stencil_row_dispatch(const double *__restrict__ 
     else if (NQ > 1 && ph == 1) stencil_row<H, (NQ > 1 ? 1 : 0), ISO, DXI, DY>(S, v, accA, accB);
     else if (NQ > 2 && ph == 2) stencil_row<H, (NQ > 2 ? 2 : 0), ISO, DXI, DY>(S, v, accA, accB);
     else if (NQ > 3 && ph == 3) stencil_row<H, (NQ > 3 ? 3 : 0), ISO, DXI, DY>(S, v, accA, accB);
-}
-
-// exact element form for ONE node at tile position (ry, rz) of plane k; element E = (ox,oy,oz) below the node
-template <int H, int Q, int A>
-__device__ __forceinline__ void element_rows(const double *ring, int k, int ry, int rz, double (&acc)[H])
-{
-    constexpr int ox = A & 1, oy = (A >> 1) & 1, oz = (A >> 2) & 1;
-    constexpr int ND = 8 * H;
-    double u0[H];
-#pragma unroll
-    for (int c = 0; c < H; ++c) u0[c] = ring[((size_t)((k - ox + 4) & 3) * H + c) * GTILE + (ry - oy) * GPZ + (rz - oz)];
-#pragma unroll
-    for (int b = 1; b < 8; ++b) {
-        const int bx = b & 1, by = (b >> 1) & 1, bz = (b >> 2) & 1;
-        double w[H];
-#pragma unroll
-        for (int c = 0; c < H; ++c)
-            w[c] = ring[((size_t)((k - ox + bx + 4) & 3) * H + c) * GTILE + (ry - oy + by) * GPZ + (rz - oz + bz)] - u0[c];
-#pragma unroll
-        for (int i = 0; i < H; ++i)
-#pragma unroll
-            for (int j = 0; j < H; ++j) acc[i] = fma(c_KQ[Q * (ND * ND) + (H * A + i) * ND + H * b + j], w[j], acc[i]);
-    }
-}
-
-template <int H, int NQ, int A>
-__device__ __forceinline__ void element_dispatch(const double *ring, int k, int ry, int rz, int ph, double (&acc)[H])
-{
-    if (NQ > 0 && ph == 0) element_rows<H, 0, A>(ring, k, ry, rz, acc);
-    else if (NQ > 1 && ph == 1) element_rows<H, (NQ > 1 ? 1 : 0), A>(ring, k, ry, rz, acc);
-    else if (NQ > 2 && ph == 2) element_rows<H, (NQ > 2 ? 2 : 0), A>(ring, k, ry, rz, acc);
-    else if (NQ > 3 && ph == 3) element_rows<H, (NQ > 3 ? 3 : 0), A>(ring, k, ry, rz, acc);
-}
-
-// ms ring: element plane p in slot (p+8)&7, tile [(GY+1)][(GZ+1)], element (ry,rz) = low corner at node tile (ry,rz)
-template <int H, int NQ>
-__device__ __forceinline__ void node_general(const double *ring, const uint16_t *mring, int k, int ry, int rz, double (&acc)[H])
-{
-#define EL_PH(ox, oy, oz) ((int)mring[((k - (ox) + 8) & 7) * GETILE + (ry - (oy)) * (GZ + 1) + (rz - 1 - (oz))])
-    element_dispatch<H, NQ, 0>(ring, k, ry, rz, EL_PH(0, 0, 0), acc);
-    element_dispatch<H, NQ, 1>(ring, k, ry, rz, EL_PH(1, 0, 0), acc);
-    element_dispatch<H, NQ, 2>(ring, k, ry, rz, EL_PH(0, 1, 0), acc);
-    element_dispatch<H, NQ, 3>(ring, k, ry, rz, EL_PH(1, 1, 0), acc);
-    element_dispatch<H, NQ, 4>(ring, k, ry, rz, EL_PH(0, 0, 1), acc);
-    element_dispatch<H, NQ, 5>(ring, k, ry, rz, EL_PH(1, 0, 1), acc);
-    element_dispatch<H, NQ, 6>(ring, k, ry, rz, EL_PH(0, 1, 1), acc);
-    element_dispatch<H, NQ, 7>(ring, k, ry, rz, EL_PH(1, 1, 1), acc);
-#undef EL_PH
 }
 
 // Interface nodes of plane k (queued by the consumers), exact element form (reference semantics: K_phase(element) (u_b - u_node0),
@@ -393,7 +341,7 @@ __device__ __forceinline__ void stencil_producer(const StencilParams &p, double 
 template <int H, int NQ, bool ISO>
 __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p, const __grid_constant__ StencilCoef<H, NQ> coef)
 {
-    const double *__restrict__ Sc = STENCIL_COEF_PARAM ? coef.S : c_S;
+    const double *__restrict__ Sc = coef.S;
     extern __shared__ __align__(16) double smem[];
     double *ring = smem;                                   // [4][H][GTILE]   combined direction planes
     double2 *stg = reinterpret_cast<double2 *>(smem + 4 * H * GTILE);  // [2][H][G_STG] raw d_old / s pairs in flight
@@ -483,15 +431,15 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
             v[c][0] = a.y, v[c][1] = b.x, v[c][2] = b.y, v[c][3] = d.x;                                         \
         }                                                                                                       \
         if (hph[0] >= 0) {                                                                                      \
-            if (STENCIL_MIXED_TABLE && (mixed & 1)) stencil_row_table<H, ISO, 2, DY>(p.Stab + hph[0] * (27 * H * H), v, acc[0][0], acc[0][1]); \
+            if (NQ == 0 || (STENCIL_MIXED_TABLE && (mixed & 1))) stencil_row_table<H, ISO, 2, DY>(p.Stab + hph[0] * (27 * H * H), v, acc[0][0], acc[0][1]); \
             else stencil_row_dispatch<H, NQ, ISO, 2, DY>(Sc, hph[0], v, acc[0][0], acc[0][1]);                       \
         }                                                                                                       \
         if (hph[1] >= 0) {                                                                                      \
-            if (STENCIL_MIXED_TABLE && (mixed & 2)) stencil_row_table<H, ISO, 1, DY>(p.Stab + hph[1] * (27 * H * H), v, acc[1][0], acc[1][1]); \
+            if (NQ == 0 || (STENCIL_MIXED_TABLE && (mixed & 2))) stencil_row_table<H, ISO, 1, DY>(p.Stab + hph[1] * (27 * H * H), v, acc[1][0], acc[1][1]); \
             else stencil_row_dispatch<H, NQ, ISO, 1, DY>(Sc, hph[1], v, acc[1][0], acc[1][1]);                       \
         }                                                                                                       \
         if (hph[2] >= 0) {                                                                                      \
-            if (STENCIL_MIXED_TABLE && (mixed & 4)) stencil_row_table<H, ISO, 0, DY>(p.Stab + hph[2] * (27 * H * H), v, acc[2][0], acc[2][1]); \
+            if (NQ == 0 || (STENCIL_MIXED_TABLE && (mixed & 4))) stencil_row_table<H, ISO, 0, DY>(p.Stab + hph[2] * (27 * H * H), v, acc[2][0], acc[2][1]); \
             else stencil_row_dispatch<H, NQ, ISO, 0, DY>(Sc, hph[2], v, acc[2][0], acc[2][1]);                       \
         }                                                                                                       \
     }
@@ -543,10 +491,6 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-static uint64_t g_stencil_stamp = 0;
-static bool g_stencil_iso = false;
-static double *g_stencil_Stab = nullptr;  // device copy of the stencil table (same content as c_S)
-
 // 27-point block stencil of a homogeneous neighbourhood from the element matrix K (8h x 8h, node-major):
 //   S[delta][i][j] = sum over local nodes a with b = a + delta inside the element of K[h a + i][h b + j]
 void stencil_from_element_matrix(int h, const double *K, double *S /* [27][h][h] */)
@@ -562,7 +506,9 @@ void stencil_from_element_matrix(int h, const double *K, double *S /* [27][h][h]
         }
 }
 
-bool stencil_supported(const fans_ctx *ctx) { return ctx->all_linear && ctx->n_k >= 1 && ctx->n_k <= STENCIL_MAXQ && ctx->n_k == ctx->n_phases; }
+// every all-linear problem: up to STENCIL_MAXQ phases with constant-bank coefficients, more through the coefficient table
+// (the node pairs of a thread and the 16-byte row copies need an even n_z; odd n_z takes the element sweep)
+bool stencil_supported(const fans_ctx *ctx) { return ctx->all_linear && ctx->n_k >= 1 && ctx->n_k == ctx->n_phases && ctx->nz % 2 == 0; }
 
 template <int H, int NQ>
 static int launch_stencil(fans_ctx *ctx, const StencilParams &p, dim3 grid, size_t smem, bool iso, const std::vector<double> &S)
@@ -602,19 +548,16 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
                 double *red_out)
 {
     const int h = ctx->h, nd = 8 * h;
-    if (g_stencil_stamp != ctx->const_stamp) {
+    if (ctx->stencil_stamp != ctx->const_stamp) {   // (re)build this context's tables after fans_set_materials
         std::vector<double> &S = ctx->S_host;
         S.assign((size_t)ctx->n_k * 27 * h * h, 0.0);
         for (int q = 0; q < ctx->n_k; ++q) stencil_from_element_matrix(h, ctx->K_host.data() + (size_t)q * nd * nd, S.data() + (size_t)q * 27 * h * h);
-        // synchronous copies: the host vector dies at scope exit
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
-        CUDA_TRY(ctx, cudaMemcpyToSymbol(c_S, S.data(), sizeof(double) * S.size()));
-        if (!g_stencil_Stab) CUDA_TRY(ctx, cudaMalloc(&g_stencil_Stab, sizeof(double) * STENCIL_MAXQ * 27 * 9));
-        CUDA_TRY(ctx, cudaMemcpy(g_stencil_Stab, S.data(), sizeof(double) * S.size(), cudaMemcpyHostToDevice));
-        CUDA_TRY(ctx, cudaMemcpyToSymbol(c_KQ, ctx->K_host.data(), sizeof(double) * (size_t)ctx->n_k * nd * nd));
-        g_stencil_stamp = ctx->const_stamp;
+        if (ctx->d_Stab) cudaFree(ctx->d_Stab), ctx->d_Stab = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_Stab, sizeof(double) * S.size()));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->d_Stab, S.data(), sizeof(double) * S.size(), cudaMemcpyHostToDevice));
         const char *env = getenv("FANS_STENCIL_ISO");
-        g_stencil_iso = stencil_iso_pattern(h, ctx->n_k, S.data()) && !(env && env[0] == '0');
+        ctx->stencil_iso = stencil_iso_pattern(h, ctx->n_k, S.data()) && !(env && env[0] == '0');
+        ctx->stencil_stamp = ctx->const_stamp;
     }
     StencilParams p;
     memset(&p, 0, sizeof(p));
@@ -622,7 +565,7 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     p.d_old = d_old, p.s = s_in, p.d_new = d_new, p.beta = beta_dev, p.out = out;
     p.phidx = ctx->phidx;
     p.Ktab = ctx->d_K;
-    p.Stab = g_stencil_Stab;
+    p.Stab = ctx->d_Stab;
     p.nq = ctx->n_k;
     p.part = ctx->d_part, p.ticket = ctx->d_ticket, p.red_out = red_out;
     if (ctx->P > 1) {
@@ -641,8 +584,8 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
     prof_begin(ctx, PC_SWEEP_LINEAR);
     int rc = FANS_ERR_ARG;
 #define ST_CASE(H_, Q_) \
-    if (h == H_ && ctx->n_k == Q_) rc = launch_stencil<H_, Q_>(ctx, p, grid, smem, g_stencil_iso, ctx->S_host);
-    ST_CASE(1, 1) ST_CASE(1, 2) ST_CASE(1, 3) ST_CASE(1, 4) ST_CASE(3, 1) ST_CASE(3, 2) ST_CASE(3, 3) ST_CASE(3, 4)
+    if (h == H_ && (Q_ > 0 ? ctx->n_k == Q_ : ctx->n_k > STENCIL_MAXQ)) rc = launch_stencil<H_, Q_>(ctx, p, grid, smem, ctx->stencil_iso, ctx->S_host);
+    ST_CASE(1, 1) ST_CASE(1, 2) ST_CASE(1, 3) ST_CASE(1, 4) ST_CASE(3, 1) ST_CASE(3, 2) ST_CASE(3, 3) ST_CASE(3, 4) ST_CASE(1, 0) ST_CASE(3, 0)
 #undef ST_CASE
     prof_end(ctx);
     ctx->launches++;

@@ -195,7 +195,7 @@ int halo_add_down(fans_ctx *ctx, double *r)
 int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const double *d, const double *s)
 {
     prof_begin(ctx, PC_CG_UPDATE);
-    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;   // fields carry one zero pad value (api.cu: ensure_field)
     k_cg_update<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)r, (const double2 *)kd, (double2 *)u, (const double2 *)d,
                                                           (const double2 *)s, n2, ctx->d_red, ctx->d_part, ctx->d_ticket);
     prof_end(ctx);
@@ -210,7 +210,7 @@ int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const d
 int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev)
 {
     prof_begin(ctx, PC_REDUCE);
-    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;   // fields carry one zero pad value (api.cu: ensure_field)
     k_reduce4<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((const double2 *)a, (const double2 *)b, n2, ctx->d_part, ctx->d_ticket, out_dev);
     prof_end(ctx);
     ctx->launches++;
@@ -225,7 +225,7 @@ int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev
 int vec_axpy(fans_ctx *ctx, double *y, double alpha, const double *x)
 {
     prof_begin(ctx, PC_AXPY);
-    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;   // fields carry one zero pad value (api.cu: ensure_field)
     k_axpy<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, alpha, (const double2 *)x, n2);
     prof_end(ctx);
     ctx->launches++;
@@ -236,7 +236,7 @@ int vec_axpy(fans_ctx *ctx, double *y, double alpha, const double *x)
 int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x)
 {
     prof_begin(ctx, PC_AXPY);
-    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;   // fields carry one zero pad value (api.cu: ensure_field)
     k_xpby<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, beta, (const double2 *)x, n2);
     prof_end(ctx);
     ctx->launches++;
@@ -247,7 +247,7 @@ int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x)
 int vec_extrapolate(fans_ctx *ctx, double *u, double *up)
 {
     prof_begin(ctx, PC_OTHER);
-    const size_t n2 = (size_t)ctx->h * ctx->nloc / 2;
+    const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;   // fields carry one zero pad value (api.cu: ensure_field)
     k_extrapolate<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)u, (double2 *)up, n2);
     prof_end(ctx);
     ctx->launches++;

@@ -176,3 +176,52 @@ def test_linear_cg_solve_sphere32(problem, materials, fe, g0):
     assert rel_err(ctx.homogenized_stress(), sol.get_homogenized_stress()) < SCALAR_TOL
     assert rel_err(ctx.download("u"), sol.u) < FIELD_TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("problem,n_ph", [("mechanical", 12), ("mechanical", 3), ("thermal", 9)])
+def test_polycrystal_many_triclinic_phases(problem, n_ph):
+    """A polycrystal-like image with one TRICLINIC tensor per grain (LinearElastic.h:77-159 / LinearThermal.h:48-118): more phases than
+    the constant-bank stencil holds take the coefficient-table instantiation of the stencil kernel (NQ = 0), fully anisotropic
+    27-point blocks; K.d against the oracle and against the element-sweep form, then the CG solve."""
+    import os
+    shape = (16, 16, 64)
+    rng = np.random.default_rng(5)
+    seeds = rng.uniform(0, 1, (n_ph, 3)) * np.array(shape)
+    g = np.stack(np.meshgrid(*[np.arange(s) + 0.5 for s in shape], indexing="ij"), -1)
+    d = np.abs(g[..., None, :] - seeds)
+    d = np.minimum(d, np.array(shape) - d)
+    ms = (d ** 2).sum(-1).argmin(-1).astype(np.uint16)          # periodic Voronoi grains
+    n = 6 if problem == "mechanical" else 3
+    tens = []
+    for _ in range(n_ph):
+        A = rng.standard_normal((n, n))
+        tens.append(A @ A.T + n * np.eye(n))                     # SPD, no symmetry at all
+    if problem == "mechanical":
+        keys = ["C_%d%d" % (r + 1, c + 1) for r in range(6) for c in range(r, 6)]
+        props = {k: [float(t[int(k[2]) - 1, int(k[3]) - 1]) * 20.0 for t in tens] for k in keys}
+        mats = [{"phases": list(range(n_ph)), "matmodel": "LinearElasticTriclinic", "material_properties": props}]
+    else:
+        keys = ["K_11", "K_12", "K_13", "K_22", "K_23", "K_33"]
+        props = {k: [float(t[int(k[2]) - 1, int(k[3]) - 1]) for t in tens] for k in keys}
+        mats = [{"phases": list(range(n_ph)), "matmodel": "LinearThermalTriclinic", "material_properties": props}]
+    sol = fo.OracleSolver(ms, [1.0, 1.0, 2.0], problem, mats, "HEX8", "cg", "small", EP, 200)
+    ctx = util.ctx_from_oracle(sol)
+    u = rng.standard_normal(ctx.field_shape) * 1e-3
+    ctx.upload("u", u)
+    ctx.apply_linear("rnew", "u")
+    kd = ctx.download("rnew")
+    assert rel_err(kd, sol.apply_linear(u)) < FIELD_TOL
+    os.environ["FANS_LINEAR_SWEEP"] = "1"
+    ctx.apply_linear("rnew", "u")
+    del os.environ["FANS_LINEAR_SWEEP"]
+    assert rel_err(kd, ctx.download("rnew")) < 1e-12
+    g0 = np.array(G0[sol.n_str])
+    sol.set_gradient(g0)
+    ctx.set_gradient(g0)
+    ctx.zero("u")
+    sol.solve()
+    res = ctx.solve("cg", 200, EP["tolerance"], EP["measure"], EP["type"])
+    assert abs(res["iters"] - sol.iter) <= 1
+    assert rel_err(ctx.homogenized_stress(), sol.get_homogenized_stress()) < SCALAR_TOL
+    assert rel_err(ctx.download("u"), sol.u) < FIELD_TOL
+    ctx.close()
