@@ -266,6 +266,12 @@ extern "C" int fans_create(fans_ctx **out, const fans_config *cfg)
     }
     // any size is accepted like the reference's FFTW plans (src/reader.cpp:300-305): sizes that are not powers of two take the
     // Bluestein passes of fft_any.cu (single GPU); the slab decomposition with its fused transposes exists for 2^k grids only
+    // solver.h:391,400: the reference multiplies the frequencies in pairs, (n_y n_x (n_z/2+1)) / 2 of them — with an odd count the last
+    // one is left untouched and the result is garbage ("it is important that at least one of the dimensions n_x and n_z is divisible
+    // by two").  Such a grid is refused instead of reproducing that.
+    if ((((long long)cfg->dims[0] * cfg->dims[1] * (cfg->dims[2] / 2 + 1)) & 1LL) != 0)
+        return fail(FANS_ERR_ARG, "n_x * n_y * (n_z/2 + 1) is odd: the reference's convolution skips the last frequency on such a grid "
+                                  "(include/solver.h:391-400); choose a grid with an even n_x, n_y or (n_z/2 + 1)");
     ctx->any_fft = !pow2;
     if (ctx->any_fft && ctx->P > 1) return fail(FANS_ERR_ARG, "world_size > 1 needs power-of-two grid dimensions (the fused NVLink transposes are radix-2^k)");
     // slab sizes as fftw_mpi_local_size_many_transposed hands them out for these grids (src/reader.cpp:311-331)

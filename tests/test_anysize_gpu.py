@@ -9,7 +9,7 @@ from util import ELASTIC, THERMAL, EP, rel_err
 
 pytestmark = pytest.mark.gpu
 G0 = {3: [0.01, 0.02, -0.01], 6: [0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001]}
-SHAPES = [(12, 20, 24), (9, 15, 10), (10, 12, 7), (24, 6, 100), (5, 7, 9)]
+SHAPES = [(12, 20, 24), (9, 15, 10), (10, 12, 7), (24, 6, 100), (5, 7, 10), (6, 7, 9)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -51,6 +51,13 @@ def test_j2_plasticity_on_a_100_like_grid():
     import test_nonlinear_gpu as tn
     ms = util.two_phase_ms(0, 17, (20, 12, 18))
     tn.compare(tn.cfg_for([tn.MODELS["j2_lin"], tn.EL1], "HEX8", "cg", tn.LOAD[:2]), ms, ("plastic_strain",))
+
+
+def test_odd_frequency_count_is_refused():
+    """n_x n_y (n_z/2+1) odd: the reference's pairwise Gamma loop drops the last frequency (solver.h:391-400) — refused loudly"""
+    from fans_b200 import _lib as L
+    with pytest.raises(L.FansError, match="skips the last frequency"):
+        L.Context((5, 7, 9), [1, 1, 1], 1, 3, "HEX8")
 
 
 def test_slabs_need_power_of_two():
