@@ -549,7 +549,6 @@ extern "C" int fans_set_materials(fans_ctx *ctx, int32_t n_phases, const fans_ph
     ctx->all_linear = all_lin;
     ctx->any_history = nhist > 0;
     ctx->any_flag = any_flag;
-    ctx->k_in_const = (size_t)nk * nd * nd <= (size_t)6144;
     if (ctx->d_K) cudaFree(ctx->d_K), ctx->d_K = nullptr;
     if (ctx->d_C) cudaFree(ctx->d_C), ctx->d_C = nullptr;
     if (nk > 0) {
@@ -799,6 +798,7 @@ extern "C" int fans_field_copy(fans_ctx *ctx, int32_t dst, int32_t src)
 int check_fault(fans_ctx *ctx)
 {
     int f = 0;
+    FANS_CHECK(comm_allreduce_int_max(ctx, ctx->d_flag));   // all slabs see the fault of any slab (every rank calls check_fault at the same points)
     CUDA_TRY(ctx, cudaMemcpyAsync(&f, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     if (f == FANS_ERR_NEG_JACOBIAN) {

@@ -143,6 +143,16 @@ extern "C" int fans_allreduce_sum(fans_ctx *ctx, double *host_inout, int32_t n)
     return rc;
 }
 
+// MAX of one int over the slabs, in place on the device: the sticky fault flag (negative Jacobian, ...) must take EVERY rank out of
+// the solve in the same iteration — a rank that returned alone would leave the others hanging in the next collective (the reference
+// aborts the whole MPI job on an uncaught exception)
+int comm_allreduce_int_max(fans_ctx *ctx, int *d_val)
+{
+    if (ctx->P == 1) return FANS_OK;
+    NCCL_TRY(ctx, g_nccl.AllReduce(d_val, d_val, 1, ncclInt, ncclMax, (ncclComm_t)ctx->cfg.nccl_comm, ctx->st));
+    return FANS_OK;
+}
+
 // ring exchange of one plane in each direction:
 //   to_prev (may be null) is sent to rank-1 and arrives there as from_next;  to_next -> rank+1 arrives as from_prev.
 int comm_halo(fans_ctx *ctx, const void *to_prev, void *from_next, const void *to_next, void *from_prev, size_t bytes)

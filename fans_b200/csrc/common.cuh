@@ -110,7 +110,6 @@ struct fans_ctx {
     uint64_t stencil_stamp = 0; // const_stamp the stencil tables were built for
     uint16_t ms_max = 0;
     int n_k = 0;
-    bool k_in_const = false;
     bool all_linear = false, any_history = false, any_flag = false;
     int *phase_lut = nullptr;   // device: phase id (ms value) -> dense index, size 65536 only when needed
     double g0[9];

@@ -58,6 +58,7 @@ int halo_add_down(fans_ctx *ctx, double *r);
 // comm.cu (slab exchanges over NCCL)
 int comm_check(fans_ctx *ctx);
 int comm_allreduce(fans_ctx *ctx, const double *in, double *out, int n, bool is_max);
+int comm_allreduce_int_max(fans_ctx *ctx, int *d_val);
 int comm_halo(fans_ctx *ctx, const void *to_prev, void *from_next, const void *to_next, void *from_prev, size_t bytes);
 int comm_alltoall(fans_ctx *ctx, const double2 *src, double2 *dst);
 int comm_map_peers(fans_ctx *ctx);

@@ -5,7 +5,6 @@
 #pragma once
 #include "common.cuh"
 
-#define FANS_CONST_K_DOUBLES 6144  // 48 KB of __constant__ for the phase stiffness table
 
 #define SQRT_HALF 7.071067811865476e-01          // include/matmodel.h:288
 #define SQRT_TWO_THIRDS 0.816496580927726        // sqrt(2/3)

@@ -22,8 +22,8 @@
 #define NELT ((TY + 1) * (TZ + 1))        // elements evaluated per plane
 #define SWEEP_THREADS (TY * TZ + 64)
 
-__constant__ double c_bg[9 * 3 * 8];  // basic gradient dN_a/dx_j at Gauss point g: [(g*3 + j)*8 + a]; g = 8: element centre
-__constant__ double c_K[FANS_CONST_K_DOUBLES];
+// No __constant__ tables: the basic gradients travel inside the kernel parameters (SweepParams::bg) and the phase stiffness table of
+// the fallback K.d sweep is read from the context's global-memory table, so two contexts never share mutable device state.
 
 enum { SW_LINEAR = 0, SW_RESIDUAL = 1, SW_STRAINSTRESS = 2 };
 
@@ -40,8 +40,9 @@ struct SweepParams {
     const PhaseDev *phases;
     int n_phases;
     const double *Kglob;     // phase stiffness table in global memory (used when it does not fit __constant__)
-    int n_k, k_const;
+    int n_k;
     double g0[9];
+    double bg[9 * 3 * 8];    // basic gradient dN_a/dx_j at Gauss point g: [(g*3 + j)*8 + a]; g = 8: element centre
     double vw;               // v_e / n_gp
     int ngp, bbar;
     double *hist, *hist_t;
@@ -78,7 +79,7 @@ __device__ __forceinline__ int wrapi(int v, int n)
     return v < 0 ? v + n : v;
 }
 
-template <int H, int NSTR, int MODE, bool KCONST>
+template <int H, int NSTR, int MODE>
 __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_sweep(const SweepParams p)
 {
     extern __shared__ double smem[];
@@ -186,28 +187,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
 #pragma unroll
                     for (int c = 0; c < H; ++c) ue[H * i + c] -= u0[c];
                 const int kidx = p.phases[ph].k_index;
-                if (KCONST) {
-                    for (int q = 0; q < p.n_k; ++q) {
-                        if (kidx == q) {
-                            const double *Kq = c_K + q * (ND * ND);
-#pragma unroll
-                            for (int i = 0; i < ND; ++i) {
-                                double a = 0.0;
-#pragma unroll
-                                for (int j = H; j < ND; ++j) a = fma(Kq[i * ND + j], ue[j], a);
-                                stg[i * NELT + eidx] = a;
-                            }
-                        }
-                    }
-                } else {
-                    const double *Kq = p.Kglob + (size_t)kidx * (ND * ND);
+                const double *Kq = p.Kglob + (size_t)kidx * (ND * ND);
 #pragma unroll 1
-                    for (int i = 0; i < ND; ++i) {
-                        double a = 0.0;
+                for (int i = 0; i < ND; ++i) {
+                    double a = 0.0;
 #pragma unroll
-                        for (int j = H; j < ND; ++j) a = fma(__ldg(&Kq[i * ND + j]), ue[j], a);
-                        stg[i * NELT + eidx] = a;
-                    }
+                    for (int j = H; j < ND; ++j) a = fma(__ldg(&Kq[i * ND + j]), ue[j], a);
+                    stg[i * NELT + eidx] = a;
                 }
             } else {
                 if (MODE == SW_RESIDUAL) {
@@ -233,13 +219,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
 #pragma unroll
                     for (int a = 0; a < 8; ++a) {
                         if (NSTR == 6) {
-                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], ue[H * a + 0], t);
-                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], ue[H * a + (H > 1 ? 1 : 0)], t);
-                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], ue[H * a + (H > 2 ? 2 : 0)], t);
+                            t = fma(p.bg[(8 * 3 + 0) * 8 + a], ue[H * a + 0], t);
+                            t = fma(p.bg[(8 * 3 + 1) * 8 + a], ue[H * a + (H > 1 ? 1 : 0)], t);
+                            t = fma(p.bg[(8 * 3 + 2) * 8 + a], ue[H * a + (H > 2 ? 2 : 0)], t);
                         } else {
-                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], ue[H * a], t);
-                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], ue[H * a], t);
-                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], ue[H * a], t);
+                            t = fma(p.bg[(8 * 3 + 0) * 8 + a], ue[H * a], t);
+                            t = fma(p.bg[(8 * 3 + 1) * 8 + a], ue[H * a], t);
+                            t = fma(p.bg[(8 * 3 + 2) * 8 + a], ue[H * a], t);
                         }
                     }
                     mc = t * (1.0 / 3.0);
@@ -273,7 +259,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                         }
                         hs.s = hmine + (size_t)(g & 1) * FANS_HIST_STAGE_SLOTS * SWEEP_THREADS;
                     }
-                    const double *bg = c_bg + g * 24;
+                    const double *bg = p.bg + g * 24;
                     double Hm[H][3];
 #pragma unroll
                     for (int c = 0; c < H; ++c)
@@ -330,7 +316,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (MODE == SW_LINEAR) ? 2 : 1) k_
                         for (int i = 0; i < NSTR; ++i) sq[i] = (i < 3) ? Qsum : 0.0;
                         double Tm[H][3];
                         stress_tensor<H, NSTR>(sq, Tm);
-                        const double *bc = c_bg + 8 * 24;
+                        const double *bc = p.bg + 8 * 24;
 #pragma unroll
                         for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -577,13 +563,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_sweep_sf(const SweepParams p)
                     for (int a = 0; a < 8; ++a) {
                         const int bx = a & 1, by = (a >> 1) & 1, bz = (a >> 2) & 1;
                         if (NSTR == 6) {
-                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
-                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN((H > 1 ? 1 : 0), bx, by, bz), t);
-                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN((H > 2 ? 2 : 0), bx, by, bz), t);
+                            t = fma(p.bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
+                            t = fma(p.bg[(8 * 3 + 1) * 8 + a], UN((H > 1 ? 1 : 0), bx, by, bz), t);
+                            t = fma(p.bg[(8 * 3 + 2) * 8 + a], UN((H > 2 ? 2 : 0), bx, by, bz), t);
                         } else {
-                            t = fma(c_bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
-                            t = fma(c_bg[(8 * 3 + 1) * 8 + a], UN(0, bx, by, bz), t);
-                            t = fma(c_bg[(8 * 3 + 2) * 8 + a], UN(0, bx, by, bz), t);
+                            t = fma(p.bg[(8 * 3 + 0) * 8 + a], UN(0, bx, by, bz), t);
+                            t = fma(p.bg[(8 * 3 + 1) * 8 + a], UN(0, bx, by, bz), t);
+                            t = fma(p.bg[(8 * 3 + 2) * 8 + a], UN(0, bx, by, bz), t);
                         }
                     }
                     mc = t * (1.0 / 3.0);
@@ -728,7 +714,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_sweep_sf(const SweepParams p)
                         for (int i = 0; i < NSTR; ++i) sq[i] = (i < 3) ? Qsum : 0.0;
                         double Tm[H][3];
                         stress_tensor<H, NSTR>(sq, Tm);
-                        const double *bc = c_bg + 8 * 24;
+                        const double *bc = p.bg + 8 * 24;
 #pragma unroll
                         for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -793,21 +779,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_sweep_sf(const SweepParams p)
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static uint64_t g_const_stamp = 0;  // which ctx content currently sits in c_bg / c_K
 static uint64_t g_stamp_counter = 0;
 
-uint64_t sweep_new_stamp() { return ++g_stamp_counter; }
-
-static int upload_constants(fans_ctx *ctx)
-{
-    if (g_const_stamp == ctx->const_stamp) return FANS_OK;
-    CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_bg, ctx->Bgp.data(), sizeof(double) * 9 * 24, 0, cudaMemcpyHostToDevice, ctx->st));
-    if (ctx->k_in_const && ctx->n_k > 0)
-        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_K, ctx->d_K, sizeof(double) * ctx->n_k * 64 * ctx->h * ctx->h, 0,
-                                              cudaMemcpyDeviceToDevice, ctx->st));
-    g_const_stamp = ctx->const_stamp;
-    return FANS_OK;
-}
+uint64_t sweep_new_stamp() { return ++g_stamp_counter; }   // identifies a context's material tables (stencil.cu rebuilds on change)
 
 template <int H, int NSTR, int MODE>
 static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t smem, bool sf)
@@ -828,13 +802,8 @@ static int launch_sweep(fans_ctx *ctx, const SweepParams &p, dim3 grid, size_t s
             return FANS_OK;
         }
     }
-    if (MODE == SW_LINEAR && ctx->k_in_const) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_sweep<H, NSTR, MODE, true><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
-    } else {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_sweep<H, NSTR, MODE, false><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
-    }
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep<H, NSTR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sweep<H, NSTR, MODE><<<grid, SWEEP_THREADS, smem, ctx->st>>>(p);
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
@@ -849,7 +818,6 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
         fans_set_error(ctx, FANS_ERR_STATE, "microstructure and materials must be set before an element sweep");
         return FANS_ERR_STATE;
     }
-    FANS_CHECK(upload_constants(ctx));
     SweepParams p;
     memset(&p, 0, sizeof(p));
     double *red_final = nullptr;
@@ -874,8 +842,8 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.n_phases = ctx->n_phases;
     p.Kglob = ctx->d_K;
     p.n_k = ctx->n_k;
-    p.k_const = ctx->k_in_const;
     for (int i = 0; i < 9; ++i) p.g0[i] = ctx->g0[i];
+    for (int i = 0; i < 9 * 24; ++i) p.bg[i] = ctx->Bgp[i];
     p.vw = ctx->ve / ctx->ngp;
     p.ngp = ctx->ngp;
     p.bbar = (ctx->fe == FANS_FE_BBAR);
