@@ -224,8 +224,11 @@ static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const
     int grid = FANS_SMS * resident;
     if (const char *env = getenv("FANS_XG_GRID")) grid = atoi(env);
     if (grid > nWork) grid = nWork;
-    const char *pf = getenv("FANS_XG_PF");   // 0: plain loads at the start of every component (A/B runs)
-    if (pf && atoi(pf) == 0) k_fft_xg_seq<N, T, false><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
+    // prefetch into the idle tiles pays with 128-byte rows (T = 8: 2.75 -> 2.63 ms at n_x = 512); with the 64-byte rows of n_x = 1024
+    // the extra barrier per component costs more than the hidden latency (3.42 -> 3.70 ms on the 8-GPU run), so it stays off there
+    const char *pf = getenv("FANS_XG_PF");   // 0 / 1: force plain loads / prefetch (A/B runs)
+    const bool use_pf = pf ? atoi(pf) != 0 : (T == 8);
+    if (!use_pf) k_fft_xg_seq<N, T, false><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
     else k_fft_xg_seq<N, T, true><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
     return FANS_OK;
 }
