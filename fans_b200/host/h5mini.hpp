@@ -4,7 +4,9 @@
 //   superblock v0/v1, old-style groups (symbol table: v1 B-tree + local heap) and new-style compact groups (link messages),
 //   v1 object headers incl. continuation blocks,
 //   dataspace v1/v2, fixed-point datatypes of 1/2/4/8 bytes (little endian), data layout v3 contiguous or chunked
-//   (v1 chunk B-tree, any number of chunks), optional deflate filter, string attribute `permute_order`.
+//   (v1 chunk B-tree, any number of chunks), optional deflate filter, string attribute `permute_order`;
+//   compact (in-header) attributes of a dataset, message versions 1-3: integer scalars and fixed- or variable-length strings
+//   (h5mini_read_attributes: what GBDiffusion reads — num_crystals, num_GB, GBVoxelInfo; GBDiffusion.h:51-58).
 // Anything else is reported as an error string, never guessed.
 #pragma once
 #include <zlib.h>
@@ -12,6 +14,7 @@
 #include <cstdint>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -317,6 +320,102 @@ inline bool h5mini_read_dataset(const std::string &file, const std::string &data
             uint64_t v = 0;
             for (int k = 0; k < elem; ++k) v |= (uint64_t)raw[i * elem + k] << (8 * k);
             data[i] = (uint16_t)v;
+        }
+        return true;
+    } catch (const std::out_of_range &) {
+        err = "truncated or malformed file";
+        return false;
+    }
+}
+
+// Attributes stored in the object header of `dataset`: integers as decimal text in `ints`, strings in `strs`.  Attributes in dense
+// storage (fractal heap) or of other types are skipped; `err` is only set when the file / dataset itself cannot be read.
+struct H5Attrs {
+    std::map<std::string, long long> ints;
+    std::map<std::string, std::string> strs;
+};
+
+inline bool h5mini_read_attributes(const std::string &file, const std::string &dataset, H5Attrs &out, std::string &err)
+{
+    using namespace h5mini;
+    File f;
+    {
+        std::ifstream in(file, std::ios::binary);
+        if (!in) {
+            err = "cannot open file";
+            return false;
+        }
+        f.b.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+    }
+    try {
+        static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+        if (f.b.size() < 96 || std::memcmp(f.b.data(), sig, 8) != 0 || f.b[8] > 1) {
+            err = "not an HDF5 file with a version 0/1 superblock";
+            return false;
+        }
+        f.so = f.b[13];
+        f.sl = f.b[14];
+        size_t p = 24 + (f.b[8] == 1 ? 4 : 0) + 4 * (size_t)f.so;
+        uint64_t obj = f.rd(p + f.so, f.so);
+        size_t s = 0;
+        while (s < dataset.size()) {
+            while (s < dataset.size() && dataset[s] == '/') ++s;
+            size_t e = dataset.find('/', s);
+            if (e == std::string::npos) e = dataset.size();
+            if (e > s) {
+                uint64_t child = 0;
+                if (!group_lookup(f, obj, dataset.substr(s, e - s), child, err)) return false;
+                obj = child;
+            }
+            s = e;
+        }
+        std::vector<Msg> msgs;
+        if (!object_messages(f, obj, msgs, err)) return false;
+        for (const Msg &m : msgs) {
+            if (m.type != 0x0c) continue;
+            const int v = f.b.at(m.pos);
+            if (v < 1 || v > 3) continue;
+            const size_t nsz = (size_t)f.rd(m.pos + 2, 2), tsz = (size_t)f.rd(m.pos + 4, 2), ssz = (size_t)f.rd(m.pos + 6, 2);
+            size_t q = m.pos + 8 + (v == 3 ? 1 : 0);   // v3: + name character-set encoding
+            auto adv = [&](size_t n) { return v == 1 ? (n + 7) / 8 * 8 : n; };   // v1 pads every part to 8 bytes
+            const std::string name((const char *)&f.b.at(q));
+            q += adv(nsz);
+            const size_t tpos = q;
+            q += adv(tsz);
+            const size_t spos = q;
+            q += adv(ssz);
+            const int cls = f.b.at(tpos) & 0x0f;
+            const size_t tsize = (size_t)f.rd(tpos + 4, 4);
+            const int srank = f.b.at(spos + 1);
+            if (srank > 1) continue;
+            if (cls == 0 && tsize >= 1 && tsize <= 8) {          // fixed-point scalar (sign-extended)
+                uint64_t raw = f.rd(q, (int)tsize);
+                const bool is_signed = (f.b.at(tpos + 1) & 0x08) != 0;
+                long long val = (long long)raw;
+                if (is_signed && tsize < 8 && (raw >> (8 * tsize - 1)) & 1) val = (long long)(raw | (~0ULL << (8 * tsize)));
+                out.ints[name] = val;
+            } else if (cls == 3) {                                // fixed-length string
+                std::string val;
+                for (size_t i = 0; i < tsize && f.b.at(q + i) != 0; ++i) val.push_back((char)f.b.at(q + i));
+                out.strs[name] = val;
+            } else if (cls == 9) {                                // variable length: {length, global heap collection, index}
+                const uint32_t len = (uint32_t)f.rd(q, 4);
+                const uint64_t gcol = f.rd(q + 4, f.so);
+                const uint32_t index = (uint32_t)f.rd(q + 4 + f.so, 4);
+                if (std::memcmp(&f.b.at(gcol), "GCOL", 4) != 0) continue;
+                const uint64_t csize = f.rd(gcol + 8, f.sl);
+                size_t o = gcol + 8 + f.sl;
+                while (o + 8 + f.sl <= gcol + csize) {
+                    const uint32_t oi = (uint32_t)f.rd(o, 2);
+                    const uint64_t osz = f.rd(o + 8, f.sl);
+                    if (oi == 0) break;   // free space object ends the collection
+                    if (oi == index) {
+                        out.strs[name] = std::string((const char *)&f.b.at(o + 8 + f.sl), std::min<size_t>(len, (size_t)osz));
+                        break;
+                    }
+                    o += 8 + f.sl + (size_t)((osz + 7) / 8 * 8);
+                }
+            }
         }
         return true;
     } catch (const std::out_of_range &) {

@@ -46,6 +46,8 @@ struct Dataset {
     std::vector<uint64_t> dims;
     uint64_t addr = 0, nbytes = 0;
     std::string attr_name, attr_value;  // optional scalar string attribute (value stored with its terminating NUL)
+    std::vector<std::pair<std::string, std::string>> str_attrs;   // further scalar string attributes
+    std::vector<std::pair<std::string, long long>> int_attrs;     // scalar 64-bit integer attributes (e.g. num_crystals, GBDiffusion.h:54-55)
 };
 
 struct Group {
@@ -81,8 +83,8 @@ class Writer {
         throw std::runtime_error("h5write: unsupported element type " + dt);
     }
     // path = "/a/b/name"; raw data is appended to the file now
-    void add_dataset(const std::string &path, const std::string &dtype, const std::vector<uint64_t> &dims, const void *data,
-                     const std::string &attr_name = "", const std::string &attr_value = "")
+    Dataset &add_dataset(const std::string &path, const std::string &dtype, const std::vector<uint64_t> &dims, const void *data,
+                         const std::string &attr_name = "", const std::string &attr_value = "")
     {
         if (!f_) throw std::runtime_error("h5write: file already closed");
         std::vector<std::string> parts;
@@ -114,6 +116,7 @@ class Writer {
         d.addr = pos_;
         put(data, d.nbytes);
         g->dsets[name] = d;
+        return g->dsets[name];   // std::map nodes are stable: the caller may add attributes until close()
     }
     void close()
     {
@@ -293,6 +296,52 @@ class Writer {
             x.zeros(7);
             x.bytes(d.attr_value.c_str(), vlen);
             x.pad8();
+            msg_header(m, 0x000c, x.b.size(), 0);
+            m.bytes(x.b.data(), x.b.size());
+            ++nmsg;
+        }
+        for (const auto &kv : d.str_attrs) {   // more scalar fixed-length strings, same encoding as above
+            Buf x;
+            const size_t nlen = kv.first.size() + 1, vlen = kv.second.size() + 1;
+            if (vlen > 60000) throw std::runtime_error("h5write: attribute '" + kv.first + "' does not fit an object header message");
+            x.u8(1);
+            x.u8(0);
+            x.le(nlen, 2);
+            x.le(8, 2);
+            x.le(8, 2);
+            x.bytes(kv.first.c_str(), nlen);
+            x.pad8();
+            x.u8(0x13);
+            x.zeros(3);
+            x.le(vlen, 4);
+            x.u8(1);
+            x.zeros(7);
+            x.bytes(kv.second.c_str(), vlen);
+            x.pad8();
+            msg_header(m, 0x000c, x.b.size(), 0);
+            m.bytes(x.b.data(), x.b.size());
+            ++nmsg;
+        }
+        for (const auto &kv : d.int_attrs) {   // scalar little-endian signed 64-bit integers
+            Buf x;
+            const size_t nlen = kv.first.size() + 1;
+            x.u8(1);
+            x.u8(0);
+            x.le(nlen, 2);
+            x.le(12, 2);  // datatype message: 8 bytes + 4 bytes of fixed-point properties
+            x.le(8, 2);
+            x.bytes(kv.first.c_str(), nlen);
+            x.pad8();
+            x.u8(0x10);   // version 1, class 0 (fixed point)
+            x.u8(0x08);   // little endian, signed
+            x.zeros(2);
+            x.le(8, 4);   // size
+            x.le(0, 2);   // bit offset
+            x.le(64, 2);  // precision
+            x.pad8();
+            x.u8(1);      // dataspace version 1, rank 0
+            x.zeros(7);
+            x.le((uint64_t)kv.second, 8);
             msg_header(m, 0x000c, x.b.size(), 0);
             m.bytes(x.b.data(), x.b.size());
             ++nmsg;

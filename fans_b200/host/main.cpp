@@ -118,6 +118,26 @@ static int h5_selftest(const char *file)
     return 0;
 }
 
+// writes a small grain-boundary image with the dataset attributes GBDiffusion reads (num_crystals, num_GB, GBVoxelInfo;
+// GBDiffusion.h:51-69): 2 crystals (tags 0, 1) separated by two one-voxel boundary layers (tags 2, 3) with oblique normals.
+// tests/test_host_cpp.py reads it back through the JSON front end (--describe).  No GPU needed.
+static int gb_selftest(const char *file)
+{
+    const size_t X = 8, Y = 4, Z = 4;
+    std::vector<uint16_t> ms(Z * Y * X);   // on disk [z][y][x]
+    for (size_t z = 0; z < Z; ++z)
+        for (size_t y = 0; y < Y; ++y)
+            for (size_t x = 0; x < X; ++x) ms[(z * Y + y) * X + x] = (uint16_t)(x < 3 ? 0 : (x == 3 ? 2 : (x < 7 ? 1 : 3)));
+    h5w::Writer w(file);
+    h5w::Dataset &d = w.add_dataset("/gb/image", "u16", {Z, Y, X}, ms.data());
+    d.int_attrs.push_back({"num_crystals", 2});
+    d.int_attrs.push_back({"num_GB", 2});
+    d.str_attrs.push_back({"GBVoxelInfo", "{\"a\": {\"GB_tag\": 2, \"GB_normal\": [1.0, 0.0, 0.0]}, "
+                                          "\"b\": {\"GB_tag\": 3, \"GB_normal\": [0.6, 0.8, 0.0]}}"});
+    w.close();
+    return 0;
+}
+
 // ---- slab world: rank / size from the environment, NCCL id through a file (the role MPI_Init + MPI_Bcast play in the reference) ----
 static int env_int(std::initializer_list<const char *> names, int dflt)
 {
@@ -259,6 +279,7 @@ int main(int argc, char **argv)
             return describe(reader);
         }
         if (argc == 3 && std::strcmp(argv[1], "--h5selftest") == 0) return h5_selftest(argv[2]);
+        if (argc == 3 && std::strcmp(argv[1], "--gbselftest") == 0) return gb_selftest(argv[2]);
         if (argc != 3 && argc != 7) {
             fprintf(stderr, "Usage: %s <input_file.json> <results_dir | results.h5> [ms.u16 nx ny nz]\n", argv[0]);
             return 10;

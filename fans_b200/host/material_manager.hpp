@@ -69,7 +69,7 @@ class MaterialManager {
         if (n_phases == 0) throw std::runtime_error("MaterialManager: No phases defined");
         phase_to_info.assign(n_phases, MaterialInfo());
         for (const Json &mg : groups) {
-            models.push_back(createMatmodel(howmany, n_str, mg["matmodel"].as_string(), mg["material_properties"]));
+            models.push_back(createMatmodel(howmany, n_str, mg["matmodel"].as_string(), mg["material_properties"], reader.ms_filename, reader.ms_datasetname));
             Matmodel *model = models.back().get();
             auto *lin = dynamic_cast<LinearModelBase *>(model);
             const bool is_linear = lin != nullptr;

@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include "h5mini.hpp"
+
 #include "../../include/fans_gpu.h"
 #include "json.hpp"
 
@@ -128,6 +130,83 @@ class LinearThermalTriclinic : public LinearModelBase {  // LinearThermal.h:48-1
         Mat k(3, 3);
         for (const auto &m : K_mats)
             for (int q = 0; q < 9; ++q) k.a[q] += m.a[q];
+        for (auto &v : k.a) v /= n_mat;
+        return k;
+    }
+};
+
+// GBDiffusion (GBDiffusion.h:45-175): polycrystal diffusion, a LinearModel — isotropic D_bulk in the crystals (tags 0..num_crystals-1),
+// transversely isotropic D_par (I - N N^T) + D_perp N N^T in the grain-boundary phases.  num_crystals, num_GB and the boundary normals
+// (GBVoxelInfo, a JSON text) are attributes of the microstructure dataset (GBDiffusion.h:51-69); images without HDF5 attributes
+// (.npy / raw) may carry the same three entries as "num_crystals", "num_GB", "GBVoxelInfo" inside material_properties (extension).
+// On the device this is FANS_MAT_LINEAR with one tangent per tag (the stencil's coefficient-table path takes any number of them).
+// Note: the reference evaluates get_sigma with the normals as stored and phase_stiffness with the normalised ones
+// (GBDiffusion.h:109-111 vs :137-161); unit normals (what MSUtils writes) make the two agree, and only those are supported here.
+class GBDiffusion : public LinearModelBase {
+  public:
+    long long num_crystals = 0, num_GB = 0;
+    vector<double> GBnormals, D_bulk, D_par, D_perp;
+    GBDiffusion(const Json &props, const string &ms_file, const string &ms_dataset) : LinearModelBase(1, 3)
+    {
+        try {
+            Json info;
+            H5Attrs at;
+            string err;
+            const bool have = !ms_file.empty() && h5mini_read_attributes(ms_file, ms_dataset, at, err) && at.ints.count("num_crystals") &&
+                              at.ints.count("num_GB") && at.strs.count("GBVoxelInfo");
+            if (have) {
+                num_crystals = at.ints["num_crystals"], num_GB = at.ints["num_GB"];
+                info = Json::parse(at.strs["GBVoxelInfo"]);
+            } else if (props.contains("num_crystals") && props.contains("num_GB") && props.contains("GBVoxelInfo")) {
+                num_crystals = props.at("num_crystals").as_int(), num_GB = props.at("num_GB").as_int();
+                info = props.at("GBVoxelInfo");
+            } else {
+                throw std::runtime_error("attributes num_crystals / num_GB / GBVoxelInfo not found on the microstructure dataset" +
+                                         (err.empty() ? string() : " (" + err + ")"));
+            }
+            n_mat = (int)(num_crystals + num_GB);
+            GBnormals.assign((size_t)n_mat * 3, 0.0);
+            for (const auto &kv : info.obj) {
+                const int tag = kv.second.at("GB_tag").as_int();
+                const vector<double> nrm = kv.second.at("GB_normal").as_vector();
+                if (tag < 0 || tag >= n_mat || nrm.size() != 3) throw std::runtime_error("bad GB_tag / GB_normal entry");
+                for (int d = 0; d < 3; ++d) GBnormals[(size_t)tag * 3 + d] = nrm[d];
+            }
+            D_bulk.assign(n_mat, 0.0), D_par.assign(n_mat, 0.0), D_perp.assign(n_mat, 0.0);
+            if (props.at("GB_unformity").as_bool()) {
+                std::fill_n(D_bulk.begin(), num_crystals, props.at("D_bulk").as_double());
+                std::fill_n(D_par.begin() + num_crystals, num_GB, props.at("D_par").as_double());
+                std::fill_n(D_perp.begin() + num_crystals, num_GB, props.at("D_perp").as_double());
+            } else {
+                const vector<double> b = props.at("D_bulk").as_vector(), pa = props.at("D_par").as_vector(), pe = props.at("D_perp").as_vector();
+                for (int i = 0; i < n_mat; ++i) D_bulk[i] = b.at(i), D_par[i] = pa.at(i), D_perp[i] = pe.at(i);
+            }
+        } catch (const std::exception &e) {
+            throw std::runtime_error("Error in GBDiffusion initialization: " + string(e.what()));
+        }
+    }
+    Mat phase_kappa(int i) const override
+    {
+        Mat k = Mat::identity(3);
+        if (i < num_crystals) {
+            for (auto &v : k.a) v *= D_bulk[i];
+            return k;
+        }
+        double n[3] = {GBnormals[3 * i], GBnormals[3 * i + 1], GBnormals[3 * i + 2]};
+        const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (len > 0)
+            for (double &c : n) c /= len;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) k(r, c) = D_par[i] * ((r == c ? 1.0 : 0.0) - n[r] * n[c]) + D_perp[i] * n[r] * n[c];
+        return k;
+    }
+    Mat get_reference_stiffness() const override  // kappa_average, GBDiffusion.h:120-122
+    {
+        Mat k(3, 3);
+        for (int i = 0; i < n_mat; ++i) {
+            const Mat m = phase_kappa(i);
+            for (int q = 0; q < 9; ++q) k.a[q] += m.a[q];
+        }
         for (auto &v : k.a) v /= n_mat;
         return k;
     }
@@ -404,11 +483,13 @@ class CompressibleNeoHookean : public LargeStrainMechModel {  // CompressibleNeo
 };
 
 // createMatmodel: include/setup.h:21-73
-static inline std::unique_ptr<Matmodel> createMatmodel(int howmany, int n_str, const string &name, const Json &props)
+static inline std::unique_ptr<Matmodel> createMatmodel(int howmany, int n_str, const string &name, const Json &props,
+                                                       const string &ms_file = "", const string &ms_dataset = "")
 {
     if (howmany == 1 && n_str == 3) {
         if (name == "LinearThermalIsotropic") return std::make_unique<LinearThermalIsotropic>(props);
         if (name == "LinearThermalTriclinic") return std::make_unique<LinearThermalTriclinic>(props);
+        if (name == "GBDiffusion") return std::make_unique<GBDiffusion>(props, ms_file, ms_dataset);
         throw std::invalid_argument(name + " is not a valid matmodel for thermal problem");
     }
     if (howmany == 3 && n_str == 6) {

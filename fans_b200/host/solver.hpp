@@ -314,6 +314,18 @@ class Solver {
             if (ncomp > 1) d.push_back(ncomp);
             sink.write(nm, load_idx, time_idx, "f64", d, buf.data(), true);
         };
+        if (want("GBnormals")) {  // GBDiffusion::postprocess (GBDiffusion.h:163-175): the boundary normal of every voxel's tag
+            for (const auto &mdl : matmanager->models)
+                if (auto *gb = dynamic_cast<GBDiffusion *>(mdl.get())) {
+                    std::vector<double> nf(N * 3, 0.0);
+                    for (size_t e = 0; e < N; ++e) {
+                        const size_t tag = reader.ms[e];
+                        if (tag * 3 + 2 < gb->GBnormals.size())
+                            for (int dcomp = 0; dcomp < 3; ++dcomp) nf[e * 3 + dcomp] = gb->GBnormals[tag * 3 + dcomp];
+                    }
+                    sink.write("GBnormals", load_idx, time_idx, "f64", gd(3), nf.data(), true);
+                }
+        }
         try_field_gp("plastic_strain_gp", 6);
         try_field_gp("isotropic_hardening_variable_gp", 1);
         try_field_gp("kinematic_hardening_variable_gp", 6);
@@ -338,7 +350,7 @@ class Solver {
                                       "phase_strain_average", "absolute_error", "microstructure", "displacement_fluctuation", "displacement",
                                       "residual", "mpi_rank", "plastic_flag", "plastic_strain", "isotropic_hardening_variable",
                                       "kinematic_hardening_variable", "plastic_strain_gp", "isotropic_hardening_variable_gp",
-                                      "kinematic_hardening_variable_gp", "homogenized_tangent"};
+                                      "kinematic_hardening_variable_gp", "homogenized_tangent", "GBnormals"};
         for (const std::string &r : results) {
             bool ok = false;
             for (const char *k : known) ok = ok || r == k;

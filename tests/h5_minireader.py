@@ -131,8 +131,10 @@ class H5File:
                 q += (dtl + 7) // 8 * 8
                 assert self.b[q] == 1 and self.b[q + 1] == 0, "only scalar attributes"
                 q += (dsl + 7) // 8 * 8
-                assert adt[0] == "S"
-                attrs[name] = self.b[q:q + adt[1]].split(b"\0")[0].decode()
+                if adt[0] == "S":
+                    attrs[name] = self.b[q:q + adt[1]].split(b"\0")[0].decode()
+                else:   # scalar integer attribute (num_crystals / num_GB of a grain-boundary image)
+                    attrs[name] = int(np.frombuffer(self.b, dtype=adt, count=1, offset=q)[0])
         if dims is None or dtype is None or layout is None:
             return None, attrs
         if layout[0] != 1:

@@ -120,3 +120,58 @@ def test_h5_results_writer(exe, tmp_path):
     ref = "/root/reference/test/microstructures/sphere32.h5"
     if os.path.exists(ref):
         assert list(h5.H5File(ref).walk()) == ["/sphere/32x32x32/ms"]
+
+
+def gb_expected():
+    normals = {2: np.array([1.0, 0.0, 0.0]), 3: np.array([0.6, 0.8, 0.0])}
+    D_bulk, D_par, D_perp = 1.5, 4.0, 0.25
+    kap = [D_bulk * np.eye(3), D_bulk * np.eye(3)]
+    for t in (2, 3):
+        n = normals[t]
+        kap.append(D_par * (np.eye(3) - np.outer(n, n)) + D_perp * np.outer(n, n))
+    return kap
+
+
+def gb_cfg(path, props_extra=None):
+    props = {"GB_unformity": True, "D_bulk": 1.5, "D_par": 4.0, "D_perp": 0.25}
+    props.update(props_extra or {})
+    return {"microstructure": {"filepath": path, "datasetname": "/gb/image", "L": [2.0, 1.0, 1.0]}, "problem_type": "thermal",
+            "materials": [{"phases": [0, 1, 2, 3], "matmodel": "GBDiffusion", "material_properties": props}], "FE_type": "HEX8",
+            "method": "cg", "error_parameters": {"measure": "Linfinity", "type": "absolute", "tolerance": 1e-10}, "n_it": 100,
+            "macroscale_loading": [[[0.01, 0.02, -0.01]]], "results": ["stress_average", "GBnormals"]}
+
+
+def test_gbdiffusion_reads_dataset_attributes(exe, tmp_path):
+    """GBDiffusion (GBDiffusion.h:45-135): num_crystals / num_GB / GBVoxelInfo come from the attributes of the microstructure dataset
+    (written here by the repo's own HDF5 writer, read back by the independent mini reader and by the C++ front end); the phase
+    tangents are D_bulk I in the crystals and D_par (I - N N^T) + D_perp N N^T in the boundary phases, kapparef their mean."""
+    import h5_minireader as h5
+    f = tmp_path / "gb.h5"
+    assert subprocess.run([exe, "--gbselftest", str(f)]).returncode == 0
+    img, attrs = h5.H5File(str(f)).walk()["/gb/image"]
+    assert img.shape == (4, 4, 8) and attrs["num_crystals"] == 2 and attrs["num_GB"] == 2 and "GB_normal" in attrs["GBVoxelInfo"]
+    inp = tmp_path / "in.json"
+    inp.write_text(json.dumps(gb_cfg(str(f))))
+    out = subprocess.run([exe, "--describe", str(inp)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout)
+    kap = gb_expected()
+    assert (d["howmany"], d["n_str"], d["n_phases"], d["all_linear"], d["dims"]) == (1, 3, 4, True, [8, 4, 4])
+    for got, want in zip(d["phases"], kap):
+        assert got["model"] == 0 and np.allclose(np.array(got["params"][:9]).reshape(3, 3), want, rtol=1e-14, atol=1e-15)
+    assert np.allclose(np.array(d["kapparef"]).reshape(3, 3), sum(kap) / 4, rtol=1e-14)
+    # the same through material_properties for images without HDF5 attributes (.npy / raw)
+    ms = np.zeros((8, 4, 4), dtype=np.uint16)
+    ms[3], ms[4:7], ms[7] = 2, 1, 3
+    raw = tmp_path / "gb.u16"
+    ms.tofile(raw)
+    info = {"a": {"GB_tag": 2, "GB_normal": [1.0, 0.0, 0.0]}, "b": {"GB_tag": 3, "GB_normal": [0.6, 0.8, 0.0]}}
+    inp.write_text(json.dumps(gb_cfg("unused.h5", {"num_crystals": 2, "num_GB": 2, "GBVoxelInfo": info})))
+    out = subprocess.run([exe, "--describe", str(inp), str(raw), "8", "4", "4"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    d2 = json.loads(out.stdout)
+    assert d2["phases"] == d["phases"] and d2["kapparef"] == d["kapparef"]
+    # no attributes, no fallback entries: the reference's error text
+    inp.write_text(json.dumps(gb_cfg("unused.h5")))
+    out = subprocess.run([exe, "--describe", str(inp), str(raw), "8", "4", "4"], capture_output=True, text=True)
+    assert out.returncode != 0 and "Error in GBDiffusion initialization" in out.stderr

@@ -152,3 +152,35 @@ def test_cli_two_ranks(tmp_path):
         assert abs(len(l2a("absolute_error", t)) - len(l1("absolute_error", t))) <= 1
         both = np.concatenate([l2a("stress", t), l2b("stress", t)], axis=0)
         assert both.shape == (32, 32, 32, 6) and rel_err(both, l1("stress", t)) < 1e-8
+
+
+def test_cli_gbdiffusion(tmp_path):
+    """GBDiffusion end to end: image + attributes from an HDF5 file, 4 tags (2 crystals, 2 boundary phases with oblique normals), solved
+    on the GPU through FANS_gpu; the oracle solves the same problem as LinearThermalTriclinic with the equivalent tensors."""
+    import fans_oracle as fo
+    import test_host_cpp as th
+    exe = cpp_host.build()
+    f = tmp_path / "gb.h5"
+    assert subprocess.run([exe, "--gbselftest", str(f)]).returncode == 0
+    cfg = th.gb_cfg(str(f))
+    inp = tmp_path / "in.json"
+    inp.write_text(json.dumps(cfg))
+    out = tmp_path / "res"
+    r = subprocess.run([exe, str(inp), str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    index = [json.loads(l) for l in open(out / "index.jsonl")]
+    e = [i for i in index if i["name"] == "stress_average"][0]
+    q = np.fromfile(str(out) + e["path"], dtype=np.float64)
+    kap = th.gb_expected()
+    keys = {"K_11": (0, 0), "K_12": (0, 1), "K_13": (0, 2), "K_22": (1, 1), "K_23": (1, 2), "K_33": (2, 2)}
+    mats = [{"phases": [0, 1, 2, 3], "matmodel": "LinearThermalTriclinic",
+             "material_properties": {k: [float(t[ij]) for t in kap] for k, ij in keys.items()}}]
+    ms = np.zeros((8, 4, 4), dtype=np.uint16)
+    ms[3], ms[4:7], ms[7] = 2, 1, 3
+    sol = fo.OracleSolver(ms, [2.0, 1.0, 1.0], "thermal", mats, "HEX8", "cg", "small", cfg["error_parameters"], 100)
+    sol.set_gradient([0.01, 0.02, -0.01])
+    sol.solve()
+    assert rel_err(q, sol.get_homogenized_stress()) < 1e-9
+    g = [i for i in index if i["name"] == "GBnormals"][0]
+    nf = np.fromfile(str(out) + g["path"], dtype=np.float64).reshape(8, 4, 4, 3)
+    assert np.allclose(nf[7, 0, 0], [0.6, 0.8, 0.0]) and np.allclose(nf[3, 1, 2], [1.0, 0.0, 0.0]) and not nf[0].any()
