@@ -866,7 +866,18 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     p.sig_gp = sig_gp;
     // x chunking: enough CTAs to fill 148 SMs a few times over, at most ~6% redundant plane loads
     // the 8-point elements take the sum-factorised kernel (FANS_SWEEP_DENSE=1: the dense B products of k_sweep, for A/B runs)
-    const bool sf = mode != SW_LINEAR && ctx->ngp == 8 && !(getenv("FANS_SWEEP_DENSE") && atoi(getenv("FANS_SWEEP_DENSE")) != 0);
+    bool sf = mode != SW_LINEAR && ctx->ngp == 8 && !(getenv("FANS_SWEEP_DENSE") && atoi(getenv("FANS_SWEEP_DENSE")) != 0);
+    // Element averages of a LINEAR law on an 8-point element are exactly the values at the element centre: the Gauss points are
+    // symmetric about it, the gradient is trilinear, the stress is linear in it (and B-bar only moves the volumetric part, whose
+    // average is the centre value by construction).  The strain/stress sweep of an all-linear problem (homogenized stress,
+    // postprocess averages) therefore evaluates one point per element — 1/8 of the law and gradient work — unless the
+    // Gauss-point fields themselves are asked for.  (FANS_SS_FULL=1 keeps the 8-point evaluation, for A/B runs and tests.)
+    if (mode == SW_STRAINSTRESS && ctx->all_linear && ctx->ngp == 8 && !eps_gp && !sig_gp && !(getenv("FANS_SS_FULL") && atoi(getenv("FANS_SS_FULL")))) {
+        sf = false;
+        p.ngp = 1;
+        p.bbar = 0;
+        for (int i = 0; i < 24; ++i) p.bg[i] = ctx->Bgp[8 * 24 + i];
+    }
     const int ty = sf ? FY : TY, tz = sf ? FZ : TZ;
     const int gy = (ctx->ny + ty - 1) / ty, gz = (ctx->nz + tz - 1) / tz;
     int xchunk = ctx->n0;

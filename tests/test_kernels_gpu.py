@@ -225,3 +225,32 @@ def test_polycrystal_many_triclinic_phases(problem, n_ph):
     assert rel_err(ctx.homogenized_stress(), sol.get_homogenized_stress()) < SCALAR_TOL
     assert rel_err(ctx.download("u"), sol.u) < FIELD_TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("fe", ["HEX8", "BBAR"])
+@pytest.mark.parametrize("problem,materials", [("thermal", THERMAL), ("mechanical", ELASTIC)])
+def test_linear_strain_stress_one_point_rule(problem, materials, fe):
+    """All-linear problems evaluate the strain/stress sweep at the element centre only (sweep.cu): exactly the Gauss-point average
+    (matmodel.h:202-225) for a linear law on a trilinear element — compared with the full 8-point evaluation and with the oracle."""
+    import os
+    if problem == "thermal" and fe == "BBAR":
+        pytest.skip("B-bar only changes mechanical elements")
+    sol, ctx = make(problem, materials, fe, (16, 8, 32))
+    rng = np.random.default_rng(7)
+    u = rng.standard_normal(ctx.field_shape) * 1e-3
+    g0 = np.array(G0[sol.n_str])
+    ctx.upload("u", u)
+    ctx.set_gradient(g0)
+    sol.set_gradient(g0)
+    sol.u = u.copy()
+    e1, s1 = ctx.strain_stress()
+    h1 = ctx.homogenized_stress()
+    os.environ["FANS_SS_FULL"] = "1"
+    e8, s8 = ctx.strain_stress()
+    h8 = ctx.homogenized_stress()
+    del os.environ["FANS_SS_FULL"]
+    assert rel_err(e1, e8) < 1e-13 and rel_err(s1, s8) < 1e-13 and rel_err(h1, h8) < 1e-13
+    eo, so = sol.strain_stress()[:2]
+    assert rel_err(e1, eo.reshape(e1.shape)) < 1e-12 and rel_err(s1, so.reshape(s1.shape)) < 1e-12
+    assert rel_err(h1, sol.get_homogenized_stress()) < 1e-12
+    ctx.close()
