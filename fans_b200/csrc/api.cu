@@ -361,6 +361,11 @@ static int create_rest(fans_ctx *ctx)
         ctx->y_grid = 96;  // SMs given to an NVLink-bound y pass while a z pass runs beside it (4 GPUs, 512x1024x1024: 64 -> 21.16, 96 -> 20.54, 120 -> 20.98, no pipeline 21.83 ms/iteration)
         if (const char *e = getenv("FANS_PIPE")) ctx->pipe = atoi(e) ? 1 : 0;
         if (const char *e = getenv("FANS_Y_GRID")) ctx->y_grid = atoi(e);
+        // kz-chunked pipeline (the x pass of chunk q under the NVLink transposes of the neighbouring chunks): opt-in, measured slower
+        // than the component pipeline at 2 and 8 GPUs and equal at 4 (profiles/r2r_chunked_pipeline_8gpu.txt) — the x pass starves on
+        // the SMs the persistent y pass leaves, and the z passes lose their overlap
+        ctx->chunks = 0;
+        if (const char *e = getenv("FANS_CHUNKS")) ctx->chunks = (ctx->nx >= 64) ? std::min(4, std::max(0, atoi(e))) : 0;
     }
 
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * (1 << 20)));

@@ -266,3 +266,12 @@ int comm_barrier(fans_ctx *ctx)
     prof_end(ctx);
     return FANS_OK;
 }
+
+// the same on another stream of this context (chunked slab pipeline, solve.cu); its own dummy operand so that it never races with
+// a barrier of the main stream
+int comm_barrier_on(fans_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->P == 1) return FANS_OK;
+    NCCL_TRY(ctx, g_nccl.AllReduce(ctx->d_red + S_BARRIER2, ctx->d_red + S_BARRIER2, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->cfg.nccl_comm, st));
+    return FANS_OK;
+}

@@ -70,6 +70,7 @@ struct fans_ctx {
     int gate_seq = 0;
     int pipe = 0;               // 1: pipelined convolution (P > 1, fused transposes, h > 1)
     int y_grid = 0;             // CTAs of the persistent y pass in the pipeline (0: one CTA per tile)
+    int chunks = 0;             // > 0: kz-chunked y <-> x pipeline (solve.cu, conv_run_chunked) with this many chunks
 
     double *field[FANS_N_FIELDS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_alt = nullptr;   // ping-pong partner of D (fused d = s + beta d must not update in place)

@@ -6,6 +6,7 @@
 //     gamma[((cta*NG + k) * (N/E) * E + e*(N/E) + jt) * T + t],   storage row = jt*E + e,   NG = H(H+1)/2 upper triangle.
 #include "fft_reg.cuh"
 #include "internal.h"
+#include <algorithm>
 
 template <int T>
 struct TileIdxX {
@@ -122,8 +123,10 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
 template <int N, int T, bool PF>
 __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 * 1024) ? 2 : 1)
     k_fft_xg_seq(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,
-                 int nWork, PeerTable peers)
+                 int nWork, PeerTable peers, int tile0, int ntc)
 {
+    // work item q of this launch = (y row q / ntc, kz tile tile0 + q % ntc): the whole spectrum (tile0 = 0, ntc = nTiles) or one
+    // kz chunk of the slab pipeline; `w` below is the item's index in the full (row, tile) numbering the Gamma layout uses
     extern __shared__ double2 sm[];  // [3][N*T]
     constexpr int H = 3, E = rp_elems(N), TPC = N / E, NST = rp_nstages(N), NG = 6, NTC = TPC * T;
     constexpr size_t NT = (size_t)N * T;
@@ -137,8 +140,10 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 
         for (int e = 0; e < E; ++e) cp_async16(dst + e * NTC, base + spec_row_x(g, rp_row<N, 0>(jt, e)));
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    if (PF && (int)blockIdx.x < nWork) prefetch(blockIdx.x, 0);
-    for (int w = blockIdx.x; w < nWork; w += gridDim.x) {
+    auto full_index = [&](int q) { return (q / ntc) * nTiles + tile0 + q % ntc; };
+    if (PF && (int)blockIdx.x < nWork) prefetch(full_index(blockIdx.x), 0);
+    for (int q = blockIdx.x; q < nWork; q += gridDim.x) {
+        const int w = full_index(q);
         const size_t off = tile_off(w);
         double2 a[1][E];
 #pragma unroll 1
@@ -196,17 +201,22 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 
                 for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
             }
             // component 1 is through its inverse transform => every thread has left tile 0: the next tile's first component may land
-            if (PF && c == 1 && NST > 1 && w + (int)gridDim.x < nWork) prefetch(w + gridDim.x, 0);
+            if (PF && c == 1 && NST > 1 && q + (int)gridDim.x < nWork) prefetch(full_index(q + gridDim.x), 0);
         }
-        if (PF && NST <= 1 && w + (int)gridDim.x < nWork) {  // single-stage transforms have no barriers to lean on
+        if (PF && NST <= 1 && q + (int)gridDim.x < nWork) {  // single-stage transforms have no barriers to lean on
             __syncthreads();
-            prefetch(w + gridDim.x, 0);
+            prefetch(full_index(q + gridDim.x), 0);
         }
     }
 }
 
+struct XPart {  // kz-tile range and launch of one x-pass call (whole spectrum: tile0 = 0, ntile = 0, st = ctx->st, grid_cap = 0)
+    cudaStream_t st;
+    int tile0, ntile, grid_cap;
+};
+
 template <int N, int T>
-static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const PeerTable &peers)
+static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const PeerTable &peers, const XPart &xp)
 {
     constexpr int E = rp_elems(N), NTHR = (N / E) * T;
     const int nTiles = (ctx->kzc + T - 1) / T;
@@ -220,16 +230,19 @@ static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fft_xg_seq<N, T, true>, NTHR, smem));
         if (resident < 1) resident = 1;
     }
-    const int nWork = ctx->n1 * nTiles;
+    const int tile0 = xp.ntile > 0 ? xp.tile0 : 0, ntc = xp.ntile > 0 ? std::min(xp.ntile, nTiles - tile0) : nTiles;
+    if (ntc <= 0) return FANS_OK;
+    const int nWork = ctx->n1 * ntc;
     int grid = FANS_SMS * resident;
     if (const char *env = getenv("FANS_XG_GRID")) grid = atoi(env);
+    if (xp.grid_cap > 0 && grid > xp.grid_cap * resident) grid = xp.grid_cap * resident;
     if (grid > nWork) grid = nWork;
     // prefetch into the idle tiles pays with 128-byte rows (T = 8: 2.75 -> 2.63 ms at n_x = 512); with the 64-byte rows of n_x = 1024
     // the extra barrier per component costs more than the hidden latency (3.42 -> 3.70 ms on the 8-GPU run), so it stays off there
     const char *pf = getenv("FANS_XG_PF");   // 0 / 1: force plain loads / prefetch (A/B runs)
     const bool use_pf = pf ? atoi(pf) != 0 : (T == 8);
-    if (!use_pf) k_fft_xg_seq<N, T, false><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
-    else k_fft_xg_seq<N, T, true><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
+    if (!use_pf) k_fft_xg_seq<N, T, false><<<grid, NTHR, smem, xp.st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers, tile0, ntc);
+    else k_fft_xg_seq<N, T, true><<<grid, NTHR, smem, xp.st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers, tile0, ntc);
     return FANS_OK;
 }
 
@@ -270,8 +283,13 @@ int fft_x_tile_width(int nx, int h)
     return T;
 }
 
-int fft_pass_x_gamma(fans_ctx *ctx)
+int fft_pass_x_gamma(fans_ctx *ctx) { return fft_pass_x_gamma_part(ctx, ctx->st, 0, 0, 0); }
+
+// kz tiles [tile0, tile0 + ntile) of the x pass (tile width ctx->gT) on stream st with at most grid_cap SMs (0: all); ntile = 0: whole
+// spectrum.  Ranges are only implemented for the sequential-component kernel (h = 3, n_x >= 64), which is what the slab pipeline uses.
+int fft_pass_x_gamma_part(fans_ctx *ctx, cudaStream_t st, int tile0, int ntile, int grid_cap)
 {
+    const XPart xp{st, tile0, ntile, grid_cap};
     prof_begin(ctx, PC_FFT_X_GAMMA);
     SpecGeom g = spec_geom_A(ctx);
     double2 *specB = ctx->P > 1 ? ctx->specB : ctx->spec;
@@ -285,7 +303,7 @@ int fft_pass_x_gamma(fans_ctx *ctx)
 #define X_CASE(N_)                                                                                     \
     case N_:                                                                                           \
         if (ctx->h == 1) rc = (T == 8) ? launch_xg<N_, 1, 8>(ctx, specB, g, peers) : (T == 4 ? launch_xg<N_, 1, 4>(ctx, specB, g, peers) : launch_xg<N_, 1, 2>(ctx, specB, g, peers)); \
-        else if (seq && N_ >= 64) rc = (T == 8 && N_ <= 512) ? launch_xg_seq<(N_ <= 512 ? N_ : 64), 8>(ctx, specB, g, peers) : ((T == 4) ? launch_xg_seq<N_, 4>(ctx, specB, g, peers) : launch_xg_seq<N_, 2>(ctx, specB, g, peers));  \
+        else if (seq && N_ >= 64) rc = (T == 8 && N_ <= 512) ? launch_xg_seq<(N_ <= 512 ? N_ : 64), 8>(ctx, specB, g, peers, xp) : ((T == 4) ? launch_xg_seq<N_, 4>(ctx, specB, g, peers, xp) : launch_xg_seq<N_, 2>(ctx, specB, g, peers, xp));  \
         else rc = (T == 4) ? launch_xg<N_, 3, 4>(ctx, specB, g, peers) : launch_xg<N_, 3, 2>(ctx, specB, g, peers);  \
         break;
     switch (ctx->nx) {

@@ -6,6 +6,7 @@
 // stored straight from registers; shared memory is only the inter-stage exchange tile.
 #include "fft_reg.cuh"
 #include "internal.h"
+#include <algorithm>
 
 template <int T>
 struct TileIdx {  // swizzled [row][t] tile: conflict-free butterflies for T = 4 (64-byte rows) and T = 8 (128-byte rows)
@@ -17,14 +18,14 @@ struct TileIdx {  // swizzled [row][t] tile: conflict-free butterflies for T = 4
     }
 };
 
-// one (component, x plane, kz tile) of the y pass; b = ((c - c0) * n0 + xl) * nTiles + tile
+// one (component, x plane, kz tile) of the y pass; b = ((c - c0) * n0 + xl) * nTiles + (tile - tile0), nTiles tiles from tile0
 template <int N, int T, bool INV>
 __device__ __forceinline__ void y_tile(double2 *__restrict__ spec, const double2 *__restrict__ tw, const SpecGeom &g, int nTiles, const PeerTable &peers,
-                                       int b, int c0, double2 *sm)
+                                       int b, int c0, double2 *sm, int tile0 = 0)
 {
     constexpr int E = rp_elems(N), NST = rp_nstages(N);
     const int t = threadIdx.x % T, jt = threadIdx.x / T;
-    const int tile = b % nTiles;
+    const int tile = tile0 + b % nTiles;
     b /= nTiles;
     const int xl = b % g.n0, c = c0 + b / g.n0;
     double2 *base = spec + (size_t)c * g.cStride + (size_t)xl * g.xStride + (size_t)tile * T + t;
@@ -78,7 +79,7 @@ __global__ void Y_BOUNDS k_fft_y(double2 *__restrict__ spec, const double2 *__re
 // another stream can hold back a concurrent kernel until this one owns its SMs.
 template <int N, int T, bool INV>
 __global__ void Y_BOUNDS k_fft_y_part(double2 *__restrict__ spec, const double2 *__restrict__ tw, SpecGeom g, int nTiles, PeerTable peers, int c0,
-                                      int nWork, int *gate, int gate_val)
+                                      int nWork, int *gate, int gate_val, int tile0)
 {
     extern __shared__ double2 sm[];
     if (gate && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -86,7 +87,7 @@ __global__ void Y_BOUNDS k_fft_y_part(double2 *__restrict__ spec, const double2 
         __threadfence();
     }
     for (int w = blockIdx.x; w < nWork; w += gridDim.x) {
-        y_tile<N, T, INV>(spec, tw, g, nTiles, peers, w, c0, sm);
+        y_tile<N, T, INV>(spec, tw, g, nTiles, peers, w, c0, sm, tile0);
         __syncthreads();  // the exchange tile is reused by the next tile
     }
 }
@@ -95,12 +96,14 @@ template <int N, int T>
 static int launch_y(fans_ctx *ctx, bool inverse, const SpecGeom &g, const PeerTable &peers, const YLaunch &yl)
 {
     constexpr int E = rp_elems(N);
-    const int nTiles = (ctx->kzc + T - 1) / T;
+    const int allTiles = (ctx->kzc + T - 1) / T;
+    const int tile0 = yl.ntile > 0 ? yl.tile0 : 0;
+    const int nTiles = yl.ntile > 0 ? std::min(yl.ntile, allTiles - tile0) : allTiles;   // tiles of THIS launch
     const size_t smem = sizeof(double2) * N * T;
     const int nWork = (int)((size_t)yl.nc * ctx->n0 * nTiles);
     const unsigned grid = (unsigned)((yl.grid > 0 && yl.grid < nWork) ? yl.grid : nWork);
     const int nthr = (N / E) * T;
-    if (grid == (unsigned)nWork && yl.c0 == 0 && !yl.gate) {  // whole-spectrum launch: one tile per CTA
+    if (grid == (unsigned)nWork && yl.c0 == 0 && !yl.gate && yl.ntile == 0) {  // whole-spectrum launch: one tile per CTA
         if (!inverse) {
             if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_fft_y<N, T, false><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers);
@@ -112,10 +115,10 @@ static int launch_y(fans_ctx *ctx, bool inverse, const SpecGeom &g, const PeerTa
         constexpr int NP = N;
         if (!inverse) {
             if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y_part<NP, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_fft_y_part<NP, T, false><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers, yl.c0, nWork, yl.gate, yl.gate_val);
+            k_fft_y_part<NP, T, false><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers, yl.c0, nWork, yl.gate, yl.gate_val, tile0);
         } else {
             if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_y_part<NP, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_fft_y_part<NP, T, true><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers, yl.c0, nWork, yl.gate, yl.gate_val);
+            k_fft_y_part<NP, T, true><<<grid, nthr, smem, yl.st>>>(ctx->spec, ctx->plany.tw, g, nTiles, peers, yl.c0, nWork, yl.gate, yl.gate_val, tile0);
         }
     }
     return FANS_OK;

@@ -13,6 +13,7 @@ struct YLaunch {  // one launch of the y pass: stream, component range, CTA cap,
     int c0, nc, grid;
     int *gate;
     int gate_val;
+    int tile0 = 0, ntile = 0;  // kz-tile range [tile0, tile0 + ntile) of this launch (ntile = 0: all tiles) — chunked slab pipeline
 };
 int  fft_pass_y_part(fans_ctx *ctx, bool inverse, const YLaunch &yl);
 int  fft_pass_z_fwd_part(fans_ctx *ctx, const double *in, int c0, int nc, cudaStream_t st);
@@ -20,6 +21,7 @@ int  fft_pass_z_inv_part(fans_ctx *ctx, double *out, double scale, const double 
                          cudaStream_t st);
 int  conv_gate(fans_ctx *ctx, int gate_val, cudaStream_t st);
 int  fft_pass_x_gamma(fans_ctx *ctx);
+int  fft_pass_x_gamma_part(fans_ctx *ctx, cudaStream_t st, int tile0, int ntile, int grid_cap);  // kz tiles [tile0, tile0 + ntile)
 int  fft_pass_z_inv(fans_ctx *ctx, double *out, double scale, const double *dotw, double *red_out);
 int  fft_x_tile_width(int nx, int h);
 struct SpecGeom;
@@ -64,6 +66,7 @@ int comm_alltoall(fans_ctx *ctx, const double2 *src, double2 *dst);
 int comm_map_peers(fans_ctx *ctx);
 void comm_unmap_peers(fans_ctx *ctx);
 int comm_barrier(fans_ctx *ctx);
+int comm_barrier_on(fans_ctx *ctx, cudaStream_t st);
 
 // solve.cu
 int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out);

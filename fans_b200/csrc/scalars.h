@@ -12,6 +12,7 @@ enum {
     S_LINF = 11,     // max |r|
     S_GEN = 12,      // 4 generic slots (sum|a|, sum a^2, sum a*b, max|a|)
     S_STRESS = 16,   // 9 slots: sum of element-averaged stress
+    S_BARRIER2 = 29, // dummy operand of the slab barrier issued on the second stream (chunked pipeline)
     S_BARRIER = 30,  // dummy operand of the stream-ordered slab barrier
     S_STAGE = 31,    // host -> device staging slot
     S_ERRMAX = 32,   // 4 slots: MAX over the slabs of (S_L1, S_L2SQ, -, S_LINF): Solver::compute_error allreduces with MPI_MAX

@@ -9,6 +9,7 @@
 #include "stencil.h"
 #include <cstdlib>
 #include <cmath>
+#include <algorithm>
 
 int ensure_fields(fans_ctx *ctx, std::initializer_list<int> ids);
 int ensure_dalt(fans_ctx *ctx);
@@ -100,6 +101,49 @@ static int conv_run_pipelined(fans_ctx *ctx, const double *in, double *out, doub
     return FANS_OK;
 }
 
+// Slab convolution as a kz-CHUNKED pipeline (world_size > 1, fused transposes, h = 3).  The two transposes are NVLink-bound, the
+// x pass with the Green operator is HBM / shared-memory bound, and a kz range of the spectrum is independent of every other one
+// from the y pass to the inverse y pass:
+//     st :  zf(all) | yf(0) yf(1) yf(2) yf(3)            | yi(0) yi(1) yi(2) yi(3) | zi(all)
+//     st2:                 b x(0) b  b x(1) b  b x(2) b   b x(3) b
+// yf(q) pushes chunk q of this rank's rows into the owners' transposed spectra; after a slab barrier (b) on the second stream the x
+// pass of chunk q runs there, on the SMs the persistent y pass leaves free, while the first stream already pushes chunk q+1; a
+// second barrier releases chunk q for the pulls of the inverse y pass.  Only the first y chunk and the last x chunk are exposed.
+static int conv_run_chunked(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out)
+{
+    const int Q = ctx->chunks;
+    cudaStream_t sA = ctx->st, sB = ctx->st2;
+    cudaEvent_t *ev = ctx->ev_pipe;   // [0, Q): y chunk pushed ; [4, 4 + Q): x chunk done everywhere
+    const int yTiles = (ctx->kzc + ctx->yT - 1) / ctx->yT, per = (yTiles + Q - 1) / Q;
+    const int ratio = ctx->yT / ctx->gT;   // x tiles per y tile (1 or 2)
+    const int ygrid = ctx->y_grid > 0 ? ctx->y_grid : 96;
+    const int xcap = std::max(16, FANS_SMS - ygrid);
+    FANS_CHECK(fft_pass_z_fwd(ctx, in));
+    for (int q = 0; q < Q; ++q) {
+        const int t0 = q * per, nt = std::min(per, yTiles - t0);
+        if (nt <= 0) {
+            CUDA_TRY(ctx, cudaEventRecord(ev[4 + q], sB));
+            continue;
+        }
+        FANS_CHECK(fft_pass_y_part(ctx, false, YLaunch{sA, 0, ctx->h, ygrid, nullptr, 0, t0, nt}));
+        CUDA_TRY(ctx, cudaEventRecord(ev[q], sA));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(sB, ev[q], 0));
+        FANS_CHECK(comm_barrier_on(ctx, sB));   // every rank has pushed chunk q
+        FANS_CHECK(fft_pass_x_gamma_part(ctx, sB, t0 * ratio, nt * ratio, xcap));
+        FANS_CHECK(comm_barrier_on(ctx, sB));   // every rank is done with chunk q: it may be pulled
+        CUDA_TRY(ctx, cudaEventRecord(ev[4 + q], sB));
+    }
+    for (int q = 0; q < Q; ++q) {
+        const int t0 = q * per, nt = std::min(per, yTiles - t0);
+        CUDA_TRY(ctx, cudaStreamWaitEvent(sA, ev[4 + q], 0));
+        if (nt > 0) FANS_CHECK(fft_pass_y_part(ctx, true, YLaunch{sA, 0, ctx->h, q + 1 < Q ? ygrid : 0, nullptr, 0, t0, nt}));
+    }
+    FANS_CHECK(fft_pass_z_inv(ctx, out, scale, dotw, red_out));
+    if (red_out) FANS_CHECK(comm_allreduce(ctx, red_out, red_out, 1, false));
+    else FANS_CHECK(comm_barrier(ctx));
+    return FANS_OK;
+}
+
 // out = scale * Gamma * in ;  optional red_out[0] = <dotw, out>
 int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out)
 {
@@ -131,6 +175,7 @@ int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const d
         ~ConvTimer() { c->conv_pending.emplace_back(a, mk()); }
     } conv_timer{ctx, ev_a, conv_event};
     if (ctx->any_fft) return conv_run_any(ctx, in, out, scale, dotw, red_out);
+    if (ctx->pipe && ctx->chunks > 0 && !ctx->prof) return conv_run_chunked(ctx, in, out, scale, dotw, red_out);
     if (ctx->pipe && !ctx->prof) return conv_run_pipelined(ctx, in, out, scale, dotw, red_out);
     FANS_CHECK(fft_pass_z_fwd(ctx, in));
     FANS_CHECK(fft_pass_y(ctx, false));

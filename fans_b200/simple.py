@@ -59,6 +59,65 @@ def linear_elastic_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1, gdi
     return ctx
 
 
+def linear_elastic_tensor_context(ms, Lbox, tangents, fe_type="HEX8", device=-1, gdims=None, comm=None):
+    """LinearElasticTriclinic-style phases: one full 6x6 Mandel tangent per phase id (LinearElastic.h:77-159); reference stiffness =
+    their mean (LinearElastic.h:146-150).  A polycrystal with one tensor per grain."""
+    tangents = np.asarray(tangents, dtype=np.float64)
+    ctx = L.Context(gdims if gdims is not None else ms.shape, Lbox, 3, 6, fe_type, device, comm)
+    descs = []
+    for i in range(len(tangents)):
+        d = L.PhaseDesc()
+        d.model, d.local_mat, d.group_n_mat = L.MAT_LINEAR, i, len(tangents)
+        for k, v in enumerate(tangents[i].reshape(-1)):
+            d.params[k] = v
+        descs.append(d)
+    ctx.set_materials(descs)
+    ctx.set_microstructure(ms)
+    ctx.set_reference_stiffness(tangents.mean(0))
+    return ctx
+
+
+def rotated_cubic_tangents(n, c11=168.0, c12=121.0, c44=75.0, seed=7):
+    """n randomly rotated cubic stiffness tensors (copper-like constants) in Mandel notation: a synthetic polycrystal"""
+    rng = np.random.default_rng(seed)
+    C = np.zeros((3, 3, 3, 3))
+    for i in range(3):
+        for j in range(3):
+            C[i, i, j, j] += c12
+            C[i, j, i, j] += c44
+            C[i, j, j, i] += c44
+        C[i, i, i, i] += c11 - c12 - 2.0 * c44
+    pairs = [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]
+    out = []
+    for _ in range(n):
+        Q, _r = np.linalg.qr(rng.standard_normal((3, 3)))
+        Cr = np.einsum("ia,jb,kc,ld,abcd->ijkl", Q, Q, Q, Q, C)
+        M = np.zeros((6, 6))
+        for a, (i, j) in enumerate(pairs):
+            for b, (k, l) in enumerate(pairs):
+                M[a, b] = Cr[i, j, k, l] * (np.sqrt(2.0) if a >= 3 else 1.0) * (np.sqrt(2.0) if b >= 3 else 1.0)
+        out.append(0.5 * (M + M.T))
+    return np.array(out)
+
+
+def voronoi_labels(dims, n_seeds, seed=2024):
+    """periodic Voronoi grain labels 0..n_seeds-1 (the generator of voronoi_microstructure without the mod 2)"""
+    from scipy.spatial import cKDTree
+    nx, ny, nz = dims
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0.0, 1.0, size=(n_seeds, 3)) * np.array([nx, ny, nz], dtype=np.float64)
+    tree = cKDTree(pts, boxsize=[nx, ny, nz])
+    yy, zz = np.meshgrid(np.arange(ny) + 0.5, np.arange(nz) + 0.5, indexing="ij")
+    q = np.empty((ny * nz, 3))
+    q[:, 1], q[:, 2] = yy.ravel(), zz.ravel()
+    ms = np.empty((nx, ny, nz), dtype=np.uint16)
+    for i in range(nx):
+        q[:, 0] = i + 0.5
+        _, lab = tree.query(q, workers=-1)
+        ms[i] = lab.reshape(ny, nz)
+    return ms
+
+
 def linear_thermal_context(ms, Lbox, conductivity, fe_type="HEX8", device=-1):
     k = np.asarray(conductivity, dtype=np.float64)
     ctx = L.Context(ms.shape, Lbox, 1, 3, fe_type, device)

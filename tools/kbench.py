@@ -15,7 +15,7 @@ ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--tag", default="")
 ap.add_argument("--fe", default="HEX8")
-ap.add_argument("--ms", default="ellipsoid", help="ellipsoid | homogeneous | layers | voronoi")
+ap.add_argument("--ms", default="ellipsoid", help="ellipsoid | homogeneous | layers | voronoi | poly16 (16 rotated cubic grains, one tensor each)")
 ap.add_argument("--no-profile", action="store_true", help="only the timed solve (used under ncu by bench.py)")
 args = ap.parse_args()
 n = args.size
@@ -29,7 +29,11 @@ elif args.ms == "voronoi":
 elif args.ms == "layers":
     ms[...] = 0
     ms[n // 4: 3 * n // 4] = 1
-ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], [62.5, 222.222], [28.8462, 166.6667], args.fe, 0)
+if args.ms == "poly16":   # more phases than the constant-bank stencil holds: the coefficient-table instantiation (stencil.cu, NQ = 0)
+    ms = simple.voronoi_labels(dims, 16)
+    ctx = simple.linear_elastic_tensor_context(ms, [1.0, 1.0, 1.0], simple.rotated_cubic_tangents(16), args.fe, 0)
+else:
+    ctx = simple.linear_elastic_context(ms, [1.0, 1.0, 1.0], [62.5, 222.222], [28.8462, 166.6667], args.fe, 0)
 ctx.set_gradient([0.001, -0.002, 0.003, 0.0015, -0.0025, 0.001])
 ctx.solve("cg", 3, 0.0, "Linfinity", "absolute")
 ctx.zero("u")
