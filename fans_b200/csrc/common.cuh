@@ -160,6 +160,30 @@ struct fans_ctx {
 
 void fans_set_error(fans_ctx *ctx, int code, const std::string &msg);
 
+// x-chunk length of a marching kernel (stencil, element sweeps): `cols` CTA columns march `n0` planes in chunks; every chunk pays
+// `runin` extra planes, `slots` CTAs are resident at a time.  Minimises waves x steps per chunk over the power-of-two splits — long
+// marches on big grids (few redundant run-in planes), many short ones on small grids (a 32^3 micro problem has 4 to 8 columns and
+// would otherwise leave most of the 148 SMs idle).
+static inline int pick_xchunk(int n0, long cols, long slots, int runin)
+{
+    auto cost_of = [&](int xc) {
+        const long chunks = (n0 + xc - 1) / xc, ctas = cols * chunks;
+        return ((ctas + slots - 1) / slots) * (long)(xc + runin);
+    };
+    long best_cost = -1;
+    for (int xc = n0;; xc = (xc + 1) / 2) {
+        const long c = cost_of(xc);
+        if (best_cost < 0 || c < best_cost) best_cost = c;
+        if (xc <= 2) break;
+    }
+    int best = n0;   // the shortest march within 3 % of the optimum: more CTAs balance the last wave better (measured at 512^3)
+    for (int xc = n0;; xc = (xc + 1) / 2) {
+        if (cost_of(xc) * 100 <= best_cost * 103) best = xc;
+        if (xc <= 2) break;
+    }
+    return best;
+}
+
 // kernel classes for profiling (index into prof_ms / prof_n); names in api.cu
 enum { PC_FFT_Z_FWD = 0, PC_FFT_Y_FWD, PC_FFT_X_GAMMA, PC_FFT_Y_INV, PC_FFT_Z_INV, PC_SWEEP_LINEAR, PC_SWEEP_RESIDUAL,
        PC_SWEEP_STRAINSTRESS, PC_CG_UPDATE, PC_REDUCE, PC_AXPY, PC_OTHER, PC_COMM_A2A, PC_COMM_HALO, PC_COMM_SCALAR };

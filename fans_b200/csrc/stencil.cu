@@ -574,10 +574,12 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
         p.halo_lo = ctx->halo_lo, p.halo_hi = ctx->halo_hi, p.ms_lo = ctx->ms_lo;
     }
     const int gy = (ctx->ny + GY - 1) / GY, gz = (ctx->nz + GZ - 1) / GZ;
-    int xchunk = ctx->n0;
-    long want = 24L * FANS_SMS;  // 12 waves of 2 resident CTAs per SM; longer marches amortise the 2-plane run-in
-    if (const char *env = getenv("FANS_STENCIL_CTAS")) want = atol(env);
-    while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < want) xchunk = (xchunk + 1) / 2;
+    int xchunk = pick_xchunk(ctx->n0, (long)gy * gz, 2L * FANS_SMS, 2);   // 2 resident CTAs per SM, 2 run-in planes per march
+    if (const char *env = getenv("FANS_STENCIL_CTAS")) {   // experiments: at least this many CTAs
+        const long want = atol(env);
+        xchunk = ctx->n0;
+        while (xchunk > 2 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < want) xchunk = (xchunk + 1) / 2;
+    }
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
     const size_t smem = sizeof(double) * 4 * h * GTILE + sizeof(double2) * 2 * h * G_STG + sizeof(uint16_t) * 8 * GETILE + 16;

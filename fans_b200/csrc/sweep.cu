@@ -880,8 +880,7 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     }
     const int ty = sf ? FY : TY, tz = sf ? FZ : TZ;
     const int gy = (ctx->ny + ty - 1) / ty, gz = (ctx->nz + tz - 1) / tz;
-    int xchunk = ctx->n0;
-    while (xchunk > 16 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < 4L * FANS_SMS) xchunk = (xchunk + 1) / 2;
+    const int xchunk = pick_xchunk(ctx->n0, (long)gy * gz, (long)FANS_SMS * ((!sf && mode == SW_LINEAR) ? 2 : 1), 1);
     p.xchunk = xchunk;
     dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
     p.hstage = (ctx->any_history && mode != SW_LINEAR && !(getenv("FANS_HIST_STAGE") && atoi(getenv("FANS_HIST_STAGE")) == 0)) ? 1 : 0;
