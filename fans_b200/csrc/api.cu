@@ -192,6 +192,7 @@ static void elem_stiffness(const ElemOps &E, const double *C, std::vector<double
 // lifetime
 // ------------------------------------------------------------------------------------------------
 static int create_rest(fans_ctx *ctx);
+int check_fault(fans_ctx *ctx);
 static int ensure_field(fans_ctx *ctx, int f)
 {
     if (f < 0 || f >= FANS_N_FIELDS) {
@@ -373,6 +374,8 @@ static int create_rest(fans_ctx *ctx)
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_red, 0, sizeof(double) * S_COUNT, ctx->st));
     CUDA_TRY(ctx, cudaMallocHost(&ctx->h_red, sizeof(double) * S_COUNT));
     CUDA_TRY(ctx, cudaMallocHost(&ctx->h_stage, sizeof(double) * 4));
+    CUDA_TRY(ctx, cudaMallocHost(&ctx->h_fault, sizeof(int)));
+    *ctx->h_fault = 0;
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int)));   // [0] grid-reduce ticket, [1] scratch word (phase-id maximum)
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket, 0, 2 * sizeof(unsigned int), ctx->st));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_flag, sizeof(int)));
@@ -403,6 +406,7 @@ extern "C" void fans_destroy(fans_ctx *ctx)
         if (p) cudaFree(p);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_fault) cudaFreeHost(ctx->h_fault);
     fft_plan_free(ctx->planx);
     fft_plan_free(ctx->plany);
     fft_plan_free(ctx->planz);
@@ -800,6 +804,19 @@ extern "C" int fans_field_copy(fans_ctx *ctx, int32_t dst, int32_t src)
 // ------------------------------------------------------------------------------------------------
 // operators
 // ------------------------------------------------------------------------------------------------
+// the fault flag as of the last read_scalars() (same stream position as the scalars it returned); slabs: all-reduce first
+int check_fault_cached(fans_ctx *ctx)
+{
+    if (ctx->P > 1) return check_fault(ctx);
+    if (*ctx->h_fault == FANS_ERR_NEG_JACOBIAN) {
+        fans_set_error(ctx, FANS_ERR_NEG_JACOBIAN, "Negative Jacobian determinant in CompressibleNeoHookean!");
+        cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->st);
+        *ctx->h_fault = 0;
+        return FANS_ERR_NEG_JACOBIAN;
+    }
+    return FANS_OK;
+}
+
 int check_fault(fans_ctx *ctx)
 {
     int f = 0;

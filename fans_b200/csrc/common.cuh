@@ -139,6 +139,7 @@ struct fans_ctx {
     double *h_stage = nullptr;  // pinned host->device staging scalar
     unsigned int *d_ticket = nullptr;
     int neg_jac_flag_host = 0;
+    int *h_fault = nullptr;     // pinned mirror of d_flag, refreshed by read_scalars (one synchronisation for scalars and fault)
     int *d_flag = nullptr;      // sticky device fault flag (J <= 0)
 
     // optional per-kernel-class device timing (bench.py roofline): event pairs resolved at the next stream sync

@@ -49,6 +49,7 @@ int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const d
 int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev);
 int vec_axpy(fans_ctx *ctx, double *y, double alpha, const double *x);
 int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x);
+int vec_xpby_dev(fans_ctx *ctx, double *y, const double *beta_dev, const double *x);
 int vec_extrapolate(fans_ctx *ctx, double *u, double *up);
 int vec_aos_to_soa(fans_ctx *ctx, const double *aos, double *soa);
 int vec_soa_to_aos(fans_ctx *ctx, const double *soa, double *aos);

@@ -12,6 +12,7 @@ enum {
     S_LINF = 11,     // max |r|
     S_GEN = 12,      // 4 generic slots (sum|a|, sum a^2, sum a*b, max|a|)
     S_STRESS = 16,   // 9 slots: sum of element-averaged stress
+    S_LS = 25,       // 4 slots: the generic block of a second reduction (<r, d> of the line search, solverCG.h:127), read together with S_GEN
     S_BARRIER2 = 29, // dummy operand of the slab barrier issued on the second stream (chunked pipeline)
     S_BARRIER = 30,  // dummy operand of the stream-ordered slab barrier
     S_STAGE = 31,    // host -> device staging slot

@@ -14,10 +14,12 @@
 int ensure_fields(fans_ctx *ctx, std::initializer_list<int> ids);
 int ensure_dalt(fans_ctx *ctx);
 int check_fault(fans_ctx *ctx);
+int check_fault_cached(fans_ctx *ctx);
 
 int read_scalars(fans_ctx *ctx)
 {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fault, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));   // see check_fault_cached
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     prof_resolve(ctx);
     return FANS_OK;
@@ -323,30 +325,26 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
             err_rel = error_from_scalars(ctx, es, S_ERRMAX);
         } else {
             double *d = ctx->field[FANS_FIELD_D];
-            // deltamid = <r,s> (solverCG.h:86)
-            FANS_CHECK(vec_reduce4(ctx, r, s, ctx->d_red + S_GEN));
-            FANS_CHECK(read_scalars(ctx));
-            const double deltamid = ctx->h_red[S_GEN + 2];
-            FANS_CHECK(conv_run(ctx, r, s, -1.0, r, ctx->d_red + S_RS));
-            FANS_CHECK(read_scalars(ctx));
-            const double delta0 = delta;
-            delta = ctx->h_red[S_RS];
-            const double beta = std::fmax(0.0, (delta - deltamid) / delta0);
-            // d = s + beta d  (solverCG.h:94)
-            FANS_CHECK(vec_xpby(ctx, d, beta, s));
+            // Host round trips per iteration: one per residual evaluation of the line search (the secant decisions are taken on the
+            // host) and one for the error — delta, beta and the direction update stay on the device like in the linear path.
+            // deltamid = <r,s> (solverCG.h:86): left in S_GEN+2 by the reduction that produced the error of the previous iteration
+            // (s = 0 before the first iteration, the initial compute_error leaves 0 there)
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_red + S_DELTAMID, ctx->d_red + S_GEN + 2, sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
+            FANS_CHECK(conv_run(ctx, r, s, -1.0, r, ctx->d_red + S_RS));        // s = -Gamma r ; S_RS = <r,s>
+            FANS_CHECK(vec_scalars_after_conv(ctx));                            // delta0 = delta ; delta = <r,s> ; beta (solverCG.h:91-94)
+            FANS_CHECK(vec_xpby_dev(ctx, d, ctx->d_red + S_BETA, s));           // d = s + beta d
             // ---- LineSearchSecant (solverCG.h:119-160) ----
             double err = 10.0;
             int it = 0;
             double alpha_prev = 0.0, alpha_curr = alpha_warm;
-            FANS_CHECK(vec_reduce4(ctx, r, d, ctx->d_red + S_GEN));
-            FANS_CHECK(read_scalars(ctx));
-            double rpd = ctx->h_red[S_GEN + 2];
+            FANS_CHECK(vec_reduce4(ctx, r, d, ctx->d_red + S_LS));              // <r,d>, read below together with <rnew,d>
             FANS_CHECK(vec_axpy(ctx, u, alpha_curr, d));
             FANS_CHECK(fans_update_mixed_bc(ctx));
             ctx->n_residual_evals++;
             FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, u, rnew, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
             FANS_CHECK(vec_reduce4(ctx, rnew, d, ctx->d_red + S_GEN));
             FANS_CHECK(read_scalars(ctx));
+            double rpd = ctx->h_red[S_LS + 2];
             double r1pd = ctx->h_red[S_GEN + 2];
             while (it < p->ls_max_iter && err > p->ls_tol) {
                 const double denom = r1pd - rpd;
@@ -372,10 +370,13 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
             ctx->field[FANS_FIELD_RNEW] = r;
             r = ctx->field[FANS_FIELD_R];
             rnew = ctx->field[FANS_FIELD_RNEW];
-            FANS_CHECK(check_fault(ctx));
             if (p->verbose) printf("line search iter %i, alpha %f - error %e - ", it, alpha_curr, err);
             es.iter++;
-            FANS_CHECK(compute_error(ctx, r, es, &err_rel));
+            // compute_error (solver.h:414-452) and the next iteration's deltamid = <r,s> in ONE pass over r; the fault flag rides along
+            FANS_CHECK(vec_reduce4(ctx, r, s, ctx->d_red + S_GEN));
+            FANS_CHECK(read_scalars(ctx));
+            FANS_CHECK(check_fault_cached(ctx));
+            err_rel = error_from_scalars(ctx, es, S_GENMAX);
         }
         if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
     }
@@ -405,7 +406,7 @@ static int solve_fp(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
         FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, u, r, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
         es.iter++;
         FANS_CHECK(compute_error(ctx, r, es, &err_rel));
-        FANS_CHECK(check_fault(ctx));
+        FANS_CHECK(check_fault_cached(ctx));   // the flag came back with the scalars of compute_error
         if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop1, ctx->st));

@@ -73,6 +73,19 @@ __global__ void __launch_bounds__(VEC_THREADS) k_axpy(double2 *__restrict__ y, d
     }
 }
 
+// the same with beta read from the device scalar block (nonlinear CG: beta is formed on the device like in the linear path)
+__global__ void __launch_bounds__(VEC_THREADS) k_xpby_dev(double2 *__restrict__ y, const double *__restrict__ beta_dev, const double2 *__restrict__ x, size_t n2)
+{
+    const double beta = *beta_dev;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 yv = y[i];
+        const double2 xv = x[i];
+        yv.x = xv.x + beta * yv.x;
+        yv.y = xv.y + beta * yv.y;
+        y[i] = yv;
+    }
+}
+
 // y = x + beta*y     (d = s + beta d, solverCG.h:94)
 __global__ void __launch_bounds__(VEC_THREADS) k_xpby(double2 *__restrict__ y, double beta, const double2 *__restrict__ x, size_t n2)
 {
@@ -218,6 +231,8 @@ int vec_reduce4(fans_ctx *ctx, const double *a, const double *b, double *out_dev
     if (out_dev == ctx->d_red + S_GEN) {  // norms: MAX over the slabs (solver.h:430); dot product: SUM (solverCG.h:57)
         FANS_CHECK(comm_allreduce(ctx, out_dev, ctx->d_red + S_GENMAX, 4, true));
         if (ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, out_dev + 2, out_dev + 2, 1, false));
+    } else if (out_dev == ctx->d_red + S_LS && ctx->P > 1) {  // only the dot product of this block is used
+        FANS_CHECK(comm_allreduce(ctx, out_dev + 2, out_dev + 2, 1, false));
     }
     return FANS_OK;
 }
@@ -238,6 +253,17 @@ int vec_xpby(fans_ctx *ctx, double *y, double beta, const double *x)
     prof_begin(ctx, PC_AXPY);
     const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;   // fields carry one zero pad value (api.cu: ensure_field)
     k_xpby<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, beta, (const double2 *)x, n2);
+    prof_end(ctx);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FANS_OK;
+}
+
+int vec_xpby_dev(fans_ctx *ctx, double *y, const double *beta_dev, const double *x)
+{
+    prof_begin(ctx, PC_AXPY);
+    const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;
+    k_xpby_dev<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)y, beta_dev, (const double2 *)x, n2);
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
