@@ -51,6 +51,7 @@ struct SweepParams {
     int *pflag;
     double gm, gp, il[3];    // sum-factorised path: Gauss coordinates 0.5 -/+ sqrt(3)/6 and 1 / element length per axis
     int stg2;                // k_sweep_sf: staging tile double-buffered (one barrier per plane)
+    int one_point;           // strain/stress sweep of an all-linear problem: element averages = values at the element centre
     int hstage;              // 1: history of Gauss point g+1 is staged in shared memory (cp.async) while g is evaluated
     int *fault;
     // reductions
@@ -542,6 +543,36 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_sweep_sf(const SweepParams p)
             // the whole element for ONE material law known at compile time: no model branch inside the Gauss-point loop
             auto element = [&](auto law_tag) {
                 constexpr int LAW = decltype(law_tag)::value;
+                if constexpr (MODE == SW_STRAINSTRESS && LAW == FANS_MAT_LINEAR) {
+                    if (p.one_point) {
+                        // linear law on a trilinear element: the Gauss-point averages of strain and stress (matmodel.h:202-225) are
+                        // exactly the values at the element centre (symmetric points; B-bar only moves the volumetric part, whose
+                        // average is the centre value by construction) — one law evaluation instead of eight
+                        double Hm[H][3];
+#pragma unroll
+                        for (int c = 0; c < H; ++c) {
+                            const double u000 = UN(c, 0, 0, 0), u100 = UN(c, 1, 0, 0), u010 = UN(c, 0, 1, 0), u110 = UN(c, 1, 1, 0);
+                            const double u001 = UN(c, 0, 0, 1), u101 = UN(c, 1, 0, 1), u011 = UN(c, 0, 1, 1), u111 = UN(c, 1, 1, 1);
+                            Hm[c][0] = 0.25 * p.il[0] * ((u100 - u000) + (u110 - u010) + (u101 - u001) + (u111 - u011));
+                            Hm[c][1] = 0.25 * p.il[1] * ((u010 - u000) + (u110 - u100) + (u011 - u001) + (u111 - u101));
+                            Hm[c][2] = 0.25 * p.il[2] * ((u001 - u000) + (u101 - u100) + (u011 - u010) + (u111 - u110));
+                        }
+                        double eps[NSTR], sig[NSTR];
+                        strain_from_grad<H, NSTR>(Hm, eps);
+#pragma unroll
+                        for (int i = 0; i < NSTR; ++i) eps[i] += p.g0[i];
+                        material_law<NSTR, LAW>(pd, eps, sig, p.hist, p.hist_t, p.pflag, p.nloc, p.nh, 8, 0, e, he, false, p.fault);
+                        if (wr) {
+#pragma unroll
+                            for (int i = 0; i < NSTR; ++i) {
+                                if (p.eps_out) p.eps_out[i * p.nloc + e] = eps[i];
+                                if (p.sig_out) p.sig_out[i * p.nloc + e] = sig[i];
+                                racc[i] += sig[i];
+                            }
+                        }
+                        return;
+                    }
+                }
                 // ---- z derivative at (gx, gy), the same for both gz: GZ[c][gx][gy]
                 double GZ[H][2][2];
 #pragma unroll
@@ -872,12 +903,7 @@ int sweep_run(fans_ctx *ctx, int mode, const double *in, double *out, const doub
     // average is the centre value by construction).  The strain/stress sweep of an all-linear problem (homogenized stress,
     // postprocess averages) therefore evaluates one point per element — 1/8 of the law and gradient work — unless the
     // Gauss-point fields themselves are asked for.  (FANS_SS_FULL=1 keeps the 8-point evaluation, for A/B runs and tests.)
-    if (mode == SW_STRAINSTRESS && ctx->all_linear && ctx->ngp == 8 && !eps_gp && !sig_gp && !(getenv("FANS_SS_FULL") && atoi(getenv("FANS_SS_FULL")))) {
-        sf = false;
-        p.ngp = 1;
-        p.bbar = 0;
-        for (int i = 0; i < 24; ++i) p.bg[i] = ctx->Bgp[8 * 24 + i];
-    }
+    p.one_point = (sf && mode == SW_STRAINSTRESS && ctx->all_linear && !eps_gp && !sig_gp && !(getenv("FANS_SS_FULL") && atoi(getenv("FANS_SS_FULL")))) ? 1 : 0;
     const int ty = sf ? FY : TY, tz = sf ? FZ : TZ;
     const int gy = (ctx->ny + ty - 1) / ty, gz = (ctx->nz + tz - 1) / tz;
     const int xchunk = pick_xchunk(ctx->n0, (long)gy * gz, (long)FANS_SMS * ((!sf && mode == SW_LINEAR) ? 2 : 1), 1);
