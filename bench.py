@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--method", default="cg", help="config5: cg | fp")
     ap.add_argument("--load-steps", type=int, default=3, help="config3 / config5: load increments to run")
     ap.add_argument("--no-selfcheck", action="store_true")
+    ap.add_argument("--sequential", action="store_true", help="config2: one solve per load case instead of fans_solve_batch")
     ap.add_argument("--no-ncu", action="store_true", help="do not measure roofline.traffic live with ncu")
     args = ap.parse_args()
     args.workload = WORKLOADS[args.workload]
@@ -469,11 +470,10 @@ def run_config2(env):
     torch = env.torch
     u_host = torch.zeros((env.n0, dims[1], dims[2], 3), dtype=torch.float64, pin_memory=True).numpy()
     env.barrier()
-    l0 = ctx.launch_count()
-    iters, t_loop, t_solve, C = 0, 0.0, 0.0, np.zeros((6, 6))
-    t0 = time.perf_counter()
-    with ClockSampler(dev) as cs:
-        for i in range(6):   # a new Solver (u = 0) per load case, main.cpp:15-16
+
+    def sequential():   # a new Solver (u = 0) per load case, main.cpp:15-16
+        iters, t_loop, t_solve, C = 0, 0.0, 0.0, np.zeros((6, 6))
+        for i in range(6):
             g = np.zeros(6)
             g[i] = 1e-3
             ctx.upload("u", u_host)          # H2D: zero start field
@@ -483,23 +483,46 @@ def run_config2(env):
             iters += r["iters"]
             t_loop += r["loop_ms"] * 1e-3
             t_solve += r["elapsed_ms"] * 1e-3
+        return iters, t_loop, t_solve, C
+
+    def batched():      # the six load cases as lanes of one CG loop (fans_solve_batch); lanes start from u = 0 on the device
+        res, sig = ctx.solve_batch(1e-3 * np.eye(6), 500, 1e-10, "Linfinity", "absolute")
+        return sum(r["iters"] for r in res), res[0]["loop_ms"] * 1e-3, res[0]["elapsed_ms"] * 1e-3, sig.T / 1e-3
+
+    use_batch = env.world == 1 and not args.sequential
+    seq = None
+    if use_batch:       # the one-after-the-other form next to it, for the record
+        batched()       # warm-up: lane buffers
+        ts = time.perf_counter()
+        it_s, tl_s, _, C_s = sequential()
+        seq = {"iters": it_s, "ms_per_step": 1e3 * tl_s / it_s, "wall_s_total": time.perf_counter() - ts}
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    with ClockSampler(dev) as cs:
+        iters, t_loop, t_solve, C = batched() if use_batch else sequential()
         env.barrier()
     t_wall = env.max_over_ranks(time.perf_counter() - t0)
     t_loop = env.max_over_ranks(t_loop)
     l1 = ctx.launch_count()
+    if seq is not None:
+        seq["tangent_max_rel_diff"] = float(np.abs(C - C_s).max() / np.abs(C_s).max())
     ctx.close()
     if env.rank != 0:
         return None
     dof = 3.0 * env.nvox
     line = base_line(env, dof * iters / t_loop, t_loop, iters, 3,
                      "config 2: linear-elastic two-phase sphere %dx%dx%d, CG to Linf 1e-10, 6 unit load cases 1e-3 e_i" % tuple(dims),
-                     {"load_cases": 6})
+                     {"load_cases": 6, "batched": bool(use_batch)})
     peaks, which = measured_peaks()
     gbs = BYTES_PER_VOXEL_ITER_H3 * env.nloc * iters / t_loop / 1e9
     line.update({"hbm_roofline_iteration": {"bytes_per_voxel_iter": BYTES_PER_VOXEL_ITER_H3, "achieved_gbs_per_gpu": gbs,
                                             "peak_gbs": float(peaks["hbm_gbs"]), "frac": gbs / float(peaks["hbm_gbs"]), "peak_source": which},
-                 "e2e": {"value": dof * iters / t_wall, "unit": "voxel-DOF/s", "h2d_bytes_per_step": env.world * 6.0 * u_host.nbytes / iters,
-                         "d2h_bytes_per_step": 6.0 * 48 / iters, "what": "6 x (upload u, solve, homogenized stress), wall clock"},
+                 "e2e": {"value": dof * iters / t_wall, "unit": "voxel-DOF/s",
+                         "h2d_bytes_per_step": (288.0 if use_batch else env.world * 6.0 * u_host.nbytes) / iters,
+                         "d2h_bytes_per_step": 6.0 * 48 / iters,
+                         "what": ("fans_solve_batch: 6 macroscopic strains in, 6 homogenized stresses out, wall clock" if use_batch
+                                  else "6 x (upload u, solve, homogenized stress), wall clock")},
+                 "sequential": seq,
                  "solve_s_total": t_solve, "wall_s_total": t_wall, "clocks": cs.summary(), "gpu_launches": l1 - l0,
                  "homogenized_tangent": [[float(x) for x in row] for row in 0.5 * (C + C.T)]})
     return line

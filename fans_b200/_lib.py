@@ -58,7 +58,7 @@ EXPORTS = [
     "fans_field_upload", "fans_field_download", "fans_field_zero", "fans_field_copy", "fans_residual", "fans_apply_linear",
     "fans_convolution", "fans_dot", "fans_axpy", "fans_norm", "fans_solve", "fans_homogenized_stress", "fans_commit_history",
     "fans_extrapolate_displacement", "fans_get_field", "fans_strain_stress", "fans_strain_stress_gp", "fans_launch_count", "fans_set_profiling", "fans_get_profile", "fans_comm_unique_id", "fans_comm_create",
-    "fans_comm_destroy", "fans_allreduce_sum",
+    "fans_comm_destroy", "fans_allreduce_sum", "fans_solve_batch", "fans_batch_load_displacement", "fans_batch_release",
 ]
 
 _lib = None
@@ -103,6 +103,9 @@ def load():
     lib.fans_norm.argtypes = [P, C.c_int32, C.c_int32, dp]
     lib.fans_solve.argtypes = [P, C.POINTER(SolveParams), C.POINTER(SolveResult), dp]
     lib.fans_homogenized_stress.argtypes = [P, dp]
+    lib.fans_solve_batch.argtypes = [P, C.c_int32, dp, C.POINTER(SolveParams), C.POINTER(SolveResult), dp, dp]
+    lib.fans_batch_load_displacement.argtypes = [P, C.c_int32, C.c_int32]
+    lib.fans_batch_release.argtypes = [P]
     lib.fans_commit_history.argtypes = [P]
     lib.fans_extrapolate_displacement.argtypes = [P]
     lib.fans_get_field.argtypes = [P, C.c_char_p, C.c_void_p, C.c_size_t]
@@ -282,6 +285,31 @@ class Context:
         self._ck(self.lib.fans_solve(self.ptr, C.byref(p), C.byref(r), _dptr(hist)))
         return {"iters": r.iters, "n_residual_evals": r.n_residual_evals, "err_last": r.err_last, "elapsed_ms": r.elapsed_ms,
                 "loop_ms": r.loop_ms, "fft_ms": r.fft_ms, "err_all": hist[: r.iters + 1].copy()}
+
+    def solve_batch(self, macro, n_it=100, tol=1e-10, measure="Linfinity", err_type="absolute", verbose=False):
+        """n_b linear load cases as lanes of ONE CG loop (fans_solve_batch; the loop of get_homogenized_tangent, solver.h:762-775).
+        macro: [n_b][n_str].  Returns (list of per-lane result dicts, homogenized stresses [n_b][n_str])."""
+        macro = np.ascontiguousarray(macro, dtype=np.float64).reshape(-1, self.n_str)
+        nb = macro.shape[0]
+        if measure not in MEASURE:
+            raise FansError("Unknown measure type: " + str(measure))
+        if err_type not in ERRTYPE:
+            raise FansError("Unknown error type: " + str(err_type))
+        p = SolveParams(METHOD["cg"], int(n_it), float(tol), MEASURE[measure], ERRTYPE[err_type], 5, 1e-2, int(bool(verbose)), 0)
+        res = (SolveResult * nb)()
+        hist = np.zeros((nb, int(n_it) + 1))
+        stress = np.zeros((nb, self.n_str))
+        self._ck(self.lib.fans_solve_batch(self.ptr, nb, _dptr(macro), C.byref(p), res, _dptr(stress), _dptr(hist)))
+        out = [{"iters": r.iters, "n_residual_evals": r.n_residual_evals, "err_last": r.err_last, "elapsed_ms": r.elapsed_ms,
+                "loop_ms": r.loop_ms, "fft_ms": r.fft_ms, "err_all": hist[i, : r.iters + 1].copy()} for i, r in enumerate(res)]
+        return out, stress
+
+    def batch_displacement(self, lane, field="u"):
+        """copies the displacement of one lane of the last solve_batch into a field of the context (default: u)"""
+        self._ck(self.lib.fans_batch_load_displacement(self.ptr, int(lane), FIELD[field] if isinstance(field, str) else int(field)))
+
+    def batch_release(self):
+        self._ck(self.lib.fans_batch_release(self.ptr))
 
     def homogenized_stress(self):
         out = np.zeros(self.n_str)

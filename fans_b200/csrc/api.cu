@@ -404,6 +404,7 @@ extern "C" void fans_destroy(fans_ctx *ctx)
                     ctx->hist, ctx->hist_t, ctx->hidx, ctx->pflag, ctx->d_Stab, ctx->d_part, ctx->d_red, ctx->d_ticket, ctx->d_flag, ctx->d_C};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    batch_arena_free(ctx);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_fault) cudaFreeHost(ctx->h_fault);

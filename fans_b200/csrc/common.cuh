@@ -154,6 +154,18 @@ struct fans_ctx {
     std::vector<cudaEvent_t> conv_pool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_pending;
 
+    // batched linear solves (solve.cu, fans_solve_batch): `nb` right-hand sides ("lanes") travel through every pass of the
+    // iteration in ONE launch.  Lane l of a field lives at base + l * h * nloc, of the spectrum at base + l * h * cStride, its scalar
+    // block at d_red + l * S_COUNT.  nb == 1 outside a batched solve.
+    int nb = 1;
+    struct BatchArena {
+        int lanes = 0;
+        double *field[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // U, R, S, D, D_alt, K.d
+        double2 *spec = nullptr;
+        double *red = nullptr, *h_red = nullptr, *part = nullptr, *h_flag = nullptr;
+        unsigned int *ticket = nullptr;
+    } arena;
+
     std::string err;
     int64_t launches = 0;
     int n_residual_evals = 0;
@@ -232,14 +244,13 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double *scratch)
 
 // Grid-level deterministic reduce: every block deposits its NV partials, the last block to arrive
 // (ticket counter) folds them in fixed block order and writes out[0..NV). "one grid-level reduce".
+// grid_reduce_part: the same over a SUBSET of the grid (one lane of a batched launch): `nb` CTAs numbered `bid` share part / ticket / out.
 template <int NV, int NSUM>
-__device__ __forceinline__ void grid_reduce(double (&v)[NV], double *scratch, double *part, unsigned int *ticket,
-                                            double *out, bool accumulate = false)
+__device__ __forceinline__ void grid_reduce_part(double (&v)[NV], double *scratch, double *part, unsigned int *ticket,
+                                                 double *out, bool accumulate, const unsigned nb, const unsigned bid)
 {
     block_reduce<NV, NSUM>(v, scratch);
     __shared__ bool is_last;
-    const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
-    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) part[(size_t)i * nb + bid] = v[i];
@@ -269,10 +280,18 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *scratch, do
         }
     }
 }
+template <int NV, int NSUM>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double *scratch, double *part, unsigned int *ticket,
+                                            double *out, bool accumulate = false)
+{
+    grid_reduce_part<NV, NSUM>(v, scratch, part, ticket, out, accumulate, gridDim.x * gridDim.y * gridDim.z,
+                               blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+}
 
 // scalar form of grid_reduce<1, 1>: the same deterministic two-level sum without an array argument (an array handed over by
 // reference pins the caller's accumulator to a local-memory slot for its whole lifetime)
-__device__ __forceinline__ void grid_reduce_sum1(double v, double *scratch, double *part, unsigned int *ticket, double *out)
+__device__ __forceinline__ void grid_reduce_sum1_part(double v, double *scratch, double *part, unsigned int *ticket, double *out,
+                                                      const unsigned nb, const unsigned bid)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = warp_sum(v);
@@ -281,8 +300,6 @@ __device__ __forceinline__ void grid_reduce_sum1(double v, double *scratch, doub
     __syncthreads();
     if (wid == 0) v = warp_sum(lane < nw ? scratch[lane] : 0.0);
     __shared__ bool is_last1;
-    const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
-    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     if (threadIdx.x == 0) {
         part[bid] = v;
         __threadfence();
@@ -305,5 +322,10 @@ __device__ __forceinline__ void grid_reduce_sum1(double v, double *scratch, doub
             }
         }
     }
+}
+__device__ __forceinline__ void grid_reduce_sum1(double v, double *scratch, double *part, unsigned int *ticket, double *out)
+{
+    grid_reduce_sum1_part(v, scratch, part, ticket, out, gridDim.x * gridDim.y * gridDim.z,
+                          blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
 }
 #endif

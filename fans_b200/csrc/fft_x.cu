@@ -31,8 +31,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int N, int H, int T>
 __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (N / rp_elems(N)) * T))
     k_fft_xg(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,
-             int nWork, PeerTable peers)
+             int nWork, PeerTable peers, int nb)
 {
+    // batched solves (nb > 1 lanes): work item wq = tile * nb + lane — the lanes of one tile run next to each other, so its Gamma_hat
+    // block comes from HBM once and from L2 for the other lanes; lane l of the spectrum starts at spec + l * H * cStride
     // One thread group per component: every thread carries E points of ONE component through the stages (32 data registers),
     // the H groups share the barriers.  At the Fourier-space boundary the groups swap their values through thread-private
     // slots of the (then idle) exchange tiles and each group forms its own row of  Gamma_hat r_hat.
@@ -46,7 +48,10 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
     const TileIdxX<T> idx{t};
     using GSync = SyncGroup<(H > 1 && NTC % 32 == 0)>;
     const GSync gsync{1 + c, NTC};  // the stage exchanges of one component only involve its own thread group
-    auto tile_ptr = [&](int w) { return spec + (size_t)c * g.cStride + (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t; };
+    auto tile_ptr = [&](int wq) {
+        const int w = wq / nb, ln = wq - w * nb;
+        return spec + (size_t)(ln * H + c) * g.cStride + (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t;
+    };
     auto issue = [&](int w, int buf) {
         const double2 *src = tile_ptr(w);
         double2 *dst = sm + buf * BUF + c * (N * T) + tc;
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
         double2 *S = sm + cur * BUF;      // all components of this tile
         double2 *X = S + c * (N * T);     // this group's exchange tile
         double2 *base = tile_ptr(w);
-        const double *gam = gamma + (size_t)w * NG * (N * T) + jt * T + t;
+        const double *gam = gamma + (size_t)(w / nb) * NG * (N * T) + jt * T + t;
         double2 a[1][E];
         cp_async_wait_all();
 #pragma unroll
@@ -123,28 +128,34 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
 template <int N, int T, bool PF>
 __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 * 1024) ? 2 : 1)
     k_fft_xg_seq(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,
-                 int nWork, PeerTable peers, int tile0, int ntc)
+                 int nWork, PeerTable peers, int tile0, int ntc, int nb)
 {
     // work item q of this launch = (y row q / ntc, kz tile tile0 + q % ntc): the whole spectrum (tile0 = 0, ntc = nTiles) or one
-    // kz chunk of the slab pipeline; `w` below is the item's index in the full (row, tile) numbering the Gamma layout uses
+    // kz chunk of the slab pipeline; `w` below is the item's index in the full (row, tile) numbering the Gamma layout uses.
+    // Batched solves (nb > 1 lanes): item = q * nb + lane, lane l of the spectrum starts at spec + l * 3 * cStride; the lanes of a tile
+    // are in flight together, so its Gamma_hat block comes from HBM once and from L2 for the others.
     extern __shared__ double2 sm[];  // [3][N*T]
     constexpr int H = 3, E = rp_elems(N), TPC = N / E, NST = rp_nstages(N), NG = 6, NTC = TPC * T;
     constexpr size_t NT = (size_t)N * T;
     const int tc = threadIdx.x, t = tc % T, jt = tc / T;
     const TileIdxX<T> idx{t};
     auto tile_off = [&](int w) { return (size_t)(w / nTiles) * g.kzp + (size_t)(w % nTiles) * T + t; };
-    auto prefetch = [&](int w, int c) {   // rows of component c of tile w -> this thread's slots of tile c; one commit group
-        const double2 *base = spec + (size_t)c * g.cStride + tile_off(w);
+    auto prefetch = [&](int w, int c, int ln) {   // rows of component c of tile w, lane ln -> this thread's slots of tile c; one commit group
+        const double2 *base = spec + (size_t)(ln * H + c) * g.cStride + tile_off(w);
         double2 *dst = sm + c * NT + tc;
 #pragma unroll
         for (int e = 0; e < E; ++e) cp_async16(dst + e * NTC, base + spec_row_x(g, rp_row<N, 0>(jt, e)));
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    auto full_index = [&](int q) { return (q / ntc) * nTiles + tile0 + q % ntc; };
-    if (PF && (int)blockIdx.x < nWork) prefetch(full_index(blockIdx.x), 0);
+    auto full_index = [&](int qb) {
+        const int q = qb / nb;
+        return (q / ntc) * nTiles + tile0 + q % ntc;
+    };
+    if (PF && (int)blockIdx.x < nWork) prefetch(full_index(blockIdx.x), 0, blockIdx.x % nb);
     for (int q = blockIdx.x; q < nWork; q += gridDim.x) {
-        const int w = full_index(q);
+        const int w = full_index(q), ln = q % nb;
         const size_t off = tile_off(w);
+        double2 *lspec = spec + (size_t)ln * H * g.cStride;
         double2 a[1][E];
 #pragma unroll 1
         for (int c = 0; c < H; ++c) {
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 
             if (PF) {
                 // tile c+1 is idle (its last use, the previous tile's inverse transform, lies behind barriers every thread has passed)
                 if (c + 1 < H) {
-                    prefetch(w, c + 1);
+                    prefetch(w, c + 1, ln);
                     asm volatile("cp.async.wait_group 1;\n" ::: "memory");
                 } else {
                     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 
                 for (int e = 0; e < E; ++e) a[0][e] = X[e * NTC + tc];
                 if (NST > 1) __syncthreads();  // everybody holds its rows before the first exchange overwrites the slots
             } else {
-                const double2 *base = spec + (size_t)c * g.cStride + off;
+                const double2 *base = lspec + (size_t)c * g.cStride + off;
 #pragma unroll
                 for (int e = 0; e < E; ++e) a[0][e] = base[spec_row_x(g, rp_row<N, 0>(jt, e))];
             }
@@ -196,16 +207,16 @@ __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 
                     peer_select(peers, row >> g.l2n0)[poff + (size_t)(row & (g.n0 - 1)) * g.xStride] = a[0][e];
                 }
             } else {
-                double2 *base = spec + (size_t)c * g.cStride + off;
+                double2 *base = lspec + (size_t)c * g.cStride + off;
 #pragma unroll
                 for (int e = 0; e < E; ++e) base[spec_row_x(g, rp_row<N, 0>(jt, e))] = a[0][e];
             }
             // component 1 is through its inverse transform => every thread has left tile 0: the next tile's first component may land
-            if (PF && c == 1 && NST > 1 && q + (int)gridDim.x < nWork) prefetch(full_index(q + gridDim.x), 0);
+            if (PF && c == 1 && NST > 1 && q + (int)gridDim.x < nWork) prefetch(full_index(q + gridDim.x), 0, (q + gridDim.x) % nb);
         }
         if (PF && NST <= 1 && q + (int)gridDim.x < nWork) {  // single-stage transforms have no barriers to lean on
             __syncthreads();
-            prefetch(full_index(q + gridDim.x), 0);
+            prefetch(full_index(q + gridDim.x), 0, (q + gridDim.x) % nb);
         }
     }
 }
@@ -232,7 +243,7 @@ static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const
     }
     const int tile0 = xp.ntile > 0 ? xp.tile0 : 0, ntc = xp.ntile > 0 ? std::min(xp.ntile, nTiles - tile0) : nTiles;
     if (ntc <= 0) return FANS_OK;
-    const int nWork = ctx->n1 * ntc;
+    const int nWork = ctx->n1 * ntc * ctx->nb;
     int grid = FANS_SMS * resident;
     if (const char *env = getenv("FANS_XG_GRID")) grid = atoi(env);
     if (xp.grid_cap > 0 && grid > xp.grid_cap * resident) grid = xp.grid_cap * resident;
@@ -241,8 +252,8 @@ static int launch_xg_seq(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const
     // the extra barrier per component costs more than the hidden latency (3.42 -> 3.70 ms on the 8-GPU run), so it stays off there
     const char *pf = getenv("FANS_XG_PF");   // 0 / 1: force plain loads / prefetch (A/B runs)
     const bool use_pf = pf ? atoi(pf) != 0 : (T == 8);
-    if (!use_pf) k_fft_xg_seq<N, T, false><<<grid, NTHR, smem, xp.st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers, tile0, ntc);
-    else k_fft_xg_seq<N, T, true><<<grid, NTHR, smem, xp.st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers, tile0, ntc);
+    if (!use_pf) k_fft_xg_seq<N, T, false><<<grid, NTHR, smem, xp.st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers, tile0, ntc, ctx->nb);
+    else k_fft_xg_seq<N, T, true><<<grid, NTHR, smem, xp.st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers, tile0, ntc, ctx->nb);
     return FANS_OK;
 }
 
@@ -262,11 +273,11 @@ static int launch_xg(fans_ctx *ctx, double2 *specB, const SpecGeom &g, const Pee
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fft_xg<N, H, T>, NTHR, smem));
         if (resident < 1) resident = 1;
     }
-    const int nWork = ctx->n1 * nTiles;
+    const int nWork = ctx->n1 * nTiles * ctx->nb;
     int grid = FANS_SMS * resident;
     if (const char *env = getenv("FANS_XG_GRID")) grid = atoi(env);
     if (grid > nWork) grid = nWork;
-    k_fft_xg<N, H, T><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers);
+    k_fft_xg<N, H, T><<<grid, NTHR, smem, ctx->st>>>(specB, ctx->gamma, ctx->planx.tw, g, nTiles, nWork, peers, ctx->nb);
     return FANS_OK;
 }
 

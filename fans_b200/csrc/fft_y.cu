@@ -140,7 +140,8 @@ SpecGeom spec_geom_A(const fans_ctx *ctx)
 }
 
 // y pass (forward or inverse) on the local x-slab
-int fft_pass_y(fans_ctx *ctx, bool inverse) { return fft_pass_y_part(ctx, inverse, YLaunch{ctx->st, 0, ctx->h, 0, nullptr, 0}); }
+// (a batched solve transforms the h components of all its lanes as nb * h components of one launch)
+int fft_pass_y(fans_ctx *ctx, bool inverse) { return fft_pass_y_part(ctx, inverse, YLaunch{ctx->st, 0, ctx->h * ctx->nb, 0, nullptr, 0}); }
 
 // the same for the components [c0, c0 + nc) on stream yl.st with at most yl.grid CTAs (0: one per tile)
 int fft_pass_y_part(fans_ctx *ctx, bool inverse, const YLaunch &yl)

@@ -77,12 +77,15 @@ __global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zi(const double2 
                                                                   const double *__restrict__ dotw, double *part,
                                                                   unsigned int *ticket, double *red_out, int accumulate)
 {
+    // batched solves: blockIdx.y = lane; a lane owns the lines [lane * nlines, (lane + 1) * nlines) (line0 = 0) and its own
+    // partial sums, ticket and scalar block
     extern __shared__ double2 sm[];
     __shared__ double scratch[32];
     constexpr int E = rp_elems(NH), TPL = z_tpl(NH), LPB = z_lpb(NH), NST = rp_nstages(NH), PITCH = zline_pitch(NH);
     const int l = threadIdx.x / TPL, jt = threadIdx.x % TPL;
-    const size_t line = line0 + (size_t)blockIdx.x * LPB + l;  // lines [line0, nlines) belong to this launch
-    const bool valid = line < nlines;
+    const size_t lline = line0 + (size_t)blockIdx.x * LPB + l;  // lines [line0, nlines) belong to this launch
+    const bool valid = lline < nlines;
+    const size_t line = lline + (size_t)blockIdx.y * nlines;
     double2 *sml = sm + l * PITCH;
     const LineIdx idx;
     if (valid) {
@@ -122,7 +125,9 @@ __global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zi(const double2 
             out[row] = v;
         }
     }
-    if (red_out) grid_reduce<1, 1>(acc, scratch, part, ticket, red_out, accumulate != 0);
+    if (red_out)
+        grid_reduce_part<1, 1>(acc, scratch, part + (size_t)blockIdx.y * gridDim.x, ticket + blockIdx.y, red_out + (size_t)blockIdx.y * S_COUNT,
+                               accumulate != 0, gridDim.x, blockIdx.x);
 }
 
 template <int NH>
@@ -141,7 +146,8 @@ static int launch_zi(fans_ctx *ctx, double *out, const SpecGeom &g, size_t line0
     constexpr int LPB = z_lpb(NH), NTHR = z_tpl(NH) * LPB;
     const size_t smem = sizeof(double2) * zline_pitch(NH) * LPB;
     if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_zi<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fft_zi<NH><<<(unsigned)((nlines - line0 + LPB - 1) / LPB), NTHR, smem, st>>>(ctx->spec, out, ctx->planz.tw, ctx->planz.pos, g, ctx->ny, line0,
+    const dim3 grid((unsigned)((nlines - line0 + LPB - 1) / LPB), (unsigned)ctx->nb);
+    k_fft_zi<NH><<<grid, NTHR, smem, st>>>(ctx->spec, out, ctx->planz.tw, ctx->planz.pos, g, ctx->ny, line0,
                                                                                  nlines, scale, dotw, ctx->d_part, ctx->d_ticket, red_out, accumulate ? 1 : 0);
     return FANS_OK;
 }
@@ -160,7 +166,8 @@ static int launch_zi(fans_ctx *ctx, double *out, const SpecGeom &g, size_t line0
     default: fans_set_error(ctx, FANS_ERR_ARG, "unsupported n_z for the z pass");                              \
     }
 
-int fft_pass_z_fwd(fans_ctx *ctx, const double *in) { return fft_pass_z_fwd_part(ctx, in, 0, ctx->h, ctx->st); }
+// (a batched solve transforms the h components of all its lanes as nb * h components of one launch)
+int fft_pass_z_fwd(fans_ctx *ctx, const double *in) { return fft_pass_z_fwd_part(ctx, in, 0, ctx->h * ctx->nb, ctx->st); }
 
 // components [c0, c0 + nc) only, on stream st (slab pipeline, solve.cu)
 int fft_pass_z_fwd_part(fans_ctx *ctx, const double *in, int c0, int nc, cudaStream_t st)

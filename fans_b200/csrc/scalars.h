@@ -6,6 +6,7 @@ enum {
     S_RS = 2,        // <r, s_new> deposited by the c2r epilogue
     S_DKD = 3,       // <d, K d>                      (solverCG.h:105)
     S_BETA = 4,      // fmax(0, (delta - deltamid)/delta0)   (solverCG.h:94)
+    S_FREEZE = 5,    // batched solves: != 0 once this lane has converged — k_cg_update leaves its r and u alone
     S_L1 = 8,        // sum |r|      -- the next four are written together by k_cg_update / k_reduce4
     S_L2SQ = 9,      // sum r^2
     S_DELTAMID = 10, // <r, s>                        (solverCG.h:86)

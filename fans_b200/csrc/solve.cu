@@ -18,7 +18,7 @@ int check_fault_cached(fans_ctx *ctx);
 
 int read_scalars(fans_ctx *ctx)
 {
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT * ctx->nb, cudaMemcpyDeviceToHost, ctx->st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fault, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));   // see check_fault_cached
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
     prof_resolve(ctx);
@@ -455,5 +455,236 @@ extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_
     res->fft_ms = conv_time_resolve(ctx);
     res->iters = es.iter;
     res->n_residual_evals = ctx->n_residual_evals - evals0;
+    return FANS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched linear solves.  Solver::get_homogenized_tangent (solver.h:739-778) runs n_str solves one after the other over the same
+// microstructure and the same Gamma_hat; config 2 of the reference's benchmark set is exactly these "6 load cases".  Here the n_b
+// right-hand sides are LANES of one CG loop: every pass of the iteration (z/y/x transforms, Gamma_hat multiply, stencil, update)
+// is ONE launch over all lanes, each lane with its own scalar block (alpha, beta, delta, norms) on the device.  What the lanes
+// share — Gamma_hat in the x pass (24 of 554 B/voxel), the phase image in the stencil (2 B) — is read from HBM once per tile and
+// from L2 for the other lanes; what a small grid cannot fill by itself (a 32^3 micro problem keeps 8..30 of 148 SMs busy and is
+// launch-latency bound) the lanes fill together.  A lane that has converged is frozen (S_FREEZE) and keeps its u and r bit for bit.
+// Every lane runs the arithmetic of the single solve on its own data, so lane l reproduces fans_solve with g0 = macro[l], u = 0.
+// ------------------------------------------------------------------------------------------------
+void batch_arena_free(fans_ctx *ctx)
+{
+    auto &A = ctx->arena;
+    for (double *&f : A.field)
+        if (f) cudaFree(f), f = nullptr;
+    if (A.spec) cudaFree(A.spec), A.spec = nullptr;
+    if (A.red) cudaFree(A.red), A.red = nullptr;
+    if (A.part) cudaFree(A.part), A.part = nullptr;
+    if (A.ticket) cudaFree(A.ticket), A.ticket = nullptr;
+    if (A.h_red) cudaFreeHost(A.h_red), A.h_red = nullptr;
+    if (A.h_flag) cudaFreeHost(A.h_flag), A.h_flag = nullptr;
+    A.lanes = 0;
+}
+
+static size_t batch_lane_parts(const fans_ctx *ctx)
+{
+    // partial sums one lane needs: z inverse pass (one per CTA, at most one CTA per line), update (4 per CTA), stencil (one per CTA)
+    return std::max<size_t>((size_t)ctx->h * ctx->n0 * ctx->ny + 64, 4 * (size_t)FANS_SMS * 16 + 64);
+}
+
+static int batch_arena_ensure(fans_ctx *ctx, int lanes)
+{
+    auto &A = ctx->arena;
+    if (A.lanes >= lanes) return FANS_OK;
+    batch_arena_free(ctx);
+    const size_t fN = (size_t)ctx->h * ctx->nloc;
+    const size_t specN = (size_t)ctx->h * ctx->n0 * ((size_t)ctx->n1 * ctx->kzp + ctx->xpad);
+    auto fail = [&](const char *what) {
+        cudaGetLastError();
+        batch_arena_free(ctx);
+        fans_set_error(ctx, FANS_ERR_CUDA, std::string("fans_solve_batch: out of device memory for ") + std::to_string(lanes) + " lanes (" + what + ")");
+        return FANS_ERR_CUDA;
+    };
+    for (double *&f : A.field) {
+        if (cudaMalloc(&f, sizeof(double) * (fN * lanes + 2)) != cudaSuccess) return fail("fields");
+        if (cudaMemsetAsync(f, 0, sizeof(double) * (fN * lanes + 2), ctx->st) != cudaSuccess) return fail("fields");
+    }
+    if (cudaMalloc(&A.spec, sizeof(double2) * specN * lanes) != cudaSuccess) return fail("spectrum");
+    if (cudaMemsetAsync(A.spec, 0, sizeof(double2) * specN * lanes, ctx->st) != cudaSuccess) return fail("spectrum");
+    const size_t nparts = std::max<size_t>((size_t)1 << 20, batch_lane_parts(ctx) * lanes);
+    if (cudaMalloc(&A.part, sizeof(double) * nparts) != cudaSuccess) return fail("partial sums");
+    if (cudaMalloc(&A.red, sizeof(double) * S_COUNT * lanes) != cudaSuccess) return fail("scalars");
+    if (cudaMalloc(&A.ticket, sizeof(unsigned int) * (lanes + 2)) != cudaSuccess) return fail("tickets");
+    if (cudaMemsetAsync(A.ticket, 0, sizeof(unsigned int) * (lanes + 2), ctx->st) != cudaSuccess) return fail("tickets");
+    if (cudaMallocHost(&A.h_red, sizeof(double) * S_COUNT * lanes) != cudaSuccess) return fail("pinned scalars");
+    if (cudaMallocHost(&A.h_flag, sizeof(double) * lanes) != cudaSuccess) return fail("pinned flags");
+    A.lanes = lanes;
+    return FANS_OK;
+}
+
+// why this context cannot run a batched solve (nullptr: it can)
+static const char *batch_unsupported(const fans_ctx *ctx, const fans_solve_params *p)
+{
+    if (!ctx->materials_ready || !ctx->ms_ready || !ctx->gamma_ready) return "microstructure, materials and reference stiffness must be set first";
+    if (!ctx->all_linear) return "batched solves need linear material models (the reference's perturbation loop remains for the others)";
+    if (!stencil_supported(ctx)) return "batched solves use the stencil form of the linear operator (even n_z, one stiffness per phase)";
+    if (ctx->P > 1) return "batched solves run on one GPU (slab-decomposed problems solve the load cases one after the other)";
+    if (ctx->any_fft) return "batched solves need power-of-two grid dimensions";
+    if (((size_t)ctx->h * ctx->nloc) % 2) return "batched solves need an even number of field values";
+    if (p->method != FANS_METHOD_CG) return "batched solves use the CG method";
+    if (ctx->mixed) return "batched solves are strain-driven (disable mixed boundary conditions)";
+    return nullptr;
+}
+
+extern "C" int fans_solve_batch(fans_ctx *ctx, int32_t nb, const double *macro, const fans_solve_params *p, fans_solve_result *res,
+                                double *stress_out, double *err_hist)
+{
+    if (!ctx || !macro || !p || !res || nb < 1 || nb > FANS_MAX_BATCH) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (const char *why = batch_unsupported(ctx, p)) {
+        fans_set_error(ctx, FANS_ERR_STATE, std::string("fans_solve_batch: ") + why);
+        return FANS_ERR_STATE;
+    }
+    if (p->measure < FANS_MEASURE_L1 || p->measure > FANS_MEASURE_LINF) {
+        fans_set_error(ctx, FANS_ERR_ARG, "Unknown measure type");
+        return FANS_ERR_ARG;
+    }
+    if (p->err_type != FANS_ERR_ABSOLUTE && p->err_type != FANS_ERR_RELATIVE) {
+        fans_set_error(ctx, FANS_ERR_ARG, "Unknown error type");
+        return FANS_ERR_ARG;
+    }
+    FANS_CHECK(batch_arena_ensure(ctx, nb));
+    auto &A = ctx->arena;
+    const size_t fN = (size_t)ctx->h * ctx->nloc;
+    const int nstr = ctx->nstr;
+    double *U = A.field[0], *R = A.field[1], *S = A.field[2], *D = A.field[3], *Dalt = A.field[4], *KD = A.field[5];
+    memset(res, 0, sizeof(*res) * nb);
+    if (err_hist)
+        for (size_t i = 0; i < (size_t)nb * (p->n_it + 1); ++i) err_hist[i] = 0.0;
+
+    // the context's own scalars, spectrum and gradient are swapped for the arena's while the lanes run
+    struct Swap {
+        fans_ctx *c;
+        double2 *spec;
+        double *red, *h_red, *part;
+        unsigned int *ticket;
+        double g0[9];
+        ~Swap()
+        {
+            c->spec = spec, c->d_red = red, c->h_red = h_red, c->d_part = part, c->d_ticket = ticket, c->nb = 1;
+            memcpy(c->g0, g0, sizeof(g0));
+        }
+    } swap{ctx, ctx->spec, ctx->d_red, ctx->h_red, ctx->d_part, ctx->d_ticket, {}};
+    memcpy(swap.g0, ctx->g0, sizeof(swap.g0));
+    ctx->spec = A.spec, ctx->d_red = A.red, ctx->h_red = A.h_red, ctx->d_part = A.part, ctx->d_ticket = A.ticket;
+
+    const int evals0 = ctx->n_residual_evals;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    conv_time_resolve(ctx);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->st));
+    for (double *f : {U, S, D}) CUDA_TRY(ctx, cudaMemsetAsync(f, 0, sizeof(double) * fN * nb, ctx->st));
+    CUDA_TRY(ctx, cudaMemsetAsync(A.red, 0, sizeof(double) * S_COUNT * nb, ctx->st));
+
+    // initial residuals r_l = residual(u = 0; g0 = macro[l]) and their error norms, lane by lane (solverCG.h:76-80)
+    std::vector<ErrState> es(nb);
+    std::vector<double> err(nb, 0.0);
+    std::vector<char> active(nb, 1);
+    for (int l = 0; l < nb; ++l) {
+        es[l] = ErrState{p->measure, p->err_type, 0.0, err_hist ? err_hist + (size_t)l * (p->n_it + 1) : nullptr, 0};
+        for (int i = 0; i < nstr; ++i) ctx->g0[i] = macro[(size_t)l * nstr + i];
+        ctx->n_residual_evals++;
+        FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, U + l * fN, R + l * fN, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        FANS_CHECK(compute_error(ctx, R + l * fN, es[l], &err[l]));   // uses lane 0's generic scalar slots, read back at once
+        FANS_CHECK(check_fault_cached(ctx));
+        if (p->verbose) printf("lane %d it %3d .... err %16.8e\n", l, 0, es[l].hist ? es[l].hist[0] : err[l]);
+    }
+    // delta = 1, deltamid = <r, s> = 0 (s = 0), nothing frozen
+    for (int l = 0; l < nb; ++l) {
+        for (int i = 0; i < S_COUNT; ++i) A.h_red[(size_t)l * S_COUNT + i] = 0.0;
+        A.h_red[(size_t)l * S_COUNT + S_DELTA] = 1.0;
+        A.h_flag[l] = 1.0;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(A.red, A.h_red, sizeof(double) * S_COUNT * nb, cudaMemcpyHostToDevice, ctx->st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+    auto freeze = [&](int l) -> int {
+        active[l] = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(A.red + (size_t)l * S_COUNT + S_FREEZE, A.h_flag + l, sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+        return FANS_OK;
+    };
+    int n_active = 0;
+    for (int l = 0; l < nb; ++l) {
+        if (p->n_it > 0 && err[l] > p->tol) n_active++;
+        else FANS_CHECK(freeze(l));
+    }
+    ctx->nb = nb;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
+    int sweeps = 0;
+    while (n_active > 0) {
+        FANS_CHECK(conv_run(ctx, R, S, -1.0, R, ctx->d_red + S_RS));              // s = -Gamma r, <r, s> per lane
+        FANS_CHECK(vec_scalars_after_conv(ctx));                                   // delta0, delta, beta per lane
+        FANS_CHECK(stencil_run(ctx, D, KD, S, Dalt, ctx->d_red + S_BETA, ctx->d_red + S_DKD));   // d = s + beta d, K d, <d, K d>
+        std::swap(D, Dalt);
+        FANS_CHECK(vec_cg_update(ctx, R, KD, U, D, S));                            // r, u, norms, <r, s> per lane
+        FANS_CHECK(read_scalars(ctx));
+        sweeps++;
+        for (int l = 0; l < nb; ++l) {
+            if (!active[l]) continue;
+            es[l].iter++;
+            err[l] = error_from_scalars(ctx, es[l], l * S_COUNT + S_L1);
+            if (p->verbose) printf("lane %d it %3d .... err %16.8e\n", l, es[l].iter, es[l].hist ? es[l].hist[es[l].iter] : err[l]);
+            if (!(es[l].iter < p->n_it && err[l] > p->tol)) {
+                FANS_CHECK(freeze(l));
+                n_active--;
+            }
+        }
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop1, ctx->st));
+    ctx->nb = 1;
+    A.field[3] = D, A.field[4] = Dalt;
+    ctx->n_residual_evals += sweeps * nb;
+    // homogenized stress of every lane (solver.h:707-737), lane by lane through the element sweep
+    if (stress_out) {
+        const double N = (double)ctx->nx * ctx->ny * ctx->nz;
+        for (int l = 0; l < nb; ++l) {
+            for (int i = 0; i < nstr; ++i) ctx->g0[i] = macro[(size_t)l * nstr + i];
+            FANS_CHECK(sweep_run(ctx, SWEEP_STRAINSTRESS, U + l * fN, nullptr, nullptr, nullptr, nullptr, ctx->d_red + S_STRESS, nullptr, nullptr));
+            FANS_CHECK(read_scalars(ctx));
+            for (int i = 0; i < nstr; ++i) stress_out[(size_t)l * nstr + i] = ctx->h_red[S_STRESS + i] / N;
+        }
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->st));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f, lms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&lms, ctx->ev_loop0, ctx->ev_loop1));
+    prof_resolve(ctx);
+    const double fft_ms = conv_time_resolve(ctx);
+    for (int l = 0; l < nb; ++l) {   // the device times are those of the whole batch
+        res[l].iters = es[l].iter;
+        res[l].err_last = err[l];
+        res[l].elapsed_ms = ms, res[l].loop_ms = lms, res[l].fft_ms = fft_ms;
+        res[l].n_residual_evals = (ctx->n_residual_evals - evals0) / nb;
+    }
+    return check_fault(ctx);
+}
+
+// displacement of lane `lane` of the last batched solve -> a field of the context (then fans_field_download, fans_strain_stress, ...)
+extern "C" int fans_batch_load_displacement(fans_ctx *ctx, int32_t lane, int32_t dst_field)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (lane < 0 || lane >= ctx->arena.lanes || !ctx->arena.field[0]) {
+        fans_set_error(ctx, FANS_ERR_STATE, "fans_batch_load_displacement: no such lane (run fans_solve_batch first)");
+        return FANS_ERR_STATE;
+    }
+    FANS_CHECK(ensure_fields(ctx, {dst_field}));
+    const size_t fN = (size_t)ctx->h * ctx->nloc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->field[dst_field], ctx->arena.field[0] + (size_t)lane * fN, sizeof(double) * fN, cudaMemcpyDeviceToDevice, ctx->st));
+    return FANS_OK;
+}
+
+// releases the lane buffers of batched solves (they are kept between calls; fans_destroy frees them as well)
+extern "C" int fans_batch_release(fans_ctx *ctx)
+{
+    if (!ctx) return FANS_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    batch_arena_free(ctx);
     return FANS_OK;
 }

@@ -62,6 +62,10 @@ struct StencilParams {
     // slab decomposition (world_size > 1): node planes -1 and n0 and element plane -1 come from the neighbour ranks
     const double *halo_lo, *halo_hi;   // [H][ny*nz], already the UPDATED direction (no s/beta combination)
     const uint16_t *ms_lo;             // [ny*nz] phases of element plane -1
+    // batched solves (k_stencil_linear<..., BATCH = true>): gridDim.z = lanes * nchunk; the fields of lane l start laneF doubles
+    // after those of lane l-1, its beta / red_out S_COUNT doubles, its partial sums lane_part doubles, its ticket one word
+    int nchunk;
+    size_t laneF, lane_part;
 };
 
 __device__ __forceinline__ int gwrap(int v, int n)
@@ -338,9 +342,22 @@ __device__ __forceinline__ void stencil_producer(const StencilParams &p, double 
 // P-1, P, P+1 (x-scatter form of the 27-point block stencil); plane P-1 is then complete.  Interface nodes (mixed-phase
 // neighbourhood) are queued and evaluated in the exact element form.  Hand-over through named barriers per ring slot, so
 // neither side ever waits for the other unless it is genuinely ahead.
-template <int H, int NQ, bool ISO>
-__global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p, const __grid_constant__ StencilCoef<H, NQ> coef)
+template <int H, int NQ, bool ISO, bool BATCH>
+__global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(const StencilParams p0, const __grid_constant__ StencilCoef<H, NQ> coef)
 {
+    // BATCH: this CTA belongs to lane blockIdx.z / nchunk; the single-problem instantiation is untouched by it (p aliases p0)
+    StencilParams pl;
+    int bz = blockIdx.z;
+    if (BATCH) {
+        const int ln = bz / p0.nchunk;
+        bz -= ln * p0.nchunk;
+        pl = p0;
+        const size_t fo = (size_t)ln * p0.laneF;
+        pl.d_old += fo, pl.d_new += fo, pl.out += fo;
+        if (pl.s) pl.s += fo, pl.beta += (size_t)ln * S_COUNT;
+        if (pl.red_out) pl.red_out += (size_t)ln * S_COUNT, pl.part += (size_t)ln * p0.lane_part, pl.ticket += ln;
+    }
+    const StencilParams &p = BATCH ? pl : p0;
     const double *__restrict__ Sc = coef.S;
     extern __shared__ __align__(16) double smem[];
     double *ring = smem;                                   // [4][H][GTILE]   combined direction planes
@@ -352,7 +369,7 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const int z0 = blockIdx.x * GZ, y0 = blockIdx.y * GY;
-    const int xs = blockIdx.z * p.xchunk, xe = min(xs + p.xchunk, p.n0);
+    const int xs = bz * p.xchunk, xe = min(xs + p.xchunk, p.n0);
     const size_t plane_sz = (size_t)p.ny * p.nz;
     double dot_final = 0.0;   // <d_new, K d_new> of this thread; the running sum lives inside the consumer branch only (a value that
                               // is live across the producer branch would have to fit the producers' 40-register budget and gets spilled)
@@ -487,7 +504,12 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
 #endif
         dot_final = dotacc;
     }
-    if (p.red_out) grid_reduce_sum1(dot_final, scratch, p.part, p.ticket, p.red_out);
+    if (p.red_out) {
+        if (BATCH)
+            grid_reduce_sum1_part(dot_final, scratch, p.part, p.ticket, p.red_out, gridDim.x * gridDim.y * p.nchunk,
+                                  blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * bz));
+        else grid_reduce_sum1(dot_final, scratch, p.part, p.ticket, p.red_out);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,13 +537,20 @@ static int launch_stencil(fans_ctx *ctx, const StencilParams &p, dim3 grid, size
 {
     StencilCoef<H, NQ> coef;
     for (size_t i = 0; i < sizeof(coef.S) / sizeof(double); ++i) coef.S[i] = i < S.size() ? S[i] : 0.0;
+#define ST_LAUNCH(ISO_, B_)                                                                                                          \
+    do {                                                                                                                             \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ, ISO_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_stencil_linear<H, NQ, ISO_, B_><<<grid, G_THREADS, smem, ctx->st>>>(p, coef);                                                 \
+    } while (0)
+    const bool batch = ctx->nb > 1;
     if (iso && H == 3) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ, (H == 3)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stencil_linear<H, NQ, (H == 3)><<<grid, G_THREADS, smem, ctx->st>>>(p, coef);
+        if (batch) ST_LAUNCH((H == 3), true);
+        else ST_LAUNCH((H == 3), false);
     } else {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_stencil_linear<H, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stencil_linear<H, NQ, false><<<grid, G_THREADS, smem, ctx->st>>>(p, coef);
+        if (batch) ST_LAUNCH(false, true);
+        else ST_LAUNCH(false, false);
     }
+#undef ST_LAUNCH
     return FANS_OK;
 }
 
@@ -574,14 +603,17 @@ int stencil_run(fans_ctx *ctx, const double *d_old, double *out, const double *s
         p.halo_lo = ctx->halo_lo, p.halo_hi = ctx->halo_hi, p.ms_lo = ctx->ms_lo;
     }
     const int gy = (ctx->ny + GY - 1) / GY, gz = (ctx->nz + GZ - 1) / GZ;
-    int xchunk = pick_xchunk(ctx->n0, (long)gy * gz, 2L * FANS_SMS, 2);   // 2 resident CTAs per SM, 2 run-in planes per march
+    int xchunk = pick_xchunk(ctx->n0, (long)gy * gz * ctx->nb, 2L * FANS_SMS, 2);   // 2 resident CTAs per SM, 2 run-in planes per march
     if (const char *env = getenv("FANS_STENCIL_CTAS")) {   // experiments: at least this many CTAs
         const long want = atol(env);
         xchunk = ctx->n0;
         while (xchunk > 2 && (long)gy * gz * ((ctx->n0 + xchunk - 1) / xchunk) < want) xchunk = (xchunk + 1) / 2;
     }
     p.xchunk = xchunk;
-    dim3 grid(gz, gy, (ctx->n0 + xchunk - 1) / xchunk);
+    p.nchunk = (ctx->n0 + xchunk - 1) / xchunk;
+    p.laneF = (size_t)ctx->h * ctx->nloc;
+    p.lane_part = (size_t)gy * gz * p.nchunk;
+    dim3 grid(gz, gy, p.nchunk * ctx->nb);
     const size_t smem = sizeof(double) * 4 * h * GTILE + sizeof(double2) * 2 * h * G_STG + sizeof(uint16_t) * 8 * GETILE + 16;
     prof_begin(ctx, PC_SWEEP_LINEAR);
     int rc = FANS_ERR_ARG;

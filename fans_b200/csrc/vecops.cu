@@ -3,6 +3,7 @@
 // 119-160), SolverFP::internalSolve (include/solverFP.h:46), Solver::compute_error (include/solver.h:414-431) and
 // Solver::extrapolateDisplacement (include/solver.h:302-311).  All fields are flat SoA arrays of h*nloc doubles.
 #include "internal.h"
+#include <algorithm>
 
 #define VEC_THREADS 256
 
@@ -22,7 +23,15 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(double2 *__restrict__
                                                             const double2 *__restrict__ s, size_t n2, double *S,
                                                             double *part, unsigned int *ticket)
 {
+    // batched solves: blockIdx.y = lane (fields n2 double2 apart, own scalar block / partial sums / ticket); a lane that has
+    // converged (S_FREEZE) is left exactly as it is
     __shared__ double scratch[4 * 32];
+    {
+        const size_t lo = (size_t)blockIdx.y * n2;
+        r += lo, kd += lo, u += lo, d += lo, s += lo;
+        S += (size_t)blockIdx.y * S_COUNT, part += (size_t)blockIdx.y * 4 * gridDim.x, ticket += blockIdx.y;
+    }
+    if (S[S_FREEZE] != 0.0) return;
     const double alpha = S[S_DELTA] / S[S_DKD];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};  // L1, L2^2, <r,s>, Linf
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
@@ -40,7 +49,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(double2 *__restrict__
         acc[2] += rv.x * sv.x + rv.y * sv.y;
         acc[3] = fmax(acc[3], fmax(fabs(rv.x), fabs(rv.y)));
     }
-    grid_reduce<4, 3>(acc, scratch, part, ticket, S + S_L1);  // -> S_L1, S_L2SQ, S_DELTAMID, S_LINF
+    grid_reduce_part<4, 3>(acc, scratch, part, ticket, S + S_L1, false, gridDim.x, blockIdx.x);  // -> S_L1, S_L2SQ, S_DELTAMID, S_LINF
 }
 
 // generic fused reductions: out[0]=sum|a|, out[1]=sum a^2, out[2]=sum a*b (b may be null), out[3]=max|a|
@@ -130,6 +139,7 @@ __global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict_
 //   delta0 = delta ; delta = <r,s> ; beta = fmax(0, (delta - deltamid)/delta0)
 __global__ void k_scalars_after_conv(double *S)
 {
+    S += (size_t)blockIdx.x * S_COUNT;   // one block per lane of a batched solve
     const double delta0 = S[S_DELTA];
     const double delta = S[S_RS];
     S[S_DELTA0] = delta0;
@@ -209,11 +219,15 @@ int vec_cg_update(fans_ctx *ctx, double *r, const double *kd, double *u, const d
 {
     prof_begin(ctx, PC_CG_UPDATE);
     const size_t n2 = ((size_t)ctx->h * ctx->nloc + 1) / 2;   // fields carry one zero pad value (api.cu: ensure_field)
-    k_cg_update<<<vec_grid(n2), VEC_THREADS, 0, ctx->st>>>((double2 *)r, (const double2 *)kd, (double2 *)u, (const double2 *)d,
-                                                          (const double2 *)s, n2, ctx->d_red, ctx->d_part, ctx->d_ticket);
+    // batched solve: lanes are exactly h*nloc doubles apart (even, checked by fans_solve_batch), every lane reads its own scalar block
+    const size_t n2l = ctx->nb > 1 ? (size_t)ctx->h * ctx->nloc / 2 : n2;
+    const unsigned gx = std::min(vec_grid(n2l), (unsigned)std::max(FANS_SMS, FANS_SMS * 16 / ctx->nb));
+    k_cg_update<<<dim3(gx, ctx->nb), VEC_THREADS, 0, ctx->st>>>((double2 *)r, (const double2 *)kd, (double2 *)u, (const double2 *)d,
+                                                               (const double2 *)s, n2l, ctx->d_red, ctx->d_part, ctx->d_ticket);
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    if (ctx->nb > 1) return FANS_OK;   // single GPU: the host reads S_L1.. of every lane directly
     // error norms: MAX over the slabs for every measure (solver.h:430);  deltamid = <r,s>: SUM (solverCG.h:57)
     FANS_CHECK(comm_allreduce(ctx, ctx->d_red + S_L1, ctx->d_red + S_ERRMAX, 4, true));
     if (ctx->P > 1) FANS_CHECK(comm_allreduce(ctx, ctx->d_red + S_DELTAMID, ctx->d_red + S_DELTAMID, 1, false));
@@ -306,7 +320,7 @@ int vec_soa_to_aos(fans_ctx *ctx, const double *soa, double *aos)
 int vec_scalars_after_conv(fans_ctx *ctx)
 {
     prof_begin(ctx, PC_OTHER);
-    k_scalars_after_conv<<<1, 1, 0, ctx->st>>>(ctx->d_red);
+    k_scalars_after_conv<<<ctx->nb, 1, 0, ctx->st>>>(ctx->d_red);
     prof_end(ctx);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());

@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <memory>
@@ -103,6 +104,7 @@ class Solver {
         error_type = "relative";  // permanent, like the reference (quirk 7)
         TOL = std::max(1e-6, TOL);
         if (matmanager->has_j2()) throw std::runtime_error("Homogenized tangent computation not implemented for J2Plasticity models.");
+        if (islinear && batch_tangent && tangent_batched()) return homogenized_tangent;
         for (int i = 0; i < n_str; ++i) {
             std::vector<double> pert(n_str, 0.0);
             if (islinear) {
@@ -122,6 +124,51 @@ class Solver {
             for (int c = 0; c < n_str; ++c) sym(r, c) = 0.5 * (homogenized_tangent(r, c) + homogenized_tangent(c, r));
         homogenized_tangent = sym;
         return homogenized_tangent;
+    }
+
+    // The n_str unit load cases of the linear branch above as lanes of ONE CG loop (fans_solve_batch) instead of n_str solves one
+    // after the other.  Leaves the solver in the state the reference's loop leaves it in: gradient = last unit strain, u = its
+    // solution, mixed BCs off.  false: the library cannot batch this problem (slabs, FP method, odd grids) — the loop above runs.
+    bool batch_tangent = true;   // FANS_TANGENT_BATCH=0 in the environment switches the batched path off (A/B runs)
+    std::vector<fans_solve_result> batch_results;
+    bool tangent_batched()
+    {
+        if (const char *env = getenv("FANS_TANGENT_BATCH"))
+            if (env[0] == '0') return false;
+        fans_solve_params p = solve_params();
+        if (p.method != FANS_METHOD_CG) return false;
+        disableMixedBC();
+        std::vector<double> macro((size_t)n_str * n_str, 0.0), sig((size_t)n_str * n_str, 0.0);
+        for (int i = 0; i < n_str; ++i) macro[(size_t)i * n_str + i] = 1.0;
+        batch_results.assign(n_str, fans_solve_result{});
+        p.verbose = 0;
+        const int rc = fans_solve_batch(ctx, n_str, macro.data(), &p, batch_results.data(), sig.data(), nullptr);
+        if (rc == FANS_ERR_STATE) return false;
+        if (rc == FANS_ERR_CUDA && std::string(fans_last_error(ctx)).find("out of device memory") != std::string::npos) return false;
+        check(rc);
+        for (int i = 0; i < n_str; ++i)
+            for (int r = 0; r < n_str; ++r) homogenized_tangent(r, i) = sig[(size_t)i * n_str + r];
+        Mat sym(n_str, n_str);
+        for (int r = 0; r < n_str; ++r)
+            for (int c = 0; c < n_str; ++c) sym(r, c) = 0.5 * (homogenized_tangent(r, c) + homogenized_tangent(c, r));
+        homogenized_tangent = sym;
+        // state after the reference's loop (solver.h:762-775)
+        std::vector<double> last(n_str, 0.0);
+        last[n_str - 1] = 1.0;
+        matmanager->set_gradient(last);
+        push_gradient();
+        check(fans_batch_load_displacement(ctx, n_str - 1, FANS_FIELD_U));
+        last_result = batch_results[n_str - 1];
+        iter = (size_t)last_result.iters;
+        // the lane buffers are 7 fields per load case: give them back unless they are small (a micro problem that is solved again and again)
+        if ((double)n_str * 7.0 * howmany * (double)local_n0 * n_y * n_z * sizeof(double) > 1e9) check(fans_batch_release(ctx));
+        if (verbose && world_rank == 0) {
+            int total = 0;
+            for (const auto &r : batch_results) total += r.iters;
+            printf("# Homogenized tangent: %d load cases in one batched CG loop, %d iterations in total, %2.6f sec\n", n_str, total,
+                   1e-3 * last_result.elapsed_ms);
+        }
+        return true;
     }
 
     // ---- MixedBCController (mixedBCs.h:150-226) ----
@@ -389,10 +436,8 @@ class Solver {
         }
         check(fans_set_mixed_bc(ctx, &d));
     }
-    void run_solve()
+    fans_solve_params solve_params() const
     {
-        push_gradient();
-        if (mixed_active) push_mixed();
         fans_solve_params p{};
         p.method = method_id();
         p.n_it = n_it;
@@ -407,6 +452,13 @@ class Solver {
         p.ls_max_iter = reader.ls_max_iter;
         p.ls_tol = reader.ls_tol;
         p.verbose = verbose && world_rank == 0;
+        return p;
+    }
+    void run_solve()
+    {
+        push_gradient();
+        if (mixed_active) push_mixed();
+        fans_solve_params p = solve_params();
         check(fans_solve(ctx, &p, &last_result, err_all.data()));
         iter = (size_t)last_result.iters;
         pull_gradient();

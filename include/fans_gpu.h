@@ -160,6 +160,19 @@ int fans_norm(fans_ctx *ctx, int32_t field, int32_t measure, double *out);  /* c
 int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result *res, double *err_hist /* n_it+1 or NULL */);
                                                                             /* Solver::solve solver.h:282-300 -> internalSolve */
 int fans_homogenized_stress(fans_ctx *ctx, double *out /* n_str */);        /* get_homogenized_stress solver.h:707-737 */
+/* Batched linear solves: the loop of Solver::get_homogenized_tangent (solver.h:762-775: set_gradient, solve, get_homogenized_stress
+ * per column) as ONE CG loop over n_b macroscopic strains ("lanes").  Every pass of the iteration is one launch over all lanes;
+ * Gamma_hat and the phase image are read from HBM once per pass.  Lane l starts from u = 0 and reproduces fans_solve with
+ * g0 = macro[l]; a converged lane is frozen.  The context's own displacement, gradient and history are left untouched.
+ *   macro      [n_b][n_str] macroscopic strains           res        [n_b]
+ *   stress_out [n_b][n_str] homogenized stresses or NULL  err_hist   [n_b][n_it+1] or NULL
+ * FANS_ERR_STATE (with the reason in fans_last_error) when the problem cannot be batched: nonlinear models, mixed BCs, slabs,
+ * non-power-of-two grids, method != CG — the caller then runs the load cases one after the other like the reference. */
+#define FANS_MAX_BATCH 16
+int fans_solve_batch(fans_ctx *ctx, int32_t n_b, const double *macro, const fans_solve_params *p, fans_solve_result *res,
+                     double *stress_out, double *err_hist);
+int fans_batch_load_displacement(fans_ctx *ctx, int32_t lane, int32_t dst_field); /* lane's u -> a field of the context */
+int fans_batch_release(fans_ctx *ctx);                                            /* frees the lane buffers (kept between calls) */
 int fans_commit_history(fans_ctx *ctx);                                     /* update_internal_variables MaterialManager.h:208-213 */
 int fans_extrapolate_displacement(fans_ctx *ctx);                           /* extrapolateDisplacement solver.h:302-311 */
 
