@@ -14,14 +14,15 @@ from util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def run_cli(tmp_path, cfg):
+def run_cli(tmp_path, cfg, env=None):
     exe = cpp_host.build()
     ms = tmp_path / "ms.u16"
     gu.sphere32().tofile(ms)
     inp = tmp_path / "in.json"
     inp.write_text(json.dumps(cfg))
     out = tmp_path / "results"
-    r = subprocess.run([exe, str(inp), str(out), str(ms), "32", "32", "32"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, str(inp), str(out), str(ms), "32", "32", "32"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stderr[-2000:]
     index = [json.loads(l) for l in open(out / "index.jsonl")]
     def load(name, lc, t):
@@ -60,6 +61,27 @@ def test_cli_scenario(tmp_path, name, steps):
         sa, ea = load("stress_average", 0, 0), load("strain_average", 0, 0)
         assert np.allclose(C @ ea, sa, rtol=1e-4, atol=1e-1) and np.allclose(C, C.T, rtol=1e-5, atol=1e-8)
         assert np.linalg.eigvalsh(C).min() > 0
+
+
+@pytest.mark.parametrize("name", ["LinearElastic", "LinearThermal"])
+def test_cli_tangent_batched_equals_the_reference_loop(tmp_path, name):
+    """get_homogenized_tangent (solver.h:739-778): the batched form (one CG loop over the n_str unit load cases) against the
+    one-solve-per-column loop of the reference, through the CLI; two time steps, so the solver state the tangent leaves behind
+    (gradient, displacement, error type — quirks the reference has) feeds the second step identically in both forms"""
+    cfg = gu.reference_input(name)
+    first = cfg["macroscale_loading"][0][0]
+    cfg["macroscale_loading"] = [[first, [2.0 * v for v in first]]]
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    load_b, out_b = run_cli(tmp_path / "a", cfg)
+    load_s, out_s = run_cli(tmp_path / "b", cfg, {"FANS_TANGENT_BATCH": "0"})
+    assert "one batched CG loop" in out_b and "one batched CG loop" not in out_s
+    for t in range(2):
+        Cb, Cs = load_b("homogenized_tangent", 0, t), load_s("homogenized_tangent", 0, t)
+        assert rel_err(Cb, Cs) < 1e-6      # both stop at the relative 1e-6 tolerance the tangent solves use
+        assert rel_err(load_b("stress_average", 0, t), load_s("stress_average", 0, t)) < 1e-6
+        # iteration counts of the step that FOLLOWS a tangent computation: same start state in both forms
+        assert abs(len(load_b("absolute_error", 0, t)) - len(load_s("absolute_error", 0, t))) <= 1
 
 
 def test_cli_hdf5_results(tmp_path):
