@@ -70,6 +70,114 @@ __global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zf(const double *
     }
 }
 
+// ---- bulk asynchronous copies (TMA, cp.async.bulk -> UBLKCP) with transaction barriers: a warp's next line travels global -> shared
+// on the copy engine while the warp transforms the current one; no registers, no address arithmetic, no load instructions in the
+// warps.  Built as the alternative to the plain kernel above and kept as an opt-in (FANS_Z_TMA=1): see z_use_tma() for the measurement ----
+__device__ __forceinline__ unsigned z_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(z_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(z_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(z_smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(z_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ZWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ZDONE;\n"
+        "bra ZWAIT;\n"
+        "ZDONE:\n"
+        "}\n" ::"r"(z_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__host__ __device__ constexpr int ztma_pitch(int NH) { return NH + NH / 8 + NH / 64; }   // LineIdx of row NH-1 is below this
+#define ZTMA_WARPS 8
+
+// Forward z pass, persistent warps (lines of nz <= 512: a line, or 32 / z_tpl lines, per warp).  Every warp owns two line buffers and
+// two transaction barriers: lane 0 starts the bulk copy of the warp's NEXT lines into the idle buffer, the warp waits for the current
+// ones, takes them into registers and then uses the same buffer as its exchange tile.  No CTA-wide barrier anywhere.
+template <int NH>
+__global__ void __launch_bounds__(ZTMA_WARPS * 32, 3) k_fft_zf_tma(const double *__restrict__ real, double2 *__restrict__ spec,
+                                                                const double2 *__restrict__ tw, const int *__restrict__ pos, SpecGeom g, int ny,
+                                                                size_t line0, size_t nlines)
+{
+    extern __shared__ __align__(16) double2 sm[];
+    constexpr int E = rp_elems(NH), TPL = z_tpl(NH), LPW = 32 / TPL, NST = rp_nstages(NH), PITCH = ztma_pitch(NH);
+    static_assert(TPL <= 32, "one line must fit a warp");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = lane / TPL, jt = lane % TPL;
+    double2 *wbuf = sm + (size_t)warp * (2 * LPW * PITCH);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + (size_t)ZTMA_WARPS * 2 * LPW * PITCH) + 2 * warp;
+    const size_t ntiles = (nlines - line0 + LPW - 1) / LPW;               // a tile = the LPW lines a warp carries at a time
+    const size_t nwarps = (size_t)gridDim.x * ZTMA_WARPS, gw = (size_t)blockIdx.x * ZTMA_WARPS + warp;
+    const double2 *in2 = reinterpret_cast<const double2 *>(real);
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    auto issue = [&](size_t tile, int buf) {   // lane 0: the lines of `tile` -> buffer `buf`
+        const size_t first = line0 + tile * LPW;
+        const int nval = (int)((nlines - first) < (size_t)LPW ? (nlines - first) : (size_t)LPW);
+        mbar_expect_tx(bars + buf, (unsigned)(nval * NH * sizeof(double2)));
+        for (int q = 0; q < nval; ++q)
+            bulk_g2s(wbuf + (size_t)(buf * LPW + q) * PITCH, in2 + (first + q) * NH, (unsigned)(NH * sizeof(double2)), bars + buf);
+    };
+    if (lane == 0 && gw < ntiles) issue(gw, 0);
+    const LineIdx idx;
+    const SyncWarp zsync;
+    int it = 0;
+    for (size_t tile = gw; tile < ntiles; tile += nwarps, ++it) {
+        const int buf = it & 1;
+        if (lane == 0 && tile + nwarps < ntiles) {   // the other buffer was left behind a __syncwarp by every lane
+            proxy_fence_async();
+            issue(tile + nwarps, buf ^ 1);
+        }
+        mbar_wait(bars + buf, (unsigned)((it >> 1) & 1));
+        const size_t line = line0 + tile * LPW + l;
+        const bool valid = line < nlines;
+        double2 *sml = wbuf + (size_t)(buf * LPW + l) * PITCH;
+        double2 a[1][E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) a[0][e] = valid ? sml[rp_row<NH, 0>(jt, e)] : make_double2(0.0, 0.0);
+        __syncwarp();   // everybody holds its rows: the line buffer becomes the exchange tile
+        rp_forward<NH, 1, LineIdx, 0, SyncWarp>(a, jt, sml, 0, idx, tw, 2, zsync);
+        if (NST > 1) zsync();
+        rp_put<NH, NST - 1>(a[0], jt, sml, idx);
+        zsync();
+        if (valid) {
+            double2 *out = spec + spec_line(g, ny, line);
+            for (int k = jt; k <= NH / 2; k += TPL) {
+                const double2 A = sml[idx(__ldg(&pos[k]))];
+                const double2 Bc = sml[idx(__ldg(&pos[(NH - k) & (NH - 1)]))];
+                const double2 B = make_double2(Bc.x, -Bc.y);
+                const double2 Ev = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y + B.y));
+                const double2 D = make_double2(0.5 * (A.x - B.x), 0.5 * (A.y - B.y));
+                const double2 wd = rc_mul(__ldg(&tw[k]), D);
+                out[NH - k] = make_double2(Ev.x - wd.y, -(Ev.y + wd.x));
+                out[k] = make_double2(Ev.x + wd.y, Ev.y - wd.x);
+            }
+        }
+        __syncwarp();   // the buffer is free for the copy after next
+    }
+}
+
 template <int NH>
 __global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zi(const double2 *__restrict__ spec, double *__restrict__ real,
                                                                   const double2 *__restrict__ tw, const int *__restrict__ pos,
@@ -130,9 +238,38 @@ __global__ void __launch_bounds__(z_tpl(NH) * z_lpb(NH)) k_fft_zi(const double2 
                                accumulate != 0, gridDim.x, blockIdx.x);
 }
 
+static bool z_use_tma()
+{
+    static const bool on = [] {
+        // opt-in: measured slower than the plain kernel on B200 (512^3: 1.40 vs 1.32 ms, 256^3: 0.177 vs 0.161 ms,
+        // profiles/r2tma_zfwd.txt) — the pass is bound by shared-memory traffic (ncu: L1/shared pipe 62 % busy, long-scoreboard stalls
+        // are a minor share), and landing the line in shared memory first adds two accesses per element to the seven of the transform
+        const char *e = getenv("FANS_Z_TMA");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 template <int NH>
 static int launch_zf(fans_ctx *ctx, const double *in, const SpecGeom &g, size_t line0, size_t nlines, cudaStream_t st)
 {
+    if constexpr (z_tpl(NH) <= 32) {
+        if (z_use_tma()) {
+            constexpr int LPW = 32 / z_tpl(NH);
+            const size_t smem = sizeof(double2) * ZTMA_WARPS * 2 * LPW * ztma_pitch(NH) + sizeof(uint64_t) * 2 * ZTMA_WARPS;
+            static int resident = 0;
+            if (!resident) {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_zf_tma<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fft_zf_tma<NH>, ZTMA_WARPS * 32, smem));
+                if (resident < 1) resident = 1;
+            }
+            const size_t ntiles = (nlines - line0 + LPW - 1) / LPW;
+            size_t grid = (ntiles + ZTMA_WARPS - 1) / ZTMA_WARPS;
+            if (grid > (size_t)FANS_SMS * resident) grid = (size_t)FANS_SMS * resident;
+            k_fft_zf_tma<NH><<<(unsigned)grid, ZTMA_WARPS * 32, smem, st>>>(in, ctx->spec, ctx->planz.tw, ctx->planz.pos, g, ctx->ny, line0, nlines);
+            return FANS_OK;
+        }
+    }
     constexpr int LPB = z_lpb(NH), NTHR = z_tpl(NH) * LPB;
     const size_t smem = sizeof(double2) * zline_pitch(NH) * LPB;
     if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_fft_zf<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

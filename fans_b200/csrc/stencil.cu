@@ -30,6 +30,9 @@
 #ifndef STENCIL_MINB
 #define STENCIL_MINB 2
 #endif
+#ifndef STENCIL_WROWS
+#define STENCIL_WROWS 1         // tile rows a consumer warp covers (1, 2, 4, 8): see the consumer branch of k_stencil_linear
+#endif
 #ifndef STENCIL_MIXED_TABLE
 #define STENCIL_MIXED_TABLE 0   // 1: warps cut by an interface take per-lane coefficients from the table in global memory (measured slower)
 #endif
@@ -131,7 +134,9 @@ __device__ __forceinline__ void stencil_row_dispatch(const double *__restrict__ 
 // include/solver.h:250-261, solverCG.h:98-103).  One (node, element) item per lane: the eight lanes of a node read their element's
 // three rows of K from the phase table in global memory (no phase branches, no divergence) and are summed with shuffles, so a queue
 // of q nodes costs ceil(8 q / 256) short passes of all consumer warps instead of one long serial chain in a few lanes.
-// Not inlined on purpose: its registers must not compete with the accumulators of the homogeneous path.
+// Not inlined on purpose: its registers must not compete with the accumulators of the homogeneous path.  (Measured, round 2: issuing
+// its loads in batches — all 8 x H neighbour values, then K row by row — instead of the load -> subtract -> multiply chains below needs
+// a stack frame for the callee-saved registers and slows the WHOLE kernel, homogeneous image included: 3.04 -> 3.35 ms.)
 struct IfaceArgs {
     const double *ring, *Ktab;
     const uint16_t *mring, *qlist;
@@ -382,9 +387,14 @@ __global__ void __launch_bounds__(G_THREADS, STENCIL_MINB) k_stencil_linear(cons
         // =================================== consumer warps ===================================
         if (STENCIL_SETMAXNREG && STENCIL_MINB == 2) reg_alloc<STENCIL_CONS_REGS>();
         double dotacc = 0.0;
-        const int ry = wy + 1, rzA = 2 * lane + 2;  // tile coordinates of node A (column = z - z0 + 2); node B = rzA + 1
-        const int rzM = 2 * lane + 1;               // column of node A in the phase-image tile (z - z0 + 1)
-        const int yA = y0 + wy, zA = z0 + 2 * lane;
+        // footprint of a warp in the (y, z) tile: STENCIL_WROWS rows x 64 / STENCIL_WROWS nodes.  A warp whose homogeneous lanes sit in
+        // different phases runs the constant-operand stencil of each of them, and the whole CTA waits for it at the hand-over: the
+        // squarer the footprint, the fewer warps an interface cuts (1 x 64: one per crossing of a z line)
+        const int wrow = (wy % (GY / STENCIL_WROWS)) * STENCIL_WROWS + lane / (32 / STENCIL_WROWS);   // tile row 0..GY-1
+        const int wzp = (wy / (GY / STENCIL_WROWS)) * (32 / STENCIL_WROWS) + lane % (32 / STENCIL_WROWS);   // node pair 0..31 along z
+        const int ry = wrow + 1, rzA = 2 * wzp + 2;  // tile coordinates of node A (column = z - z0 + 2); node B = rzA + 1
+        const int rzM = 2 * wzp + 1;                 // column of node A in the phase-image tile (z - z0 + 1)
+        const int yA = y0 + wrow, zA = z0 + 2 * wzp;
         const bool valid = (yA < p.ny) && (zA < p.nz);  // nz is even, so A valid <=> B valid
         // accumulators of the output planes P-1, P, P+1 (slots 0,1,2) of this thread's node pair, with their homogeneity flags
         double acc[3][2][H];
