@@ -242,8 +242,9 @@ static bool z_use_tma()
 {
     static const bool on = [] {
         // opt-in: measured slower than the plain kernel on B200 (512^3: 1.40 vs 1.32 ms, 256^3: 0.177 vs 0.161 ms,
-        // profiles/r2tma_zfwd.txt) — the pass is bound by shared-memory traffic (ncu: L1/shared pipe 62 % busy, long-scoreboard stalls
-        // are a minor share), and landing the line in shared memory first adds two accesses per element to the seven of the transform
+        // profiles/r2tma_zfwd_bulk_copy.txt).  ncu of the plain kernel: 175 M shared-memory wavefronts = 49 % of the wavefront
+        // rate, stalls mio_throttle 3.5 / short scoreboard 3.6 next to long scoreboard 4.3 — the shared-memory queue is as much the limit
+        // as the global loads, and landing the line in shared memory first adds two accesses per element to the seven of the transform
         const char *e = getenv("FANS_Z_TMA");
         return e && e[0] == '1';
     }();
