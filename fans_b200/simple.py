@@ -2,6 +2,8 @@
 Host-side restatement of what the reference's LinearElasticIsotropic / LinearThermalIsotropic constructors and
 MaterialManager::compute_reference_stiffness do (include/material_models/LinearElastic.h:7-75,
 LinearThermal.h:7-46, MaterialManager.h:177-205) — parameter bookkeeping only, all numerics run in libfans_gpu."""
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -225,12 +227,32 @@ def voronoi_microstructure(dims, n_seeds=None, seed=2024, x0=0, n0=None):
     rng = np.random.default_rng(seed)
     pts = rng.uniform(0.0, 1.0, size=(n_seeds, 3)) * np.array([nx, ny, nz], dtype=np.float64)
     tree = cKDTree(pts, boxsize=[nx, ny, nz])   # periodic nearest neighbour
-    yy, zz = np.meshgrid(np.arange(ny) + 0.5, np.arange(nz) + 0.5, indexing="ij")
-    q = np.empty((ny * nz, 3))
+    # Voronoi cells are convex: when two voxels of a z line lie in the same cell, so does everything between them.  Query every
+    # STRIDE-th voxel and only fill in the segments whose ends disagree (a few per cent at ~128-voxel grains): the same image as the
+    # voxel-by-voxel query at about a sixth of its cost (a 1024^3 image is 10^9 nearest-neighbour queries otherwise).
+    stride = 8 if nz % 8 == 0 and nz >= 64 else 1
+    workers = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
+    zc = np.arange(0, nz, stride)
+    yy, zz = np.meshgrid(np.arange(ny) + 0.5, zc + 0.5, indexing="ij")
+    q = np.empty((ny * len(zc), 3))
     q[:, 1], q[:, 2] = yy.ravel(), zz.ravel()
     ms = np.empty((n0, ny, nz), dtype=np.uint16)
     for i in range(n0):
         q[:, 0] = x0 + i + 0.5
-        _, lab = tree.query(q, workers=-1)
-        ms[i] = (lab % 2).reshape(ny, nz)
+        _, lab = tree.query(q, workers=workers)
+        lab = lab.reshape(ny, len(zc))
+        if stride == 1:
+            ms[i] = lab % 2
+            continue
+        full = np.repeat(lab, stride, axis=1)                       # segment [z, z + stride) takes the label of its left end ...
+        differ = lab != np.roll(lab, -1, axis=1)                    # ... unless the next sample (periodic) sits in another cell
+        iy, iz = np.nonzero(differ)
+        if len(iy):
+            off = np.arange(1, stride)
+            qy = np.repeat(iy, stride - 1)
+            qz = np.repeat(zc[iz], stride - 1) + np.tile(off, len(iy))
+            qq = np.stack([np.full(len(qy), x0 + i + 0.5), qy + 0.5, qz + 0.5], axis=1)
+            _, l2 = tree.query(qq, workers=workers)
+            full[qy, qz] = l2
+        ms[i] = full % 2
     return ms

@@ -97,6 +97,23 @@ def main():
         ctx.extrapolate_displacement()
     np.savez(os.path.join(outdir, "j2_rank%d.npz" % r), **out)
     ctx.close()
+
+    # ---- 5. compressible Neo-Hooke with mixed boundary conditions (BASELINE config 5's path): finite-strain sweep, sigma-bar sweep +
+    #         all-reduce inside every mixed-BC update, line search
+    ms = util.two_phase_ms(0, 12, (16, 16, 16))
+    out = {}
+
+    def make_ctx(par):
+        c, x0, n0 = slab_ctx(par, comm)
+        out["x0"] = x0
+        return c
+
+    def on_step(c, lc, t, res):
+        out["iters%d" % t], out["sig%d" % t], out["u%d" % t], out["g0_%d" % t] = res["iters"], c.homogenized_stress(), c.download("u"), res["g0"]
+
+    _, ctx = util.run_gpu_load_cases(ms, util.NH_MIXED_CFG, on_step=on_step, make_ctx=make_ctx)
+    np.savez(os.path.join(outdir, "nhmixed_rank%d.npz" % r), **out)
+    ctx.close()
     comm.close()
 
 

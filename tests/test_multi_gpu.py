@@ -126,3 +126,20 @@ def test_j2_plasticity(run):
         ep = gather(out, "j2", P, "ep%d" % t)[0]
         assert rel_err(ep, sol.models[0].ep_t.mean(1).reshape(ep.shape)) < 1e-8  # J2Plasticity.h:245-322: GP mean of the committed values
         sol.extrapolate_displacement()
+
+
+def test_neohooke_mixed_bc(run):
+    """BASELINE config 5's path on slabs: finite-strain Neo-Hooke, stress-controlled components through the mixed-BC update (its
+    homogenized-stress sweep is all-reduced over the ranks), CG with line search; two load steps with displacement extrapolation"""
+    P, out = run
+    ms = util.two_phase_ms(0, 12, (16, 16, 16))
+    if ms.shape[0] // 4 < P:
+        pytest.skip("n_x/4 < world_size (reader.cpp:306)")
+    ro, _ = fo.run_load_cases(ms, util.NH_MIXED_CFG, on_step=lambda sol, lc, t, res: res.update(u=sol.u.copy(), sig=sol.get_homogenized_stress()))
+    for t, b in enumerate(ro[0]):
+        u, parts = gather(out, "nhmixed", P, "u%d" % t)
+        for p in parts:
+            assert abs(int(p["iters%d" % t]) - b["iters"]) <= 1
+            assert rel_err(p["sig%d" % t], b["sig"]) < 1e-9
+            assert rel_err(p["g0_%d" % t], b["g0"]) < 1e-9
+        assert rel_err(u, b["u"]) < 1e-8

@@ -82,7 +82,16 @@ ELASTIC = [{"phases": [0, 1], "matmodel": "LinearElasticIsotropic",
 EP = {"measure": "Linfinity", "type": "absolute", "tolerance": 1e-10}
 
 
-def run_gpu_load_cases(ms, cfg, max_steps=None, on_step=None):
+NH_MIXED_CFG = {   # config 5's path in small: compressible Neo-Hooke, F33 ramp with P11 = P22 = 0 (test_MixedBCs_LargeStrain.json, load case 1)
+    "microstructure": {"L": [1.0, 1.5, 2.0]}, "problem_type": "mechanical", "strain_type": "large", "FE_type": "HEX8", "method": "cg",
+    "materials": [{"phases": [0, 1], "matmodel": "CompressibleNeoHookean",
+                   "material_properties": {"bulk_modulus": [62.5, 222.222], "shear_modulus": [28.8462, 166.6667]}}],
+    "error_parameters": {"measure": "Linfinity", "type": "absolute", "tolerance": 1e-9}, "n_it": 400,
+    "macroscale_loading": [{"strain_indices": [1, 2, 3, 5, 6, 7, 8], "stress_indices": [0, 4],
+                            "strain": [[0, 0, 0, 0, 0, 0, 1.02], [0, 0, 0, 0, 0, 0, 1.04]], "stress": [[0.0, 0.0], [0.0, 0.0]]}]}
+
+
+def run_gpu_load_cases(ms, cfg, max_steps=None, on_step=None, make_ctx=None):
     """Python mirror of runSolver (src/main.cpp:9-46) + MixedBCController::activate (mixedBCs.h:180-226) driving the
     CUDA library through its C ABI.  Returns (per load case -> per step dict) like fans_oracle.run_load_cases."""
     problem = cfg["problem_type"]
@@ -95,7 +104,7 @@ def run_gpu_load_cases(ms, cfg, max_steps=None, on_step=None):
         # the oracle object is used here ONLY as a parameter parser (phase descriptors, kapparef): n_it=0, never solved
         par = fo.OracleSolver(ms, cfg["microstructure"]["L"], problem, cfg["materials"], cfg.get("FE_type", "HEX8"), cfg["method"],
                               strain_type, ep, 0, None, cfg.get("reference_material"))
-        ctx = ctx_from_oracle(par)
+        ctx = ctx_from_oracle(par) if make_ctx is None else make_ctx(par)   # make_ctx: e.g. one slab of a multi-GPU run
         mbc = None
         if isinstance(entry, dict):
             mbc = fo.MixedBC(entry["strain_indices"], entry["stress_indices"], entry.get("strain", []), entry.get("stress", []), n_str)
