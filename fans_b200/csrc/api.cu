@@ -405,6 +405,7 @@ extern "C" void fans_destroy(fans_ctx *ctx)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     batch_arena_free(ctx);
+    iter_graph_free(ctx);
     if (ctx->h_red) cudaFreeHost(ctx->h_red);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_fault) cudaFreeHost(ctx->h_fault);

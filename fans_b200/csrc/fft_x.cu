@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(H * (N / rp_elems(N)) * T, xg_min_blocks(H * (
 // PF: the strided rows of the NEXT component (and, during the inverse transforms, of the next tile's first component) travel
 // global -> shared with cp.async straight into that component's tile, which is idle until its own forward transform starts — the
 // load latency that one CTA per SM cannot hide with other warps disappears behind the butterflies, at no register cost.
+// (Parking the transformed components in registers instead — r[3][E], no park / read / write-back / re-read of the slots, 10 instead
+// of 14 shared-memory accesses per element — does not fit the 128 registers a 512-thread CTA has: ptxas spills 672 + 832 bytes per
+// thread and tile, as much local-memory traffic through the same L1 as the shared-memory traffic it saves.)
 template <int N, int T, bool PF>
 __global__ void __launch_bounds__((N / rp_elems(N)) * T, (3 * N * T * 16 <= 112 * 1024) ? 2 : 1)
     k_fft_xg_seq(double2 *__restrict__ spec, const double *__restrict__ gamma, const double2 *__restrict__ tw, SpecGeom g, int nTiles,

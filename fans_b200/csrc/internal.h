@@ -73,3 +73,4 @@ int comm_barrier_on(fans_ctx *ctx, cudaStream_t st);
 int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const double *dotw, double *red_out);
 int read_scalars(fans_ctx *ctx);  // d_red -> h_red, synchronises the stream
 void batch_arena_free(fans_ctx *ctx);  // lane buffers of fans_solve_batch
+void iter_graph_free(fans_ctx *ctx);   // CUDA graphs of the linear CG iteration

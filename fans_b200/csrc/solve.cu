@@ -165,16 +165,19 @@ int conv_run(fans_ctx *ctx, const double *in, double *out, double scale, const d
         cudaEventRecord(e, ctx->st);
         return e;
     };
-    if (ctx->conv_pending.size() > 1024) {  // many convolutions outside a solve: do not let the event pairs pile up
+    if (!ctx->capturing && ctx->conv_pending.size() > 1024) {  // many convolutions outside a solve: do not let the event pairs pile up
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
         conv_time_resolve(ctx);
     }
-    const cudaEvent_t ev_a = conv_event();
+    const cudaEvent_t ev_a = ctx->capturing ? nullptr : conv_event();
     struct ConvTimer {
         fans_ctx *c;
         cudaEvent_t a;
         decltype(conv_event) &mk;
-        ~ConvTimer() { c->conv_pending.emplace_back(a, mk()); }
+        ~ConvTimer()
+        {
+            if (a) c->conv_pending.emplace_back(a, mk());
+        }
     } conv_timer{ctx, ev_a, conv_event};
     if (ctx->any_fft) return conv_run_any(ctx, in, out, scale, dotw, red_out);
     if (ctx->pipe && ctx->chunks > 0 && !ctx->prof) return conv_run_chunked(ctx, in, out, scale, dotw, red_out);
@@ -280,6 +283,93 @@ extern "C" int fans_update_mixed_bc(fans_ctx *ctx)
     return FANS_OK;
 }
 
+// ---- one linear CG iteration as a CUDA graph (see fans_ctx::IterGraph) ----
+void iter_graph_free(fans_ctx *ctx)
+{
+    for (cudaGraphExec_t &e : ctx->igraph.exec)
+        if (e) cudaGraphExecDestroy(e), e = nullptr;
+    ctx->igraph.valid = false;
+}
+
+static bool iter_graph_wanted(const fans_ctx *ctx)
+{
+    if (const char *e = getenv("FANS_GRAPH")) return e[0] == '1';
+    return ctx->nloc <= (size_t)128 * 128 * 128;   // above this an iteration is bound by HBM, not by launches
+}
+
+static void iter_graph_key(const fans_ctx *ctx, const double *r, const double *s, const double *u, const double *rnew, const void *(&key)[8])
+{
+    key[0] = r, key[1] = s, key[2] = u, key[3] = rnew, key[4] = ctx->spec, key[5] = ctx->gamma, key[6] = ctx->phidx, key[7] = ctx->d_red;
+}
+
+// graphs exist for exactly these fields / tables and the current direction is one of the two buffers they alternate between
+static bool iter_graph_ready(const fans_ctx *ctx, const double *r, const double *s, const double *u, const double *rnew)
+{
+    const auto &G = ctx->igraph;
+    if (!G.valid || G.cstamp != ctx->const_stamp || G.sstamp != ctx->stencil_stamp) return false;
+    const void *key[8];
+    iter_graph_key(ctx, r, s, u, rnew, key);
+    for (int i = 0; i < 8; ++i)
+        if (key[i] != G.key[i]) return false;
+    const double *D = ctx->field[FANS_FIELD_D], *A = ctx->d_alt;
+    return (D == G.dA && A == G.dB) || (D == G.dB && A == G.dA);
+}
+
+// the body of the linear iteration (also what the plain loop runs); under capture the trailing read-back has no synchronisation
+static int linear_iteration(fans_ctx *ctx, double *r, double *s, double *u, double *rnew, const double *d_old, double *d_new, bool use_stencil)
+{
+    FANS_CHECK(conv_run(ctx, r, s, -1.0, r, ctx->d_red + S_RS));         // s = -Gamma r ; S_RS = <r,s>
+    FANS_CHECK(vec_scalars_after_conv(ctx));                             // delta0, delta, beta
+    if (use_stencil) FANS_CHECK(stencil_run(ctx, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD));
+    else FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD, nullptr, nullptr));
+    FANS_CHECK(vec_cg_update(ctx, r, rnew, u, d_new, s));                // r,u update + norms + deltamid
+    if (ctx->capturing) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fault, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+        return FANS_OK;
+    }
+    return read_scalars(ctx);
+}
+
+// Captures the iteration for both orientations of the direction ping-pong.  Called after one plain iteration of the same solve, so
+// every lazy initialisation of the launchers (coefficient tables, function attributes) lies behind.  A failed capture only
+// switches the graphs off for this context: the plain launches remain.
+static int iter_graph_build(fans_ctx *ctx, double *r, double *s, double *u, double *rnew)
+{
+    auto &G = ctx->igraph;
+    iter_graph_free(ctx);
+    G.dA = ctx->field[FANS_FIELD_D], G.dB = ctx->d_alt;
+    for (int par = 0; par < 2; ++par) {
+        const double *d_old = par ? G.dB : G.dA;
+        double *d_new = par ? G.dA : G.dB;
+        const int64_t l0 = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            G.failed = true;
+            return FANS_OK;
+        }
+        ctx->capturing = true;
+        const int rc = linear_iteration(ctx, r, s, u, rnew, d_old, d_new, true);
+        ctx->capturing = false;
+        const cudaError_t ce = cudaStreamEndCapture(ctx->st, &graph);
+        G.launches = (int)(ctx->launches - l0);
+        ctx->launches = l0;   // nothing ran
+        if (rc != FANS_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec[par], graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            iter_graph_free(ctx);
+            G.failed = true;
+            return FANS_OK;
+        }
+        cudaGraphDestroy(graph);
+    }
+    iter_graph_key(ctx, r, s, u, rnew, G.key);
+    G.cstamp = ctx->const_stamp, G.sstamp = ctx->stencil_stamp;
+    G.valid = true;
+    return FANS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // SolverCG::internalSolve, linear fast path (solverCG.h:96-107): everything between two error checks stays on
 // the device; alpha/beta are formed from device scalars. One host poll per iteration (the error).
@@ -306,21 +396,33 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
     if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
     FANS_CHECK(write_scalar(ctx, S_DELTA, 1.0));
     FANS_CHECK(write_scalar(ctx, S_DELTAMID, 0.0));  // <r, s> with s = 0
-    double delta = 1.0;
+    // small grids: iterations after the first replay a CUDA graph (single GPU, stencil form, no per-kernel profiling / printing)
+    const bool graph_ok = linear && use_stencil && ctx->P == 1 && ctx->nb == 1 && !ctx->prof && !p->verbose && !ctx->any_fft && iter_graph_wanted(ctx);
+    bool graph_tried = false;
+    int graph_iters = 0;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
     while (es.iter < p->n_it && err_rel > p->tol) {
         if (linear) {
             // deltamid already sits in S_DELTAMID (left by k_cg_update, 0 at iter 0)
-            FANS_CHECK(conv_run(ctx, r, s, -1.0, r, ctx->d_red + S_RS));         // s = -Gamma r ; S_RS = <r,s>
-            FANS_CHECK(vec_scalars_after_conv(ctx));                             // delta0, delta, beta
             double *d_old = ctx->field[FANS_FIELD_D], *d_new = ctx->d_alt;
             ctx->n_residual_evals++;
-            if (use_stencil) FANS_CHECK(stencil_run(ctx, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD));
-            else FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD, nullptr, nullptr));
+            if (graph_ok && iter_graph_ready(ctx, r, s, u, rnew)) {   // the whole iteration, read-back included, as one graph launch
+                const auto &G = ctx->igraph;
+                CUDA_TRY(ctx, cudaGraphLaunch(G.exec[d_old == G.dA ? 0 : 1], ctx->st));
+                ctx->launches += G.launches;
+                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+                graph_iters++;
+            } else {
+                FANS_CHECK(linear_iteration(ctx, r, s, u, rnew, d_old, d_new, use_stencil));
+                if (graph_ok && !ctx->igraph.failed && !graph_tried) {
+                    graph_tried = true;
+                    ctx->field[FANS_FIELD_D] = d_new, ctx->d_alt = d_old;   // the graphs alternate between the buffers as they are NOW
+                    FANS_CHECK(iter_graph_build(ctx, r, s, u, rnew));
+                    ctx->field[FANS_FIELD_D] = d_old, ctx->d_alt = d_new;
+                }
+            }
             ctx->field[FANS_FIELD_D] = d_new;
             ctx->d_alt = d_old;
-            FANS_CHECK(vec_cg_update(ctx, r, rnew, u, d_new, s));                // r,u update + norms + deltamid
-            FANS_CHECK(read_scalars(ctx));
             es.iter++;
             err_rel = error_from_scalars(ctx, es, S_ERRMAX);
         } else {
@@ -382,6 +484,7 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop1, ctx->st));
     res->err_last = err_rel;
+    ctx->igraph.replays = graph_iters;   // fans_solve: the convolutions inside graph replays carry no event pair
     return FANS_OK;
 }
 
@@ -428,6 +531,7 @@ extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_
         return FANS_ERR_ARG;
     }
     memset(res, 0, sizeof(*res));
+    ctx->igraph.replays = 0;
     if (err_hist)
         for (int i = 0; i <= p->n_it; ++i) err_hist[i] = 0.0;
     ErrState es{p->measure, p->err_type, 0.0, err_hist, 0};
@@ -453,6 +557,11 @@ extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_
     res->loop_ms = ms;
     prof_resolve(ctx);
     res->fft_ms = conv_time_resolve(ctx);
+    if (p->method == FANS_METHOD_CG && ctx->igraph.replays > 0) {   // replayed iterations: the convolution time of the plain ones stands in
+        const int plain = es.iter - ctx->igraph.replays;
+        if (plain > 0) ctx->igraph.fft_per_iter = res->fft_ms / plain;
+        res->fft_ms = ctx->igraph.fft_per_iter * es.iter;
+    }
     res->iters = es.iter;
     res->n_residual_evals = ctx->n_residual_evals - evals0;
     return FANS_OK;

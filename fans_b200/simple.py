@@ -41,13 +41,11 @@ def elastic_tangent(lam, mu):
     return k
 
 
-def linear_elastic_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1, gdims=None, comm=None):
-    """LinearElasticIsotropic on phases 0..len(bulk)-1; reference stiffness = (max+min)/2 of lambda and mu.
-    ms is this rank's slab; gdims the global grid (defaults to ms.shape)."""
+def elastic_phase_descs(bulk, shear):
+    """phase descriptors of LinearElasticIsotropic phases 0..len(bulk)-1 (LinearElastic.h:43-53: lambda = K - 2 mu / 3)"""
     bulk = np.asarray(bulk, dtype=np.float64)
     mu = np.asarray(shear, dtype=np.float64)
     lam = bulk - (2.0 / 3.0) * mu
-    ctx = L.Context(gdims if gdims is not None else ms.shape, Lbox, 3, 6, fe_type, device, comm)
     descs = []
     for i in range(len(bulk)):
         d = L.PhaseDesc()
@@ -55,7 +53,17 @@ def linear_elastic_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1, gdi
         for k, v in enumerate(elastic_tangent(lam[i], mu[i]).reshape(-1)):
             d.params[k] = v
         descs.append(d)
-    ctx.set_materials(descs)
+    return descs
+
+
+def linear_elastic_context(ms, Lbox, bulk, shear, fe_type="HEX8", device=-1, gdims=None, comm=None):
+    """LinearElasticIsotropic on phases 0..len(bulk)-1; reference stiffness = (max+min)/2 of lambda and mu.
+    ms is this rank's slab; gdims the global grid (defaults to ms.shape)."""
+    bulk = np.asarray(bulk, dtype=np.float64)
+    mu = np.asarray(shear, dtype=np.float64)
+    lam = bulk - (2.0 / 3.0) * mu
+    ctx = L.Context(gdims if gdims is not None else ms.shape, Lbox, 3, 6, fe_type, device, comm)
+    ctx.set_materials(elastic_phase_descs(bulk, mu))
     ctx.set_microstructure(ms)
     ctx.set_reference_stiffness(elastic_tangent((lam.max() + lam.min()) / 2, (mu.max() + mu.min()) / 2))
     return ctx
