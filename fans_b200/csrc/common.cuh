@@ -53,6 +53,22 @@ struct PhaseDev {  // device copy of one fans_phase_desc (params trimmed)
     double params[12];
 };
 
+// One linear CG iteration as a CUDA graph (solve.cu): on small grids (the micro problems of a two-scale simulation) the seven
+// kernels of an iteration take a few microseconds each and the iteration is bound by launch latency; replayed as a graph the
+// whole iteration — scalars' read-back included — is one launch.  Two graphs, one per orientation of the d / d_alt ping-pong;
+// rebuilt when any captured pointer or coefficient table changes.
+struct IterGraph {
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    double *dA = nullptr, *dB = nullptr;      // exec[0]: d_old = dA, d_new = dB; exec[1]: the other way round
+    const void *key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t cstamp = 0, sstamp = 0;
+    int nb = 1;                               // lanes the graphs were captured for (batched solves)
+    int launches = 0;                         // kernels per replay
+    int replays = 0;                          // iterations of the last solve that were graph replays
+    double fft_per_iter = 0.0;                // device time inside the convolution per iteration, measured on plain iterations
+    bool valid = false, failed = false;
+};
+
 struct fans_ctx {
     fans_config cfg;
     int nx, ny, nz, n0, x0, n1, y1, h, nstr, ngp, fe, P, rank;
@@ -164,22 +180,10 @@ struct fans_ctx {
         double2 *spec = nullptr;
         double *red = nullptr, *h_red = nullptr, *part = nullptr, *h_flag = nullptr;
         unsigned int *ticket = nullptr;
+        IterGraph graph;                          // one sweep over all lanes as a CUDA graph
     } arena;
 
-    // One linear CG iteration as a CUDA graph (solve.cu): on small grids (the micro problems of a two-scale simulation) the seven
-    // kernels of an iteration take a few microseconds each and the iteration is bound by launch latency; replayed as a graph the
-    // whole iteration — scalars' read-back included — is one launch.  Two graphs, one per orientation of the d / d_alt ping-pong;
-    // rebuilt when any captured pointer or coefficient table changes.
-    struct IterGraph {
-        cudaGraphExec_t exec[2] = {nullptr, nullptr};
-        double *dA = nullptr, *dB = nullptr;      // exec[0]: d_old = dA, d_new = dB; exec[1]: the other way round
-        const void *key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-        uint64_t cstamp = 0, sstamp = 0;
-        int launches = 0;                         // kernels per replay
-        int replays = 0;                          // iterations of the last solve that were graph replays
-        double fft_per_iter = 0.0;                // device time inside the convolution per iteration, measured on plain iterations
-        bool valid = false, failed = false;
-    } igraph;
+    IterGraph igraph;                             // the linear CG iteration as a CUDA graph (small grids)
     bool capturing = false;                       // launchers run under stream capture: no synchronisation, no timing events
 
     std::string err;

@@ -283,18 +283,23 @@ extern "C" int fans_update_mixed_bc(fans_ctx *ctx)
     return FANS_OK;
 }
 
-// ---- one linear CG iteration as a CUDA graph (see fans_ctx::IterGraph) ----
+// ---- one linear CG iteration as a CUDA graph (see IterGraph, common.cuh) ----
+static void iter_graph_free(IterGraph &G)
+{
+    for (cudaGraphExec_t &e : G.exec)
+        if (e) cudaGraphExecDestroy(e), e = nullptr;
+    G.valid = false;
+}
 void iter_graph_free(fans_ctx *ctx)
 {
-    for (cudaGraphExec_t &e : ctx->igraph.exec)
-        if (e) cudaGraphExecDestroy(e), e = nullptr;
-    ctx->igraph.valid = false;
+    iter_graph_free(ctx->igraph);
+    iter_graph_free(ctx->arena.graph);
 }
 
-static bool iter_graph_wanted(const fans_ctx *ctx)
+static bool iter_graph_wanted(const fans_ctx *ctx, int lanes)
 {
     if (const char *e = getenv("FANS_GRAPH")) return e[0] == '1';
-    return ctx->nloc <= (size_t)128 * 128 * 128;   // above this an iteration is bound by HBM, not by launches
+    return ctx->nloc * (size_t)lanes <= (size_t)128 * 128 * 128;   // above this an iteration is bound by HBM, not by launches
 }
 
 static void iter_graph_key(const fans_ctx *ctx, const double *r, const double *s, const double *u, const double *rnew, const void *(&key)[8])
@@ -302,20 +307,19 @@ static void iter_graph_key(const fans_ctx *ctx, const double *r, const double *s
     key[0] = r, key[1] = s, key[2] = u, key[3] = rnew, key[4] = ctx->spec, key[5] = ctx->gamma, key[6] = ctx->phidx, key[7] = ctx->d_red;
 }
 
-// graphs exist for exactly these fields / tables and the current direction is one of the two buffers they alternate between
-static bool iter_graph_ready(const fans_ctx *ctx, const double *r, const double *s, const double *u, const double *rnew)
+// graphs exist for exactly these fields / tables / lanes and the current direction D is one of the two buffers they alternate between
+static bool iter_graph_ready(const fans_ctx *ctx, const IterGraph &G, const double *r, const double *s, const double *u, const double *rnew,
+                             const double *D, const double *Dalt)
 {
-    const auto &G = ctx->igraph;
-    if (!G.valid || G.cstamp != ctx->const_stamp || G.sstamp != ctx->stencil_stamp) return false;
+    if (!G.valid || G.cstamp != ctx->const_stamp || G.sstamp != ctx->stencil_stamp || G.nb != ctx->nb) return false;
     const void *key[8];
     iter_graph_key(ctx, r, s, u, rnew, key);
     for (int i = 0; i < 8; ++i)
         if (key[i] != G.key[i]) return false;
-    const double *D = ctx->field[FANS_FIELD_D], *A = ctx->d_alt;
-    return (D == G.dA && A == G.dB) || (D == G.dB && A == G.dA);
+    return (D == G.dA && Dalt == G.dB) || (D == G.dB && Dalt == G.dA);
 }
 
-// the body of the linear iteration (also what the plain loop runs); under capture the trailing read-back has no synchronisation
+// the body of the linear iteration (all lanes of a batched solve at once); under capture the trailing read-back has no synchronisation
 static int linear_iteration(fans_ctx *ctx, double *r, double *s, double *u, double *rnew, const double *d_old, double *d_new, bool use_stencil)
 {
     FANS_CHECK(conv_run(ctx, r, s, -1.0, r, ctx->d_red + S_RS));         // s = -Gamma r ; S_RS = <r,s>
@@ -324,21 +328,20 @@ static int linear_iteration(fans_ctx *ctx, double *r, double *s, double *u, doub
     else FANS_CHECK(sweep_run(ctx, SWEEP_LINEAR, d_old, rnew, s, d_new, ctx->d_red + S_BETA, ctx->d_red + S_DKD, nullptr, nullptr));
     FANS_CHECK(vec_cg_update(ctx, r, rnew, u, d_new, s));                // r,u update + norms + deltamid
     if (ctx->capturing) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * S_COUNT * ctx->nb, cudaMemcpyDeviceToHost, ctx->st));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fault, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
         return FANS_OK;
     }
     return read_scalars(ctx);
 }
 
-// Captures the iteration for both orientations of the direction ping-pong.  Called after one plain iteration of the same solve, so
-// every lazy initialisation of the launchers (coefficient tables, function attributes) lies behind.  A failed capture only
-// switches the graphs off for this context: the plain launches remain.
-static int iter_graph_build(fans_ctx *ctx, double *r, double *s, double *u, double *rnew)
+// Captures the iteration for both orientations of the direction ping-pong: exec[0] reads dA and writes dB.  Called after one plain
+// iteration of the same solve, so every lazy initialisation of the launchers (coefficient tables, function attributes) lies behind.
+// A failed capture only switches the graphs off for this context: the plain launches remain.
+static int iter_graph_build(fans_ctx *ctx, IterGraph &G, double *r, double *s, double *u, double *rnew, double *dA, double *dB)
 {
-    auto &G = ctx->igraph;
-    iter_graph_free(ctx);
-    G.dA = ctx->field[FANS_FIELD_D], G.dB = ctx->d_alt;
+    iter_graph_free(G);
+    G.dA = dA, G.dB = dB;
     for (int par = 0; par < 2; ++par) {
         const double *d_old = par ? G.dB : G.dA;
         double *d_new = par ? G.dA : G.dB;
@@ -358,14 +361,14 @@ static int iter_graph_build(fans_ctx *ctx, double *r, double *s, double *u, doub
         if (rc != FANS_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec[par], graph, 0) != cudaSuccess) {
             cudaGetLastError();
             if (graph) cudaGraphDestroy(graph);
-            iter_graph_free(ctx);
+            iter_graph_free(G);
             G.failed = true;
             return FANS_OK;
         }
         cudaGraphDestroy(graph);
     }
     iter_graph_key(ctx, r, s, u, rnew, G.key);
-    G.cstamp = ctx->const_stamp, G.sstamp = ctx->stencil_stamp;
+    G.cstamp = ctx->const_stamp, G.sstamp = ctx->stencil_stamp, G.nb = ctx->nb;
     G.valid = true;
     return FANS_OK;
 }
@@ -397,7 +400,7 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
     FANS_CHECK(write_scalar(ctx, S_DELTA, 1.0));
     FANS_CHECK(write_scalar(ctx, S_DELTAMID, 0.0));  // <r, s> with s = 0
     // small grids: iterations after the first replay a CUDA graph (single GPU, stencil form, no per-kernel profiling / printing)
-    const bool graph_ok = linear && use_stencil && ctx->P == 1 && ctx->nb == 1 && !ctx->prof && !p->verbose && !ctx->any_fft && iter_graph_wanted(ctx);
+    const bool graph_ok = linear && use_stencil && ctx->P == 1 && ctx->nb == 1 && !ctx->prof && !p->verbose && !ctx->any_fft && iter_graph_wanted(ctx, 1);
     bool graph_tried = false;
     int graph_iters = 0;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
@@ -406,7 +409,7 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
             // deltamid already sits in S_DELTAMID (left by k_cg_update, 0 at iter 0)
             double *d_old = ctx->field[FANS_FIELD_D], *d_new = ctx->d_alt;
             ctx->n_residual_evals++;
-            if (graph_ok && iter_graph_ready(ctx, r, s, u, rnew)) {   // the whole iteration, read-back included, as one graph launch
+            if (graph_ok && iter_graph_ready(ctx, ctx->igraph, r, s, u, rnew, d_old, d_new)) {   // the whole iteration as one graph launch
                 const auto &G = ctx->igraph;
                 CUDA_TRY(ctx, cudaGraphLaunch(G.exec[d_old == G.dA ? 0 : 1], ctx->st));
                 ctx->launches += G.launches;
@@ -416,9 +419,7 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
                 FANS_CHECK(linear_iteration(ctx, r, s, u, rnew, d_old, d_new, use_stencil));
                 if (graph_ok && !ctx->igraph.failed && !graph_tried) {
                     graph_tried = true;
-                    ctx->field[FANS_FIELD_D] = d_new, ctx->d_alt = d_old;   // the graphs alternate between the buffers as they are NOW
-                    FANS_CHECK(iter_graph_build(ctx, r, s, u, rnew));
-                    ctx->field[FANS_FIELD_D] = d_old, ctx->d_alt = d_new;
+                    FANS_CHECK(iter_graph_build(ctx, ctx->igraph, r, s, u, rnew, d_new, d_old));   // the next iteration reads d_new
                 }
             }
             ctx->field[FANS_FIELD_D] = d_new;
@@ -580,6 +581,7 @@ extern "C" int fans_solve(fans_ctx *ctx, const fans_solve_params *p, fans_solve_
 void batch_arena_free(fans_ctx *ctx)
 {
     auto &A = ctx->arena;
+    iter_graph_free(A.graph);
     for (double *&f : A.field)
         if (f) cudaFree(f), f = nullptr;
     if (A.spec) cudaFree(A.spec), A.spec = nullptr;
@@ -722,15 +724,24 @@ extern "C" int fans_solve_batch(fans_ctx *ctx, int32_t nb, const double *macro, 
         else FANS_CHECK(freeze(l));
     }
     ctx->nb = nb;
+    const bool graph_ok = !ctx->prof && !p->verbose && iter_graph_wanted(ctx, nb);
+    bool graph_tried = false;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
     int sweeps = 0;
     while (n_active > 0) {
-        FANS_CHECK(conv_run(ctx, R, S, -1.0, R, ctx->d_red + S_RS));              // s = -Gamma r, <r, s> per lane
-        FANS_CHECK(vec_scalars_after_conv(ctx));                                   // delta0, delta, beta per lane
-        FANS_CHECK(stencil_run(ctx, D, KD, S, Dalt, ctx->d_red + S_BETA, ctx->d_red + S_DKD));   // d = s + beta d, K d, <d, K d>
+        // d = s + beta d, K d, <d, K d>, r / u update, norms: one pass each over ALL lanes; replayed as a graph on small grids
+        if (graph_ok && iter_graph_ready(ctx, A.graph, R, S, U, KD, D, Dalt)) {
+            CUDA_TRY(ctx, cudaGraphLaunch(A.graph.exec[D == A.graph.dA ? 0 : 1], ctx->st));
+            ctx->launches += A.graph.launches;
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->st));
+        } else {
+            FANS_CHECK(linear_iteration(ctx, R, S, U, KD, D, Dalt, true));
+            if (graph_ok && !A.graph.failed && !graph_tried) {
+                graph_tried = true;
+                FANS_CHECK(iter_graph_build(ctx, A.graph, R, S, U, KD, Dalt, D));
+            }
+        }
         std::swap(D, Dalt);
-        FANS_CHECK(vec_cg_update(ctx, R, KD, U, D, S));                            // r, u, norms, <r, s> per lane
-        FANS_CHECK(read_scalars(ctx));
         sweeps++;
         for (int l = 0; l < nb; ++l) {
             if (!active[l]) continue;
