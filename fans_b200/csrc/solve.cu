@@ -399,8 +399,8 @@ static int solve_cg(fans_ctx *ctx, const fans_solve_params *p, fans_solve_result
     if (p->verbose) printf("it %3d .... err %16.8e\n", es.iter, es.hist ? es.hist[es.iter] : err_rel);
     FANS_CHECK(write_scalar(ctx, S_DELTA, 1.0));
     FANS_CHECK(write_scalar(ctx, S_DELTAMID, 0.0));  // <r, s> with s = 0
-    // small grids: iterations after the first replay a CUDA graph (single GPU, stencil form, no per-kernel profiling / printing)
-    const bool graph_ok = linear && use_stencil && ctx->P == 1 && ctx->nb == 1 && !ctx->prof && !p->verbose && !ctx->any_fft && iter_graph_wanted(ctx, 1);
+    // small grids: iterations after the first replay a CUDA graph (single GPU, stencil form, no per-kernel profiling)
+    const bool graph_ok = linear && use_stencil && ctx->P == 1 && ctx->nb == 1 && !ctx->prof && !ctx->any_fft && iter_graph_wanted(ctx, 1);
     bool graph_tried = false;
     int graph_iters = 0;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
@@ -724,7 +724,7 @@ extern "C" int fans_solve_batch(fans_ctx *ctx, int32_t nb, const double *macro, 
         else FANS_CHECK(freeze(l));
     }
     ctx->nb = nb;
-    const bool graph_ok = !ctx->prof && !p->verbose && iter_graph_wanted(ctx, nb);
+    const bool graph_ok = !ctx->prof && iter_graph_wanted(ctx, nb);
     bool graph_tried = false;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_loop0, ctx->st));
     int sweeps = 0;
