@@ -692,7 +692,8 @@ extern "C" int fans_solve_batch(fans_ctx *ctx, int32_t nb, const double *macro, 
     for (double *f : {U, S, D}) CUDA_TRY(ctx, cudaMemsetAsync(f, 0, sizeof(double) * fN * nb, ctx->st));
     CUDA_TRY(ctx, cudaMemsetAsync(A.red, 0, sizeof(double) * S_COUNT * nb, ctx->st));
 
-    // initial residuals r_l = residual(u = 0; g0 = macro[l]) and their error norms, lane by lane (solverCG.h:76-80)
+    // initial residuals r_l = residual(u = 0; g0 = macro[l]) and their error norms (solverCG.h:76-80): one element sweep and one
+    // reduction per lane, each into the lane's own scalar block, ONE read-back for all of them
     std::vector<ErrState> es(nb);
     std::vector<double> err(nb, 0.0);
     std::vector<char> active(nb, 1);
@@ -701,8 +702,14 @@ extern "C" int fans_solve_batch(fans_ctx *ctx, int32_t nb, const double *macro, 
         for (int i = 0; i < nstr; ++i) ctx->g0[i] = macro[(size_t)l * nstr + i];
         ctx->n_residual_evals++;
         FANS_CHECK(sweep_run(ctx, SWEEP_RESIDUAL, U + l * fN, R + l * fN, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
-        FANS_CHECK(compute_error(ctx, R + l * fN, es[l], &err[l]));   // uses lane 0's generic scalar slots, read back at once
-        FANS_CHECK(check_fault_cached(ctx));
+        FANS_CHECK(vec_reduce4(ctx, R + l * fN, nullptr, ctx->d_red + (size_t)l * S_COUNT + S_GEN));
+    }
+    ctx->nb = nb;   // read_scalars: all lanes' blocks
+    FANS_CHECK(read_scalars(ctx));
+    ctx->nb = 1;
+    FANS_CHECK(check_fault_cached(ctx));
+    for (int l = 0; l < nb; ++l) {
+        err[l] = error_from_scalars(ctx, es[l], l * S_COUNT + S_GEN);
         if (p->verbose) printf("lane %d it %3d .... err %16.8e\n", l, 0, es[l].hist ? es[l].hist[0] : err[l]);
     }
     // delta = 1, deltamid = <r, s> = 0 (s = 0), nothing frozen
@@ -761,12 +768,16 @@ extern "C" int fans_solve_batch(fans_ctx *ctx, int32_t nb, const double *macro, 
     // homogenized stress of every lane (solver.h:707-737), lane by lane through the element sweep
     if (stress_out) {
         const double N = (double)ctx->nx * ctx->ny * ctx->nz;
-        for (int l = 0; l < nb; ++l) {
+        for (int l = 0; l < nb; ++l) {   // every lane's sums into its own scalar block, one read-back
             for (int i = 0; i < nstr; ++i) ctx->g0[i] = macro[(size_t)l * nstr + i];
-            FANS_CHECK(sweep_run(ctx, SWEEP_STRAINSTRESS, U + l * fN, nullptr, nullptr, nullptr, nullptr, ctx->d_red + S_STRESS, nullptr, nullptr));
-            FANS_CHECK(read_scalars(ctx));
-            for (int i = 0; i < nstr; ++i) stress_out[(size_t)l * nstr + i] = ctx->h_red[S_STRESS + i] / N;
+            FANS_CHECK(sweep_run(ctx, SWEEP_STRAINSTRESS, U + l * fN, nullptr, nullptr, nullptr, nullptr, ctx->d_red + (size_t)l * S_COUNT + S_STRESS,
+                                 nullptr, nullptr));
         }
+        ctx->nb = nb;
+        FANS_CHECK(read_scalars(ctx));
+        ctx->nb = 1;
+        for (int l = 0; l < nb; ++l)
+            for (int i = 0; i < nstr; ++i) stress_out[(size_t)l * nstr + i] = ctx->h_red[(size_t)l * S_COUNT + S_STRESS + i] / N;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->st));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
